@@ -1,0 +1,266 @@
+"""``torch_native`` backend: forward + adjoint stencil kernels as a ``torch.autograd.Function``.
+
+Drop-in for /root/reference/src/pystencils_autodiff/backends/_torch_native.py:10-142
+(``create_autograd_function(autodiff_obj, use_cuda, op_name=None)``), with the same marshalling rules
+(SURVEY.md Appendix A-4): positional inputs bind to ``forward_input_fields`` (sorted by name), outputs are a
+tuple in ``forward_output_fields`` order, backward binds ``grad_outputs[i]`` to the i-th ``diff<out>`` field and
+returns the ``diff<in>`` tensors.  Differences, all deliberate:
+
+* the kernels are the NVRTC-specialised sm_100a kernels of this package, launched through the C ABI on
+  **torch's current stream** (the reference launches on the legacy default stream, printer.py:102-106);
+* outputs are ``torch.empty`` — the kernels write every cell including the zero border — instead of
+  ``torch.zeros`` + kernel (reference :64,:108: an extra HBM write pass per output);
+* only the tensors the adjoint kernel actually reads are saved for backward (the reference stashes every
+  kwarg, :84), so linear stencils save nothing;
+* the gradient tuple is aligned with the positional inputs (``None`` for constant fields) — the reference
+  returns one tensor per backward output and breaks with ``constant_fields``;
+* CUDA only: ``use_cuda=False`` raises; there is no CPU path.
+"""
+import hashlib
+from collections import OrderedDict
+
+import numpy as np
+
+from ..emit import emit_generic, emit_march, march_ineligible_reason
+from ..ir import StencilKernelIR
+from .. import runtime
+
+__all__ = ['create_autograd_function', 'compile_kernel', 'CompiledKernel', 'numpy_dtype_to_torch']
+
+
+def numpy_dtype_to_torch(dtype):
+    """dtype name mapping (reference: backends/_pytorch.py:95-97)."""
+    import torch
+    return getattr(torch, np.dtype(dtype).name)
+
+
+class CompiledKernel:
+    """One lowered kernel, callable like the reference's ``call_<kernel>(**tensors, **scalars)`` wrapper
+    (backends/astnodes.py:143-146): fields are passed by name, outputs are written in place."""
+
+    def __init__(self, ir: StencilKernelIR, tuning=None):
+        self.ir = ir
+        self.function_name = ir.function_name
+        self.tuning = tuning
+        self._emitted = {}
+        self._native = {}
+        self._march_reason = march_ineligible_reason(ir)
+        if self._march_reason is None:
+            try:
+                self._emitted['march'] = emit_march(ir, tuning)
+            except ValueError as e:
+                self._march_reason = str(e)
+        self._emitted['generic'] = emit_generic(ir)
+        self.fields = ir.all_fields
+        self.scalars = [s.name for s in ir.scalars]
+        self.last_variant = None
+
+    # -- introspection ---------------------------------------------------------------------------------------
+    @property
+    def code(self):
+        return '\n'.join(self._emitted[k].source for k in sorted(self._emitted))
+
+    @property
+    def variants(self):
+        return sorted(self._emitted)
+
+    def emitted(self, variant):
+        return self._emitted[variant]
+
+    def get_parameters(self):
+        return self.ir.get_parameters()
+
+    def native(self, variant):
+        if variant not in self._native:
+            self._native[variant] = runtime.NativeKernel(self._emitted[variant])
+        return self._native[variant]
+
+    def precompile(self):
+        """NVRTC-compile every variant into the cubin cache (no GPU needed)."""
+        logs = {}
+        for v, ek in self._emitted.items():
+            logs[v] = runtime.compile_source(ek.source, ek.cache_key, list(ek.options) + ['--ptxas-options=-v'])
+        return logs
+
+    # -- launch --------------------------------------------------------------------------------------------------
+    def _select_variant(self, tensors):
+        if 'march' not in self._emitted:
+            return 'generic'
+        for f, t in zip(self.fields, tensors):
+            es = t.element_size()
+            if t.stride(-1) != 1 or t.data_ptr() % 16 or (t.shape[-1] * es) % 16:
+                return 'generic'
+            for d in range(t.dim() - 1):
+                if (t.stride(d) * es) % 16:
+                    return 'generic'
+        return 'march'
+
+    def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
+        import torch
+        tensors = []
+        for f in self.fields:
+            if f.name not in kwargs:
+                raise TypeError('%s: missing field argument %r' % (self.function_name, f.name))
+            t = kwargs[f.name]
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise TypeError('%s: field %r must be a CUDA tensor (this backend has no CPU path)'
+                                % (self.function_name, f.name))
+            if t.dtype != numpy_dtype_to_torch(f.dtype.numpy_dtype):
+                raise TypeError('%s: field %r expects dtype %s, got %s' % (self.function_name, f.name,
+                                                                          f.dtype.numpy_dtype, t.dtype))
+            if t.dim() != f.spatial_dimensions + f.index_dimensions:
+                raise ValueError('%s: field %r expects %d dims, got shape %s'
+                                 % (self.function_name, f.name, f.spatial_dimensions + f.index_dimensions, tuple(t.shape)))
+            tensors.append(t)
+        nd = self.ir.ndim
+        shape0 = tuple(tensors[0].shape[:nd])
+        dev = tensors[0].device
+        for f, t in zip(self.fields, tensors):
+            if tuple(t.shape[:nd]) != shape0:
+                raise ValueError('%s: all fields must share one spatial shape: %r is %s, expected %s'
+                                 % (self.function_name, f.name, tuple(t.shape[:nd]), shape0))
+            if t.device != dev:
+                raise ValueError('%s: all fields must live on the same device' % self.function_name)
+        scal = []
+        for s in self.scalars:
+            if s not in kwargs:
+                raise TypeError('%s: missing scalar argument %r' % (self.function_name, s))
+            scal.append(float(kwargs[s]))
+        variant = _variant or self._select_variant(tensors)
+        field_args = []
+        for f, t in zip(self.fields, tensors):
+            st = list(t.stride()[:nd]) + [0] * (3 - nd)
+            st.append(t.stride(nd) if f.index_dimensions else 0)
+            field_args.append((t.data_ptr(), tuple(t.shape[:nd]), st))
+        with torch.cuda.device(dev):
+            stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
+            self.native(variant).launch(field_args, scal, stream, _range)
+        self.last_variant = variant
+        return None
+
+
+_KERNEL_CACHE = {}
+
+
+def compile_kernel(ir: StencilKernelIR, tuning=None) -> CompiledKernel:
+    key = (id(ir), repr(tuning))
+    if key not in _KERNEL_CACHE:
+        _KERNEL_CACHE[key] = (ir, CompiledKernel(ir, tuning))
+    return _KERNEL_CACHE[key][1]
+
+
+def _hash(data):
+    return hashlib.md5(data)
+
+
+def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=None):
+    import torch
+    if not use_cuda:
+        raise NotImplementedError('pystencils_autodiff_b200 is CUDA-only: use_cuda=False has no implementation')
+
+    forward_ir = autodiff_obj.forward_ast_gpu
+    backward_ir = autodiff_obj.backward_ast_gpu if autodiff_obj.backward_output_fields else None
+    fwd_kernel = CompiledKernel(forward_ir, tuning)
+    bwd_kernel = CompiledKernel(backward_ir, tuning) if backward_ir is not None else None
+
+    if not op_name:
+        digest = _hash((fwd_kernel.code + str(autodiff_obj) + str(autodiff_obj.constant_fields)).encode()).hexdigest()
+        op_name = '%s_%s' % (autodiff_obj.op_name, digest)
+
+    fwd_inputs = list(autodiff_obj.forward_input_fields)
+    fwd_outputs = list(autodiff_obj.forward_output_fields)
+    bwd_inputs = list(autodiff_obj.backward_input_fields)
+    bwd_outputs = list(autodiff_obj.backward_output_fields)
+    fwd_accessed = {f.name for f in forward_ir.fields_accessed}
+    fwd_read = {f.name for f in forward_ir.fields_read}
+    bwd_accessed = {f.name for f in backward_ir.fields_accessed} if backward_ir is not None else set()
+    bwd_read = {f.name for f in backward_ir.fields_read} if backward_ir is not None else set()
+    grad_fields = [f for f in bwd_inputs if f not in fwd_inputs and f not in fwd_outputs and f not in bwd_outputs]
+    # adjoint of forward input i (None for constant fields)
+    prefix_map = {}
+    for f in bwd_outputs:
+        fwd = getattr(f, 'corresponding_forward_field', None)
+        prefix_map[fwd.name if fwd is not None else f.name] = f
+    class_kwargs = dict()
+
+    def _alloc(field, like, device, read_too):
+        shape = tuple(int(s) for s in field.shape) if field.has_fixed_shape else \
+            tuple(like.shape[:field.spatial_dimensions]) + tuple(int(s) for s in field.index_shape)
+        maker = torch.zeros if read_too else torch.empty
+        return maker(shape, dtype=numpy_dtype_to_torch(field.dtype.numpy_dtype), device=device)
+
+    def forward(ctx, *args, **kwargs):
+        kwargs.update(class_kwargs)
+        args = [a.cuda().contiguous() if isinstance(a, torch.Tensor) else a for a in args]
+        kwargs = {k: v.cuda().contiguous() if isinstance(v, torch.Tensor) else v for k, v in kwargs.items()}
+        if len(args) > len(fwd_inputs):
+            raise TypeError('%s takes %d input tensors (%s), got %d'
+                            % (op_name, len(fwd_inputs), [f.name for f in fwd_inputs], len(args)))
+        kwargs.update({f.name: args[i] for i, f in enumerate(fwd_inputs) if f.name in fwd_accessed and i < len(args)})
+        first = next(v for v in list(args) + list(kwargs.values()) if isinstance(v, torch.Tensor))
+        for f in fwd_outputs:
+            if f.name not in kwargs:
+                kwargs[f.name] = _alloc(f, first, first.device, f.name in fwd_read)
+        outputs = OrderedDict((f.name, kwargs[f.name]) for f in fwd_outputs)
+        fwd_kernel(**{k: v for k, v in kwargs.items() if k in fwd_accessed or k in fwd_kernel.scalars})
+        # keep only what the adjoint kernel reads (tensors through save_for_backward, scalars on ctx)
+        saved_names = [n for n in bwd_read if n in kwargs and isinstance(kwargs[n], torch.Tensor)]
+        ctx.saved_names = saved_names
+        ctx.save_for_backward(*[kwargs[n] for n in saved_names])
+        ctx.saved_scalars = {k: v for k, v in kwargs.items() if not isinstance(v, torch.Tensor)}
+        ctx.n_args = len(args)
+        ctx.like = (first.shape, first.device)
+        return tuple(outputs.values())
+
+    def backward(ctx, *grad_outputs):
+        if bwd_kernel is None:
+            return tuple(None for _ in range(ctx.n_args))
+        saved = dict(zip(ctx.saved_names, ctx.saved_tensors))
+        shape, device = ctx.like
+        gradients = {}
+        for i, f in enumerate(grad_fields):
+            g = grad_outputs[i] if i < len(grad_outputs) else None
+            if g is None:
+                g = torch.zeros(tuple(int(s) for s in f.shape) if f.has_fixed_shape else shape,
+                                dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=device)
+            g = g.contiguous()
+            if not g.is_cuda:
+                raise AssertionError('Some of the tensors where on the wrong device. Op was compiled for CUDA: True')
+            if f.has_fixed_shape and tuple(int(s) for s in f.shape) != tuple(g.shape):
+                raise AssertionError('gradient for %s has shape %s, expected %s' % (f.name, tuple(g.shape), f.shape))
+            gradients[f.name] = g
+        like = next(iter(gradients.values())) if gradients else next(iter(saved.values()))
+        outs = OrderedDict((f.name, _alloc(f, like, device, f.name in bwd_read)) for f in bwd_outputs)
+        kw = {**gradients, **saved, **outs}
+        kw = {k: v for k, v in kw.items() if k in bwd_accessed}
+        kw.update({k: v for k, v in ctx.saved_scalars.items() if k in bwd_kernel.scalars})
+        bwd_kernel(**kw)
+        result = []
+        for i in range(ctx.n_args):
+            adj = prefix_map.get(fwd_inputs[i].name)
+            result.append(outs[adj.name] if adj is not None and adj.name in outs else None)
+        return tuple(result)
+
+    def call(cls, **kwargs):
+        rtn = cls.apply(*[kwargs[p.symbol.name] for p in cls.forward_parameters])
+        if len(rtn) == 1:
+            rtn = rtn[0]
+        return rtn
+
+    cls = type(op_name, (torch.autograd.Function,), {
+        'forward': staticmethod(forward),
+        'backward': staticmethod(backward),
+    })
+    cls.class_kwargs = class_kwargs
+    cls.kernel = staticmethod(forward)
+    cls.ast = (fwd_kernel, bwd_kernel)
+    cls.parameters = forward_ir.get_parameters()
+    cls.forward_parameters = [p for p in cls.parameters if p.symbol.name in [f.name for f in fwd_inputs]]
+    cls.forward_ast = forward_ir
+    cls.backward_ast = backward_ir
+    cls.forward_kernel = fwd_kernel
+    cls.backward_kernel = bwd_kernel
+    cls.num_regs = None
+    cls.call = classmethod(call)
+    cls.code = fwd_kernel.code + ('\n' + bwd_kernel.code if bwd_kernel is not None else '')
+    return cls

@@ -1,0 +1,27 @@
+// psad_args.h — kernel parameter block shared by the host runtime (psad_runtime.cpp) and the NVRTC-compiled
+// kernels.  Plain C types only: this header is compiled by g++ and by NVRTC (no system includes there).
+//
+// All kernels see fields as 3-D (z, y, x) with x the contiguous axis; 1-D / 2-D fields get leading extents of 1.
+#ifndef PSAD_ARGS_H
+#define PSAD_ARGS_H
+
+#define PSAD_MAX_FIELDS 12
+#define PSAD_MAX_SCALARS 16
+
+struct PsadArgs {
+  void* ptr[PSAD_MAX_FIELDS];              // field base pointers, plan order (outputs first, then inputs)
+  long long stride[PSAD_MAX_FIELDS][4];    // element strides (z, y, x, index)
+  long long shape[3];                      // (Z, Y, X)
+  long long it_lo[3], it_hi[3];            // cells evaluated with the stencil expression
+  long long wr_lo[3], wr_hi[3];            // cells written (0 outside the iteration range)
+  double scalar[PSAD_MAX_SCALARS];         // free scalar symbols, sorted by name
+  long long n_items;                       // march: number of work items
+  int tiles_x, tiles_y, n_chunks, chunk;   // march: work decomposition
+};
+
+// 128-byte opaque CUtensorMap image (cuTensorMapEncodeTiled output), 64-byte aligned as the driver requires.
+struct __attribute__((aligned(64))) PsadTensorMap {
+  unsigned long long opaque[16];
+};
+
+#endif

@@ -1,0 +1,85 @@
+// psad_common.cuh — hand-written sm_100a device primitives used by every specialised stencil kernel:
+// mbarrier handshakes, TMA (cp.async.bulk.tensor) tile loads, vector shared/global accessors, warp halo shuffles.
+#ifndef PSAD_COMMON_CUH
+#define PSAD_COMMON_CUH
+
+#include "psad_args.h"
+
+typedef unsigned int psad_u32;
+typedef unsigned long long psad_u64;
+
+#define PSAD_DEV __device__ __forceinline__
+
+PSAD_DEV psad_u32 psad_smem_u32(const void* p) { return (psad_u32)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------------------
+PSAD_DEV void psad_mbar_init(psad_u64* bar, psad_u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(psad_smem_u32(bar)), "r"(count) : "memory");
+}
+PSAD_DEV void psad_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PSAD_DEV void psad_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PSAD_DEV void psad_mbar_arrive_expect_tx(psad_u64* bar, psad_u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(psad_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+PSAD_DEV void psad_mbar_wait(psad_u64* bar, psad_u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "PSAD_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra PSAD_DONE;\n"
+      "bra PSAD_WAIT;\n"
+      "PSAD_DONE:\n"
+      "}\n" ::"r"(psad_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- TMA tile loads (global -> shared, completion on an mbarrier; out-of-bounds elements are zero-filled) ---
+PSAD_DEV void psad_tma_load_2d(void* smem_dst, const PsadTensorMap* tmap, psad_u64* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(psad_smem_u32(smem_dst)), "l"((psad_u64)tmap), "r"(psad_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+PSAD_DEV void psad_tma_load_3d(void* smem_dst, const PsadTensorMap* tmap, psad_u64* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(psad_smem_u32(smem_dst)), "l"((psad_u64)tmap), "r"(psad_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+PSAD_DEV void psad_tma_prefetch_desc(const PsadTensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((psad_u64)tmap) : "memory");
+}
+
+// ---- 16-byte vectors of the field element type -----------------------------------------------------------------
+template <typename T> struct PsadVec;
+template <> struct PsadVec<float> {
+  typedef float4 type;
+  static constexpr int N = 4;
+  PSAD_DEV static void unpack(const float4& v, float* e) { e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; }
+  PSAD_DEV static float4 pack(const float* e) { return make_float4(e[0], e[1], e[2], e[3]); }
+};
+template <> struct PsadVec<double> {
+  typedef double2 type;
+  static constexpr int N = 2;
+  PSAD_DEV static void unpack(const double2& v, double* e) { e[0] = v.x; e[1] = v.y; }
+  PSAD_DEV static double2 pack(const double* e) { return make_double2(e[0], e[1]); }
+};
+
+// shared -> registers, one aligned 16-byte vector (LDS.128)
+template <typename T> PSAD_DEV void psad_lds_vec(const T* p, T* e) {
+  typename PsadVec<T>::type v = *reinterpret_cast<const typename PsadVec<T>::type*>(p);
+  PsadVec<T>::unpack(v, e);
+}
+// registers -> global, one aligned 16-byte streaming store (STG.128, evict-first: outputs are not re-read)
+template <typename T> PSAD_DEV void psad_stg_vec(T* p, const T* e) {
+  __stcs(reinterpret_cast<typename PsadVec<T>::type*>(p), PsadVec<T>::pack(e));
+}
+
+// ---- warp halo exchange: element of the lane to the left / right -----------------------------------------------
+template <typename T> PSAD_DEV T psad_from_left(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+template <typename T> PSAD_DEV T psad_from_right(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+#endif

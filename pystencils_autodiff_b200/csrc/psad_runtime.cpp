@@ -1,0 +1,562 @@
+// psad_runtime.cpp — host runtime behind include/psad.h.
+//
+// Replaces, for the torch_native path of the reference, the generated C++ wrapper + pybind11 module + nvcc JIT
+// (/root/reference/src/pystencils_autodiff/backends/astnodes.py:95-186, framework_integration/printer.py:88-145):
+// specialised CUDA source -> NVRTC -> sm_100a cubin (content-addressed on-disk cache, like the reference's md5
+// keyed object cache, backends/astnodes.py:157-166) -> cuModuleLoadData -> cuLaunchKernel on the caller's stream
+// with tensor maps encoded per launch.  libcuda / libnvrtc / libnccl are dlopen'ed lazily so that the library
+// loads (and compiles cubins) on a machine without a GPU.
+#include "../../include/psad.h"
+
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels/psad_args.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// error handling
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+extern "C" const char* psad_last_error(void) { return g_err.c_str(); }
+extern "C" int psad_abi_version(void) { return PSAD_ABI_VERSION; }
+extern "C" void psad_free(void* p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// minimal driver-API / NVRTC / NCCL declarations (resolved with dlsym; no CUDA headers needed to build)
+typedef int CUresult;
+typedef int CUdevice;
+typedef struct CUctx_st* CUcontext;
+typedef struct CUmod_st* CUmodule;
+typedef struct CUfunc_st* CUfunction;
+typedef struct CUstream_st* CUstream;
+typedef unsigned long long CUdeviceptr;
+struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
+
+enum { CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT = 16, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR = 75,
+       CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR = 76, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN = 97 };
+enum { CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES = 1, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES = 3, CU_FUNC_ATTRIBUTE_NUM_REGS = 4,
+       CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8 };
+enum { CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7, CU_TENSOR_MAP_DATA_TYPE_FLOAT64 = 8 };
+
+struct Driver {
+  void* lib = nullptr;
+  CUresult (*cuInit)(unsigned);
+  CUresult (*cuDeviceGet)(CUdevice*, int);
+  CUresult (*cuDeviceGetAttribute)(int*, int, CUdevice);
+  CUresult (*cuCtxGetCurrent)(CUcontext*);
+  CUresult (*cuCtxSetCurrent)(CUcontext);
+  CUresult (*cuCtxGetDevice)(CUdevice*);
+  CUresult (*cuDevicePrimaryCtxRetain)(CUcontext*, CUdevice);
+  CUresult (*cuModuleLoadData)(CUmodule*, const void*);
+  CUresult (*cuModuleUnload)(CUmodule);
+  CUresult (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*);
+  CUresult (*cuFuncSetAttribute)(CUfunction, int, int);
+  CUresult (*cuFuncGetAttribute)(int*, int, CUfunction);
+  CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+  CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void**, void**);
+  CUresult (*cuGetErrorString)(CUresult, const char**);
+  CUresult (*cuTensorMapEncodeTiled)(CUtensorMap*, int, unsigned, void*, const unsigned long long*,
+                                     const unsigned long long*, const unsigned*, const unsigned*, int, int, int, int);
+};
+static Driver g_drv;
+static std::once_flag g_drv_once;
+static std::string g_drv_err;
+
+template <typename T> static bool sym(void* lib, const char* name, T& fn, std::string& err) {
+  fn = reinterpret_cast<T>(dlsym(lib, name));
+  if (!fn) { err = std::string("missing symbol ") + name; return false; }
+  return true;
+}
+
+static void load_driver() {
+  void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { g_drv_err = std::string("cannot load libcuda.so.1 (no NVIDIA driver on this machine): ") + dlerror(); return; }
+  Driver d; d.lib = lib; std::string e;
+  bool ok = sym(lib, "cuInit", d.cuInit, e) && sym(lib, "cuDeviceGet", d.cuDeviceGet, e) &&
+            sym(lib, "cuDeviceGetAttribute", d.cuDeviceGetAttribute, e) && sym(lib, "cuCtxGetCurrent", d.cuCtxGetCurrent, e) &&
+            sym(lib, "cuCtxSetCurrent", d.cuCtxSetCurrent, e) && sym(lib, "cuCtxGetDevice", d.cuCtxGetDevice, e) &&
+            sym(lib, "cuDevicePrimaryCtxRetain", d.cuDevicePrimaryCtxRetain, e) &&
+            sym(lib, "cuModuleLoadData", d.cuModuleLoadData, e) && sym(lib, "cuModuleUnload", d.cuModuleUnload, e) &&
+            sym(lib, "cuModuleGetFunction", d.cuModuleGetFunction, e) && sym(lib, "cuFuncSetAttribute", d.cuFuncSetAttribute, e) &&
+            sym(lib, "cuFuncGetAttribute", d.cuFuncGetAttribute, e) &&
+            sym(lib, "cuOccupancyMaxActiveBlocksPerMultiprocessor", d.cuOccupancyMaxActiveBlocksPerMultiprocessor, e) &&
+            sym(lib, "cuLaunchKernel", d.cuLaunchKernel, e) && sym(lib, "cuGetErrorString", d.cuGetErrorString, e) &&
+            sym(lib, "cuTensorMapEncodeTiled", d.cuTensorMapEncodeTiled, e);
+  if (!ok) { g_drv_err = e; return; }
+  CUresult r = d.cuInit(0);
+  if (r != 0) { g_drv_err = "cuInit failed with code " + std::to_string(r); return; }
+  g_drv = d;
+}
+
+static int need_driver() {
+  std::call_once(g_drv_once, load_driver);
+  if (!g_drv.lib) return fail(PSAD_ERR_NO_DRIVER, "%s", g_drv_err.c_str());
+  return 0;
+}
+
+static int cu_fail(CUresult r, const char* what) {
+  const char* s = nullptr;
+  if (g_drv.cuGetErrorString) g_drv.cuGetErrorString(r, &s);
+  return fail(PSAD_ERR_CUDA, "%s failed: %s (CUresult %d)", what, s ? s : "?", r);
+}
+#define CU_CHECK(call) do { CUresult _r = (call); if (_r != 0) return cu_fail(_r, #call); } while (0)
+
+// make sure the calling thread has a current context (torch's primary context when called from PyTorch)
+static int ensure_context() {
+  CUcontext ctx = nullptr;
+  CU_CHECK(g_drv.cuCtxGetCurrent(&ctx));
+  if (ctx) return 0;
+  CUdevice dev;
+  CU_CHECK(g_drv.cuDeviceGet(&dev, 0));
+  CU_CHECK(g_drv.cuDevicePrimaryCtxRetain(&ctx, dev));
+  CU_CHECK(g_drv.cuCtxSetCurrent(ctx));
+  return 0;
+}
+
+// NVRTC
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+  void* lib = nullptr;
+  int (*nvrtcCreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  int (*nvrtcDestroyProgram)(nvrtcProgram*);
+  int (*nvrtcCompileProgram)(nvrtcProgram, int, const char* const*);
+  int (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t*);
+  int (*nvrtcGetProgramLog)(nvrtcProgram, char*);
+  int (*nvrtcGetCUBINSize)(nvrtcProgram, size_t*);
+  int (*nvrtcGetCUBIN)(nvrtcProgram, char*);
+  const char* (*nvrtcGetErrorString)(int);
+  int (*nvrtcVersion)(int*, int*);
+};
+static Nvrtc g_rtc;
+static std::once_flag g_rtc_once;
+static std::string g_rtc_err;
+
+static void load_nvrtc() {
+  const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+  void* lib = nullptr;
+  for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
+  if (!lib) { g_rtc_err = std::string("cannot load libnvrtc: ") + dlerror(); return; }
+  Nvrtc n; n.lib = lib; std::string e;
+  bool ok = sym(lib, "nvrtcCreateProgram", n.nvrtcCreateProgram, e) && sym(lib, "nvrtcDestroyProgram", n.nvrtcDestroyProgram, e) &&
+            sym(lib, "nvrtcCompileProgram", n.nvrtcCompileProgram, e) && sym(lib, "nvrtcGetProgramLogSize", n.nvrtcGetProgramLogSize, e) &&
+            sym(lib, "nvrtcGetProgramLog", n.nvrtcGetProgramLog, e) && sym(lib, "nvrtcGetCUBINSize", n.nvrtcGetCUBINSize, e) &&
+            sym(lib, "nvrtcGetCUBIN", n.nvrtcGetCUBIN, e) && sym(lib, "nvrtcGetErrorString", n.nvrtcGetErrorString, e) &&
+            sym(lib, "nvrtcVersion", n.nvrtcVersion, e);
+  if (!ok) { g_rtc_err = e; return; }
+  g_rtc = n;
+}
+
+static int need_nvrtc() {
+  std::call_once(g_rtc_once, load_nvrtc);
+  if (!g_rtc.lib) return fail(PSAD_ERR_NO_DRIVER, "%s", g_rtc_err.c_str());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// configuration
+static std::mutex g_cfg_mutex;
+static std::string g_include_dir, g_cache_dir;
+static std::atomic<uint64_t> g_launches{0};
+
+static void mkdir_p(const std::string& path) {
+  std::string cur;
+  for (size_t i = 0; i < path.size(); ++i) {
+    cur += path[i];
+    if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0755);
+  }
+}
+
+extern "C" int psad_init(const char* kernel_include_dir, const char* cache_dir) {
+  if (!kernel_include_dir || !cache_dir) return fail(PSAD_ERR_INVALID, "psad_init: null argument");
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  g_include_dir = kernel_include_dir;
+  g_cache_dir = cache_dir;
+  mkdir_p(g_cache_dir);
+  struct stat st;
+  if (stat((g_include_dir + "/psad_common.cuh").c_str(), &st) != 0)
+    return fail(PSAD_ERR_IO, "psad_init: %s/psad_common.cuh not found", kernel_include_dir);
+  return 0;
+}
+
+extern "C" uint64_t psad_launch_count(void) { return g_launches.load(); }
+
+extern "C" int psad_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
+  if (int rc = need_driver()) return rc;
+  if (int rc = ensure_context()) return rc;
+  CUdevice dev;
+  CU_CHECK(g_drv.cuCtxGetDevice(&dev));
+  int v;
+  if (device) *device = dev;
+  if (sm_count) { CU_CHECK(g_drv.cuDeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev)); *sm_count = v; }
+  if (cc_major) { CU_CHECK(g_drv.cuDeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, dev)); *cc_major = v; }
+  if (cc_minor) { CU_CHECK(g_drv.cuDeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, dev)); *cc_minor = v; }
+  if (smem_optin) { CU_CHECK(g_drv.cuDeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN, dev)); *smem_optin = (size_t)v; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// compilation + cubin cache
+static bool read_file(const std::string& path, std::vector<char>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize((size_t)n);
+  size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  return got == (size_t)n;
+}
+
+static int compile_to_cache(const char* source, const char* cache_key, const char* const* options, int n_options,
+                            int* cache_hit, char** log_out, std::string* cubin_path_out) {
+  if (!source || !cache_key) return fail(PSAD_ERR_INVALID, "psad_compile: null argument");
+  std::string inc, cache;
+  {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    inc = g_include_dir;
+    cache = g_cache_dir;
+  }
+  if (inc.empty()) return fail(PSAD_ERR_INVALID, "psad_init() has not been called");
+  const std::string path = cache + "/" + cache_key + ".cubin";
+  if (cubin_path_out) *cubin_path_out = path;
+  if (log_out) *log_out = nullptr;
+  struct stat st;
+  if (stat(path.c_str(), &st) == 0 && st.st_size > 0) {
+    if (cache_hit) *cache_hit = 1;
+    return 0;
+  }
+  if (cache_hit) *cache_hit = 0;
+  if (int rc = need_nvrtc()) return rc;
+
+  nvrtcProgram prog;
+  std::string name = std::string(cache_key) + ".cu";
+  int r = g_rtc.nvrtcCreateProgram(&prog, source, name.c_str(), 0, nullptr, nullptr);
+  if (r != 0) return fail(PSAD_ERR_NVRTC, "nvrtcCreateProgram: %s", g_rtc.nvrtcGetErrorString(r));
+  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-I" + inc};
+  for (int i = 0; i < n_options; ++i) opts.push_back(options[i]);
+  std::vector<const char*> copts;
+  for (auto& o : opts) copts.push_back(o.c_str());
+  r = g_rtc.nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+  size_t log_size = 0;
+  g_rtc.nvrtcGetProgramLogSize(prog, &log_size);
+  std::string log(log_size, '\0');
+  if (log_size > 1) g_rtc.nvrtcGetProgramLog(prog, &log[0]);
+  if (log_out && log_size > 1) *log_out = strdup(log.c_str());
+  if (r != 0) {
+    g_rtc.nvrtcDestroyProgram(&prog);
+    return fail(PSAD_ERR_NVRTC, "NVRTC compilation of %s failed: %s\n%s", name.c_str(), g_rtc.nvrtcGetErrorString(r), log.c_str());
+  }
+  size_t n = 0;
+  r = g_rtc.nvrtcGetCUBINSize(prog, &n);
+  if (r != 0 || n == 0) { g_rtc.nvrtcDestroyProgram(&prog); return fail(PSAD_ERR_NVRTC, "nvrtcGetCUBINSize failed"); }
+  std::vector<char> cubin(n);
+  r = g_rtc.nvrtcGetCUBIN(prog, cubin.data());
+  g_rtc.nvrtcDestroyProgram(&prog);
+  if (r != 0) return fail(PSAD_ERR_NVRTC, "nvrtcGetCUBIN failed");
+
+  mkdir_p(cache);
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(PSAD_ERR_IO, "cannot write %s", tmp.c_str());
+  fwrite(cubin.data(), 1, n, f);
+  fclose(f);
+  if (rename(tmp.c_str(), path.c_str()) != 0) return fail(PSAD_ERR_IO, "cannot rename %s", tmp.c_str());
+  // keep the specialised source beside the cubin (the reference keeps its generated .cu too)
+  FILE* s = fopen((cache + "/" + cache_key + ".cu").c_str(), "w");
+  if (s) { fputs(source, s); fclose(s); }
+  return 0;
+}
+
+extern "C" int psad_compile(const char* source, const char* cache_key, const char* const* options, int n_options,
+                            int* cache_hit, char** log) {
+  return compile_to_cache(source, cache_key, options, n_options, cache_hit, log, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel objects
+struct psad_kernel {
+  psad_plan_t plan;
+  CUmodule module = nullptr;
+  CUfunction fn = nullptr;
+  int sm_count = 0;
+  std::string name;
+};
+
+extern "C" int psad_kernel_create(const char* source, const char* kernel_name, const char* cache_key,
+                                  const char* const* options, int n_options, const psad_plan_t* plan,
+                                  psad_kernel_t* out) {
+  if (!kernel_name || !plan || !out) return fail(PSAD_ERR_INVALID, "psad_kernel_create: null argument");
+  if (plan->abi_version != PSAD_ABI_VERSION) return fail(PSAD_ERR_INVALID, "plan ABI version %d != %d", plan->abi_version, PSAD_ABI_VERSION);
+  if (plan->n_fields < 1 || plan->n_fields > PSAD_MAX_FIELDS || plan->n_scalars < 0 || plan->n_scalars > PSAD_MAX_SCALARS ||
+      plan->ndim < 1 || plan->ndim > 3 || plan->threads < 32 || plan->threads > 1024)
+    return fail(PSAD_ERR_INVALID, "psad_kernel_create: plan out of range");
+  std::string path;
+  if (int rc = compile_to_cache(source, cache_key, options, n_options, nullptr, nullptr, &path)) return rc;
+  if (int rc = need_driver()) return rc;
+  if (int rc = ensure_context()) return rc;
+  std::vector<char> cubin;
+  if (!read_file(path, cubin)) return fail(PSAD_ERR_IO, "cannot read %s", path.c_str());
+  psad_kernel* k = new psad_kernel();
+  k->plan = *plan;
+  k->name = kernel_name;
+  CUresult r = g_drv.cuModuleLoadData(&k->module, cubin.data());
+  if (r != 0) { delete k; return cu_fail(r, "cuModuleLoadData"); }
+  r = g_drv.cuModuleGetFunction(&k->fn, k->module, kernel_name);
+  if (r != 0) { g_drv.cuModuleUnload(k->module); delete k; return cu_fail(r, "cuModuleGetFunction"); }
+  if (plan->smem_bytes > 48 * 1024) {
+    r = g_drv.cuFuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, plan->smem_bytes);
+    if (r != 0) { g_drv.cuModuleUnload(k->module); delete k; return cu_fail(r, "cuFuncSetAttribute(max dynamic smem)"); }
+  }
+  CUdevice dev;
+  g_drv.cuCtxGetDevice(&dev);
+  g_drv.cuDeviceGetAttribute(&k->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
+  *out = k;
+  return 0;
+}
+
+extern "C" int psad_kernel_destroy(psad_kernel_t k) {
+  if (!k) return 0;
+  if (k->module && g_drv.lib) g_drv.cuModuleUnload(k->module);
+  delete k;
+  return 0;
+}
+
+extern "C" int psad_kernel_attributes(psad_kernel_t k, int* num_regs, int* static_smem, int* local_bytes,
+                                      int* max_ctas_per_sm) {
+  if (!k) return fail(PSAD_ERR_INVALID, "null kernel");
+  if (num_regs) CU_CHECK(g_drv.cuFuncGetAttribute(num_regs, CU_FUNC_ATTRIBUTE_NUM_REGS, k->fn));
+  if (static_smem) CU_CHECK(g_drv.cuFuncGetAttribute(static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, k->fn));
+  if (local_bytes) CU_CHECK(g_drv.cuFuncGetAttribute(local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, k->fn));
+  if (max_ctas_per_sm)
+    CU_CHECK(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas_per_sm, k->fn, k->plan.threads, (size_t)k->plan.smem_bytes));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields,
+                                  const double* scalars, int n_scalars, const psad_range_t* range, void* stream) {
+  if (!k || !fields) return fail(PSAD_ERR_INVALID, "psad_kernel_launch: null argument");
+  const psad_plan_t& P = k->plan;
+  if (n_fields != P.n_fields) return fail(PSAD_ERR_INVALID, "%s: expected %d fields, got %d", k->name.c_str(), P.n_fields, n_fields);
+  if (n_scalars != P.n_scalars) return fail(PSAD_ERR_INVALID, "%s: expected %d scalars, got %d", k->name.c_str(), P.n_scalars, n_scalars);
+  if (n_scalars > 0 && !scalars) return fail(PSAD_ERR_INVALID, "null scalars");
+  if (int rc = ensure_context()) return rc;
+
+  const int nd = P.ndim;
+  PsadArgs A;
+  memset(&A, 0, sizeof(A));
+  // normalise to (z, y, x): leading dims of extent 1
+  for (int d = 0; d < 3; ++d) A.shape[d] = 1;
+  for (int d = 0; d < nd; ++d) A.shape[3 - nd + d] = fields[0].shape[d];
+  for (int f = 0; f < n_fields; ++f) {
+    if (!fields[f].ptr) return fail(PSAD_ERR_INVALID, "%s: field %d has a null pointer", k->name.c_str(), f);
+    for (int d = 0; d < nd; ++d) {
+      if (fields[f].shape[d] != fields[0].shape[d])
+        return fail(PSAD_ERR_INVALID, "%s: all fields of a kernel must share one spatial shape (field %d, dim %d: %lld vs %lld)",
+                    k->name.c_str(), f, d, (long long)fields[f].shape[d], (long long)fields[0].shape[d]);
+      A.stride[f][3 - nd + d] = fields[f].stride[d];
+    }
+    A.stride[f][3] = fields[f].stride[3];
+    A.ptr[f] = fields[f].ptr;
+  }
+  for (int i = 0; i < n_scalars; ++i) A.scalar[i] = scalars[i];
+  for (int d = 0; d < 3; ++d) { A.it_lo[d] = 0; A.it_hi[d] = A.shape[d]; A.wr_lo[d] = 0; A.wr_hi[d] = A.shape[d]; }
+  if (range) {
+    for (int d = 0; d < nd; ++d) {
+      const int e = 3 - nd + d;
+      A.it_lo[e] = range->iter_lo[d]; A.it_hi[e] = range->iter_hi[d];
+      A.wr_lo[e] = range->write_lo[d]; A.wr_hi[e] = range->write_hi[d];
+      if (A.wr_lo[e] < 0 || A.wr_hi[e] > A.shape[e] || A.it_lo[e] < A.wr_lo[e] - 64 || A.it_hi[e] > A.wr_hi[e] + 64)
+        return fail(PSAD_ERR_INVALID, "%s: range out of bounds in dim %d", k->name.c_str(), d);
+    }
+  } else if (P.boundary == 0 && P.ghost_layers > 0) {
+    for (int d = 0; d < nd; ++d) {
+      const int e = 3 - nd + d;
+      A.it_lo[e] = P.ghost_layers;
+      A.it_hi[e] = A.shape[e] - P.ghost_layers;
+    }
+  }
+  for (int d = 0; d < 3; ++d) {
+    if (A.it_hi[d] < A.it_lo[d]) A.it_hi[d] = A.it_lo[d];
+    if (A.wr_hi[d] <= A.wr_lo[d]) return 0;  // nothing to write
+  }
+
+  unsigned grid = 1;
+  void* params[2];
+  int n_params = 1;
+  params[0] = &A;
+  // tensor maps live here for the duration of cuLaunchKernel (parameters are copied at launch)
+  struct alignas(64) { CUtensorMap m[PSAD_MAX_FIELDS]; } TM;
+
+  if (P.kind == PSAD_KIND_GENERIC) {
+    long long cells = 1;
+    for (int d = 0; d < 3; ++d) cells *= (A.wr_hi[d] - A.wr_lo[d]);
+    long long blocks = cdiv(cells, P.threads);
+    long long cap = (long long)k->sm_count * (P.ctas_per_sm > 0 ? P.ctas_per_sm : 8);
+    grid = (unsigned)(blocks < cap ? blocks : cap);
+  } else if (P.kind == PSAD_KIND_MARCH) {
+    if (nd < 2) return fail(PSAD_ERR_INVALID, "march kernels need 2 or 3 spatial dims");
+    if (A.wr_lo[2] != 0 || A.wr_hi[2] != A.shape[2] || A.wr_lo[1] < 0)
+      return fail(PSAD_ERR_INVALID, "march kernels write full rows: the x range must be the whole axis");
+    A.tiles_x = (int)cdiv(A.shape[2], P.tile_x);
+    A.tiles_y = (int)cdiv(A.shape[1], P.tile_y);
+    long long span = (nd == 3) ? (A.wr_hi[0] - A.wr_lo[0]) : A.tiles_y;
+    // balance: pick the number of chunks so that the static round-robin fills the persistent grid evenly
+    long long chunk = P.chunk > 0 ? P.chunk : span;
+    if (chunk > span) chunk = span;
+    long long n_chunks = cdiv(span, chunk);
+    chunk = cdiv(span, n_chunks);
+    n_chunks = cdiv(span, chunk);
+    A.chunk = (int)chunk;
+    A.n_chunks = (int)n_chunks;
+    A.n_items = (long long)A.tiles_x * (nd == 3 ? A.tiles_y : 1) * n_chunks;
+    long long cap = (long long)k->sm_count * (P.ctas_per_sm > 0 ? P.ctas_per_sm : 1);
+    grid = (unsigned)(A.n_items < cap ? A.n_items : cap);
+    int n_tma = 0;
+    for (int f = 0; f < n_fields; ++f) {
+      const psad_field_plan_t& fp = P.field[f];
+      if (A.stride[f][2] != 1) return fail(PSAD_ERR_INVALID, "%s: field %d is not contiguous along x", k->name.c_str(), f);
+      if (((uintptr_t)A.ptr[f]) % 16 != 0) return fail(PSAD_ERR_INVALID, "%s: field %d pointer is not 16-byte aligned", k->name.c_str(), f);
+      if ((A.stride[f][1] * fp.elem_size) % 16 != 0 || (nd == 3 && (A.stride[f][0] * fp.elem_size) % 16 != 0))
+        return fail(PSAD_ERR_INVALID, "%s: field %d row/plane pitch is not a multiple of 16 bytes", k->name.c_str(), f);
+      if (!fp.tma) continue;
+      if (fp.elem_size != 4 && fp.elem_size != 8) return fail(PSAD_ERR_INVALID, "TMA fields must be float32/float64");
+      unsigned long long gdim[3] = {(unsigned long long)A.shape[2], (unsigned long long)A.shape[1], (unsigned long long)A.shape[0]};
+      unsigned long long gstr[2] = {(unsigned long long)A.stride[f][1] * fp.elem_size, (unsigned long long)A.stride[f][0] * fp.elem_size};
+      unsigned box[3] = {(unsigned)fp.box[0], (unsigned)fp.box[1], (unsigned)(nd == 3 ? fp.box[2] : 1)};
+      unsigned estr[3] = {1, 1, 1};
+      for (int d = 0; d < nd; ++d)
+        if (box[d] < 1 || box[d] > 256) return fail(PSAD_ERR_INVALID, "TMA box dim %d = %u out of range", d, box[d]);
+      CUresult r = g_drv.cuTensorMapEncodeTiled(&TM.m[n_tma], fp.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                                (unsigned)nd, A.ptr[f], gdim, gstr, box, estr,
+                                                /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion 256B*/ 3, /*oob fill: zeros*/ 0);
+      if (r != 0) return cu_fail(r, "cuTensorMapEncodeTiled");
+      ++n_tma;
+    }
+    params[1] = &TM;
+    n_params = 2;
+  } else {
+    return fail(PSAD_ERR_INVALID, "unknown kernel kind %d", P.kind);
+  }
+  (void)n_params;
+  if (grid == 0) return 0;
+  CUresult r = g_drv.cuLaunchKernel(k->fn, grid, 1, 1, (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
+  if (r != 0) return cu_fail(r, "cuLaunchKernel");
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL ghost-layer exchange
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct Nccl {
+  void* lib = nullptr;
+  int (*ncclGetUniqueId)(NcclUniqueId*);
+  int (*ncclCommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
+  int (*ncclCommDestroy)(ncclComm_t);
+  int (*ncclGroupStart)();
+  int (*ncclGroupEnd)();
+  int (*ncclSend)(const void*, size_t, int, int, ncclComm_t, CUstream);
+  int (*ncclRecv)(void*, size_t, int, int, ncclComm_t, CUstream);
+  const char* (*ncclGetErrorString)(int);
+};
+static Nccl g_nccl;
+static std::once_flag g_nccl_once;
+static std::string g_nccl_err;
+
+static void load_nccl() {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) { g_nccl_err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+  Nccl n; n.lib = lib; std::string e;
+  bool ok = sym(lib, "ncclGetUniqueId", n.ncclGetUniqueId, e) && sym(lib, "ncclCommInitRank", n.ncclCommInitRank, e) &&
+            sym(lib, "ncclCommDestroy", n.ncclCommDestroy, e) && sym(lib, "ncclGroupStart", n.ncclGroupStart, e) &&
+            sym(lib, "ncclGroupEnd", n.ncclGroupEnd, e) && sym(lib, "ncclSend", n.ncclSend, e) && sym(lib, "ncclRecv", n.ncclRecv, e) &&
+            sym(lib, "ncclGetErrorString", n.ncclGetErrorString, e);
+  if (!ok) { g_nccl_err = e; return; }
+  g_nccl = n;
+}
+static int need_nccl() {
+  std::call_once(g_nccl_once, load_nccl);
+  if (!g_nccl.lib) return fail(PSAD_ERR_NO_DRIVER, "%s", g_nccl_err.c_str());
+  return 0;
+}
+#define NCCL_CHECK(call) do { int _r = (call); if (_r != 0) return fail(PSAD_ERR_NCCL, "%s failed: %s", #call, g_nccl.ncclGetErrorString(_r)); } while (0)
+
+extern "C" int psad_nccl_unique_id(void* unique_id_128) {
+  if (!unique_id_128) return fail(PSAD_ERR_INVALID, "null id");
+  if (int rc = need_nccl()) return rc;
+  NcclUniqueId id;
+  NCCL_CHECK(g_nccl.ncclGetUniqueId(&id));
+  memcpy(unique_id_128, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int psad_nccl_comm_create(const void* unique_id_128, int rank, int world_size, void** comm) {
+  if (!unique_id_128 || !comm) return fail(PSAD_ERR_INVALID, "null argument");
+  if (int rc = need_nccl()) return rc;
+  NcclUniqueId id;
+  memcpy(&id, unique_id_128, sizeof(id));
+  ncclComm_t c;
+  NCCL_CHECK(g_nccl.ncclCommInitRank(&c, world_size, id, rank));
+  *comm = c;
+  return 0;
+}
+
+extern "C" int psad_nccl_comm_destroy(void* comm) {
+  if (!comm) return 0;
+  if (int rc = need_nccl()) return rc;
+  NCCL_CHECK(g_nccl.ncclCommDestroy((ncclComm_t)comm));
+  return 0;
+}
+
+extern "C" int psad_halo_exchange(void* comm, const void* lo_send, void* lo_recv, const void* hi_send, void* hi_recv,
+                                  size_t bytes, int lo_rank, int hi_rank, void* stream) {
+  if (!comm) return fail(PSAD_ERR_INVALID, "null communicator");
+  if (int rc = need_nccl()) return rc;
+  if (bytes == 0 || (lo_rank < 0 && hi_rank < 0)) return 0;
+  ncclComm_t c = (ncclComm_t)comm;
+  CUstream s = (CUstream)stream;
+  NCCL_CHECK(g_nccl.ncclGroupStart());
+  int rc = 0;
+  // ncclInt8 == ncclChar == 0: counts are bytes
+  if (lo_rank >= 0) {
+    if (!rc) rc = g_nccl.ncclSend(lo_send, bytes, 0, lo_rank, c, s);
+    if (!rc) rc = g_nccl.ncclRecv(lo_recv, bytes, 0, lo_rank, c, s);
+  }
+  if (hi_rank >= 0) {
+    if (!rc) rc = g_nccl.ncclSend(hi_send, bytes, 0, hi_rank, c, s);
+    if (!rc) rc = g_nccl.ncclRecv(hi_recv, bytes, 0, hi_rank, c, s);
+  }
+  int rc2 = g_nccl.ncclGroupEnd();
+  if (rc) return fail(PSAD_ERR_NCCL, "ncclSend/ncclRecv failed: %s", g_nccl.ncclGetErrorString(rc));
+  if (rc2) return fail(PSAD_ERR_NCCL, "ncclGroupEnd failed: %s", g_nccl.ncclGetErrorString(rc2));
+  return 0;
+}

@@ -1,0 +1,482 @@
+"""CUDA source emitter: instantiates the hand-written sm_100a kernel templates for one stencil.
+
+This is the replacement of the reference's backend printer
+(/root/reference/src/pystencils_autodiff/framework_integration/printer.py:12-176 together with pystencils'
+``generate_c``): instead of printing a one-thread-per-cell kernel it emits a small translation unit that
+
+* ``march`` variant — configures ``csrc/kernels/psad_march.cuh`` (persistent CTAs, TMA-staged haloed tiles in a
+  shared-memory ring, mbarrier pipeline) and generates the per-step body ``psad_step``: a register window along the
+  march axis (each staged element is read from shared memory once and carried in registers while its plane moves
+  through the stencil), 128-bit shared loads, warp-shuffle x-halos and 128-bit streaming stores;
+* ``generic`` variant — a grid-stride kernel with scalar loads for anything the fast path cannot take (unaligned
+  row pitch such as the README's 20x30 fp32 fields, 1-D fields, index dimensions, off-centre writes).
+
+Both are compiled by NVRTC for sm_100a through the C ABI (``include/psad.h``).
+"""
+import hashlib
+import os
+from dataclasses import dataclass, field as dc_field
+from typing import Dict, List, Optional
+
+import numpy as np
+import sympy as sp
+from sympy.codegen.ast import float32, float64, real
+from sympy.printing.c import C99CodePrinter
+
+from .field import Field
+from .ir import StencilKernelIR
+
+KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
+EMITTER_VERSION = '1'
+
+_CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
+
+
+@dataclass
+class EmittedKernel:
+    name: str
+    kind: str                      # 'generic' | 'march'
+    source: str
+    ir: StencilKernelIR
+    fields: List[Field]            # plan order: outputs then inputs
+    scalars: List[str]
+    plan: Dict = dc_field(default_factory=dict)
+    options: List[str] = dc_field(default_factory=list)
+
+    @property
+    def cache_key(self):
+        h = hashlib.md5()
+        h.update(EMITTER_VERSION.encode())
+        h.update(self.source.encode())
+        h.update(' '.join(self.options).encode())
+        for fn in sorted(os.listdir(KERNEL_DIR)):
+            with open(os.path.join(KERNEL_DIR, fn), 'rb') as fh:
+                h.update(fh.read())
+        return '%s_%s' % (self.name[:40], h.hexdigest())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class _CudaPrinter(C99CodePrinter):
+    """sympy -> CUDA C expression in the kernel's compute type (float literals get an ``F`` suffix)."""
+
+    def __init__(self, compute_dtype):
+        alias = {real: float32 if np.dtype(compute_dtype) == np.float32 else float64}
+        super().__init__(settings={'type_aliases': alias})
+        self._one = '1.0F' if np.dtype(compute_dtype) == np.float32 else '1.0'
+        self._sqrt = 'sqrtf' if np.dtype(compute_dtype) == np.float32 else 'sqrt'
+
+    def _print_Pow(self, expr):
+        b, e = expr.base, expr.exp
+        if e.is_Integer and 1 < abs(int(e)) <= 8:
+            base = self._print(b)
+            if not (b.is_Symbol or b.is_Number):
+                base = '(%s)' % base
+            s = '*'.join([base] * abs(int(e)))
+            return '(%s)' % s if int(e) > 0 else '(%s/(%s))' % (self._one, s)
+        if e == -1:
+            return '(%s/(%s))' % (self._one, self._print(b))
+        if e == sp.Rational(1, 2):
+            return '%s(%s)' % (self._sqrt, self._print(b))
+        if e == sp.Rational(-1, 2):
+            return '(%s/%s(%s))' % (self._one, self._sqrt, self._print(b))
+        return super()._print_Pow(expr)
+
+
+def _c_ident(name):
+    out = ''.join(ch if (ch.isalnum() or ch == '_') else '_' for ch in name)
+    if not out or out[0].isdigit():
+        out = '_' + out
+    return out
+
+
+def _off3(offsets):
+    return (0,) * (3 - len(offsets)) + tuple(int(o) for o in offsets)
+
+
+def _kernel_name(ir, kind):
+    return _c_ident('psad_%s_%s' % (ir.function_name, kind))
+
+
+def _header(ir, kind, extra=''):
+    lines = ['// Specialised by pystencils_autodiff_b200.emit for kernel "%s" (%s variant).' % (ir.function_name, kind),
+             '// boundary=%s ghost_layers=%d ndim=%d compute=%s' % (ir.boundary, ir.ghost_layers, ir.ndim,
+                                                                   _CT[ir.compute_dtype])]
+    for lhs, rhs in ir.subexpressions:
+        lines.append('//   %s <- %s' % (lhs, rhs))
+    for lhs, rhs in ir.main:
+        lines.append('//   %s <- %s' % (lhs.field_str(), rhs))
+    if extra:
+        lines.append(extra)
+    return lines
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def emit_generic(ir: StencilKernelIR, threads=256) -> EmittedKernel:
+    name = _kernel_name(ir, 'generic')
+    CT = _CT[ir.compute_dtype]
+    pr = _CudaPrinter(ir.compute_dtype)
+    fields = ir.all_fields
+    fidx = {f.name: i for i, f in enumerate(fields)}
+    scalars = [s.name for s in ir.scalars]
+    lz, ly, lx = _off3(ir.lhs_offset)
+
+    L = _header(ir, 'generic')
+    L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT]
+    for f in fields:
+        L.append('typedef %s T_%d;  // %s' % (_CT[f.dtype.numpy_dtype], fidx[f.name], f.name))
+    L += ['',
+          'extern "C" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ PsadArgs A)' % (threads, name),
+          '{',
+          '  const long long nx = A.wr_hi[2] - A.wr_lo[2], ny = A.wr_hi[1] - A.wr_lo[1], nz = A.wr_hi[0] - A.wr_lo[0];',
+          '  const long long total = nx * ny * nz;']
+    for i, s in enumerate(scalars):
+        L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s), i))
+    L += ['  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;',
+          '       i += (long long)gridDim.x * blockDim.x) {',
+          '    const long long x = A.wr_lo[2] + i % nx;',
+          '    const long long t = i / nx;',
+          '    const long long y = A.wr_lo[1] + t % ny;',
+          '    const long long z = A.wr_lo[0] + t / ny;',
+          '    const long long cz = z - (%d), cy = y - (%d), cx = x - (%d);  // cell the expression is evaluated at' % (lz, ly, lx),
+          '    const bool inside = cz >= A.it_lo[0] && cz < A.it_hi[0] && cy >= A.it_lo[1] && cy < A.it_hi[1] &&',
+          '                        cx >= A.it_lo[2] && cx < A.it_hi[2];']
+    outs = []
+    for k, (lhs, _) in enumerate(ir.main):
+        L.append('    CT o_%d = (CT)0;' % k)
+        outs.append(lhs)
+    L.append('    if (inside) {')
+    local = {}
+    n = 0
+    for fname in sorted(ir.read_accesses):
+        fi = fidx[fname]
+        for a in ir.read_accesses[fname]:
+            dz, dy, dx = _off3(a.offsets)
+            idx = int(a.index[0]) if a.index else 0
+            var = 'r_%d' % n
+            n += 1
+            addr = ('((const T_%d*)A.ptr[%d])[(cz + (%d)) * A.stride[%d][0] + (cy + (%d)) * A.stride[%d][1] + '
+                    '(cx + (%d)) * A.stride[%d][2] + %d * A.stride[%d][3]]' % (fi, fi, dz, fi, dy, fi, dx, fi, idx, fi))
+            if ir.boundary == 'zeros' and (dz or dy or dx):
+                conds = []
+                for o, c, d in ((dz, 'cz', 0), (dy, 'cy', 1), (dx, 'cx', 2)):
+                    if o < 0:
+                        conds.append('%s + (%d) >= 0' % (c, o))
+                    elif o > 0:
+                        conds.append('%s + (%d) < A.shape[%d]' % (c, o, d))
+                L.append('      const CT %s = (%s) ? (CT)%s : (CT)0;' % (var, ' && '.join(conds), addr))
+            else:
+                L.append('      const CT %s = (CT)%s;' % (var, addr))
+            local[a] = sp.Symbol(var)
+    for s in ir.scalars:
+        local[s] = sp.Symbol(_c_ident(s.name))
+    for lhs, rhs in ir.subexpressions:
+        L.append('      const CT %s = %s;' % (_c_ident(lhs.name), pr.doprint(rhs.xreplace(local))))
+        local[lhs] = sp.Symbol(_c_ident(lhs.name))
+    for k, (lhs, rhs) in enumerate(ir.main):
+        L.append('      o_%d = %s;' % (k, pr.doprint(rhs.xreplace(local))))
+    L.append('    }')
+    for k, lhs in enumerate(outs):
+        fi = fidx[lhs.field.name]
+        idx = int(lhs.index[0]) if lhs.index else 0
+        L.append('    ((T_%d*)A.ptr[%d])[z * A.stride[%d][0] + y * A.stride[%d][1] + x * A.stride[%d][2] + %d * A.stride[%d][3]] = (T_%d)o_%d;'
+                 % (fi, fi, fi, fi, fi, idx, fi, fi, k))
+    L += ['  }', '}', '']
+
+    plan = dict(kind=0, ndim=ir.ndim, n_fields=len(fields), n_scalars=len(scalars), threads=threads, smem_bytes=0,
+                tile_x=0, tile_y=0, chunk=0, ctas_per_sm=8, boundary=1 if ir.boundary == 'zeros' else 0,
+                ghost_layers=ir.ghost_layers,
+                fields=[dict(elem_size=f.dtype.itemsize, is_input=int(f in ir.input_fields),
+                             is_output=int(f in ir.output_fields),
+                             index_size=int(f.index_shape[0]) if f.index_dimensions else 1, tma=0, box=(0, 0, 0))
+                        for f in fields])
+    return EmittedKernel(name, 'generic', '\n'.join(L), ir, fields, scalars, plan)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class MarchTuning:
+    """Tile geometry of the march template.  ``sx`` cells per thread along x (one warp spans a tile row, so the
+    tile is 32*sx cells wide), ``ry`` rows per thread, ``ty`` rows per tile, ``stages`` ring slots,
+    ``chunk`` planes (3-D) / row tiles (2-D) per work item (0 = whole axis, balanced by the runtime)."""
+    sx: int = 0
+    ry: int = 0
+    ty: int = 0
+    lookahead: int = 3
+    chunk: int = 0
+    min_ctas: int = 0
+    carry: bool = True     # keep staged elements in registers while their plane moves through the stencil
+    shuffle: bool = True   # x-halo elements from neighbouring lanes instead of shared memory
+
+
+def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
+    if ir.ndim not in (2, 3):
+        return 'needs 2 or 3 spatial dimensions'
+    if any(o != 0 for o in ir.lhs_offset):
+        return 'off-centre writes'
+    for f in ir.all_fields:
+        if f.index_dimensions:
+            return 'index dimensions'
+        if f.dtype.numpy_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            return 'only float32/float64 fields'
+    if not ir.input_fields:
+        return 'no input fields'
+    for f in ir.input_fields:
+        if f in ir.output_fields and any(any(o != 0 for o in a.offsets) for a in ir.read_accesses[f.name]):
+            return 'in-place update of a field read at an offset'
+    if len(ir.all_fields) > 12:
+        return 'too many fields'
+    return None
+
+
+def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> EmittedKernel:
+    reason = march_ineligible_reason(ir)
+    if reason:
+        raise ValueError('march variant not applicable: ' + reason)
+    t = tuning or MarchTuning()
+    name = _kernel_name(ir, 'march')
+    CT = _CT[ir.compute_dtype]
+    pr = _CudaPrinter(ir.compute_dtype)
+    fields = ir.all_fields
+    fidx = {f.name: i for i, f in enumerate(fields)}
+    scalars = [s.name for s in ir.scalars]
+    nd = ir.ndim
+    max_esize = max(f.dtype.itemsize for f in fields)
+
+    # ---- geometry ------------------------------------------------------------------------------------------
+    SX = t.sx or 4                         # 4 cells per thread: one LDS.128 for fp32, two for fp64
+    if (SX * min(f.dtype.itemsize for f in fields)) % 16:
+        raise ValueError('sx*itemsize must be a multiple of 16 bytes')
+    TX = 32 * SX
+    mh = ir.max_halo                        # per ndim axis (lo, hi)
+    mh3 = [(0, 0)] * (3 - nd) + list(mh)
+    HZL, HZH = (mh3[0] if nd == 3 else (0, 0))
+    D = HZL + HZH
+    RY = t.ry or (2 if max_esize == 4 else 1)
+    TY = t.ty or ((16 if nd == 3 else 32) if max_esize == 4 else 8)
+    if TY % RY:
+        raise ValueError('ty must be a multiple of ry')
+    THREADS = 32 * (TY // RY)
+    if THREADS > 1024:
+        raise ValueError('tile too tall: %d threads' % THREADS)
+    STAGES = D + 1 + max(1, t.lookahead)
+
+    tma_fields = [f for f in fields if f in ir.input_fields]   # plan order: the runtime numbers tensor maps this way
+    geo = {}
+    off = 0
+    for ti, f in enumerate(tma_fields):
+        h3 = [(0, 0)] * (3 - nd) + list(ir.halo(f.name))
+        es = f.dtype.itemsize
+        vec = 16 // es
+        hxl, hxr = h3[2]
+        if hxl > SX or hxr > SX:
+            raise ValueError('x halo wider than the per-thread strip')
+        padl = -(-hxl // vec) * vec
+        padr = -(-hxr // vec) * vec
+        boxw = TX + padl + padr
+        boxh = TY + h3[1][0] + h3[1][1]
+        if boxw > 256 or boxh > 256:
+            raise ValueError('TMA box too large')
+        nbytes = boxw * boxh * es
+        geo[f.name] = dict(ti=ti, es=es, vec=vec, nv=SX // vec, hz=h3[0], hy=h3[1], hx=h3[2], padl=padl, boxw=boxw,
+                           boxh=boxh, bytes=nbytes, off=off, T=_CT[f.dtype.numpy_dtype])
+        off += -(-nbytes // 128) * 128
+    STAGE_BYTES = off
+    smem_bytes = STAGES * STAGE_BYTES + 8 * STAGES
+    if smem_bytes > 227 * 1024:
+        raise ValueError('ring does not fit in shared memory (%d bytes)' % smem_bytes)
+
+    # ---- register-window analysis ------------------------------------------------------------------------------
+    # unit = ('U', row, v): aligned 16-byte vector v of the thread's own strip in tile row `row` (relative to the
+    # thread's first row);  ('H', row, c): single halo element at strip column c (<0 or >=SX).
+    def src_col(c):
+        return SX + c if c < 0 else c - SX
+
+    need = {f.name: [set() for _ in range(D + 1)] for f in tma_fields}
+    for f in tma_fields:
+        g = geo[f.name]
+        for a in ir.read_accesses[f.name]:
+            dz, dy, dx = _off3(a.offsets)
+            j = dz + HZL
+            for r in range(RY):
+                for c in range(SX):
+                    cc = c + dx
+                    if 0 <= cc < SX:
+                        need[f.name][j].add(('U', r + dy, cc // g['vec']))
+                    else:
+                        need[f.name][j].add(('H', r + dy, cc))
+                        if t.shuffle:
+                            need[f.name][j].add(('U', r + dy, src_col(cc) // g['vec']))
+    carried = {f.name: [set() for _ in range(D + 1)] for f in tma_fields}   # available from the previous step
+    held = {f.name: [set() for _ in range(D + 1)] for f in tma_fields}
+    fresh = {f.name: [set() for _ in range(D + 1)] for f in tma_fields}
+    for f in tma_fields:
+        nm = f.name
+        for j in range(D, -1, -1):
+            future = set().union(*[need[nm][jj] for jj in range(j)]) if j > 0 else set()
+            if j < D and t.carry:
+                carried[nm][j] = held[nm][j + 1] & (need[nm][j] | future)
+            held[nm][j] = need[nm][j] | carried[nm][j]
+            fresh[nm][j] = need[nm][j] - carried[nm][j]
+
+    # register budget: window elements + outputs + addressing; decides how many CTAs we ask ptxas to fit per SM
+    words = sum(len({(u[1], c) for u in held[f.name][j] for c in
+                     (range(u[2] * geo[f.name]['vec'], (u[2] + 1) * geo[f.name]['vec']) if u[0] == 'U' else [u[2]])})
+                * (geo[f.name]['es'] // 4) for f in tma_fields for j in range(D + 1))
+    words += sum(SX * (lhs.field.dtype.itemsize // 4) for lhs, _ in ir.main)
+    est_regs = min(255, words + 48)
+    min_ctas = t.min_ctas or max(1, min(2048 // THREADS, (227 * 1024) // smem_bytes, 65536 // (THREADS * est_regs)))
+
+    def arr(f, j, row):
+        g = geo[f.name]
+        return 'R.f%d_p%d_r%d' % (g['ti'], j, row + g['hy'][0])
+
+    def elem(f, j, row, c):
+        return '%s[%d]' % (arr(f, j, row), c + geo[f.name]['hx'][0])
+
+    # ---- source -------------------------------------------------------------------------------------------------
+    L = _header(ir, 'march')
+    L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT, 'namespace cfg {',
+          'constexpr int NDIM = %d, TX = %d, TY = %d, RY = %d, SX = %d;' % (nd, TX, TY, RY, SX),
+          'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d;' % (THREADS, min_ctas, STAGES, HZL, HZH),
+          'constexpr int NTMA = %d, STAGE_BYTES = %d, TX_BYTES = %d;' % (len(tma_fields), STAGE_BYTES,
+                                                                         sum(geo[f.name]['bytes'] for f in tma_fields)),
+          '__device__ constexpr int F_OFF[NTMA] = {%s};' % ', '.join(str(geo[f.name]['off']) for f in tma_fields),
+          '__device__ constexpr int F_ORGX[NTMA] = {%s};' % ', '.join(str(-geo[f.name]['padl']) for f in tma_fields),
+          '__device__ constexpr int F_ORGY[NTMA] = {%s};' % ', '.join(str(-geo[f.name]['hy'][0]) for f in tma_fields),
+          '}  // namespace cfg', '']
+    # carry struct
+    L.append('struct PsadCarry {')
+    for f in tma_fields:
+        g = geo[f.name]
+        rows = sorted({(j, u[1]) for j in range(D + 1) for u in held[f.name][j]})
+        W = g['hx'][0] + SX + g['hx'][1]
+        for j, row in rows:
+            L.append('  %s f%d_p%d_r%d[%d];  // %s, plane %+d, row %+d' % (g['T'], g['ti'], j, row + g['hy'][0], W, f.name,
+                                                                        j - HZL, row))
+    L.append('};')
+    L.append('')
+    L.append('PSAD_DEV void psad_step(const PsadArgs& A, const unsigned char* ring, int slot, PsadCarry& R, int lane,')
+    L.append('                        int wy, bool do_store, long long z, long long y0, long long x0)')
+    L.append('{')
+    for i, s in enumerate(scalars):
+        L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s), i))
+    for j in range(D + 1):
+        if any(fresh[f.name][j] for f in tma_fields):
+            back = D - j
+            if back == 0:
+                L.append('  const unsigned char* st%d = ring + (long long)slot * cfg::STAGE_BYTES;' % j)
+            else:
+                L.append('  const unsigned char* st%d = ring + (long long)(slot >= %d ? slot - %d : slot - %d + cfg::STAGES) * cfg::STAGE_BYTES;'
+                         % (j, back, back, back))
+    # fresh loads
+    for j in range(D, -1, -1):
+        for f in tma_fields:
+            g = geo[f.name]
+            fr = fresh[f.name][j]
+            if not fr:
+                continue
+            rows = sorted({u[1] for u in fr})
+            for row in rows:
+                rp = 'p%d_%d_%d' % (g['ti'], j, row + g['hy'][0])
+                L.append('  const %s* %s = reinterpret_cast<const %s*>(st%d + %d) + (wy * %d + %d) * %d + %d + lane * %d;'
+                         % (g['T'], rp, g['T'], j, g['off'], RY, row + g['hy'][0], g['boxw'], g['padl'], SX))
+                for u in sorted(x for x in fr if x[0] == 'U' and x[1] == row):
+                    L.append('  psad_lds_vec<%s>(%s + %d, &%s);' % (g['T'], rp, u[2] * g['vec'], elem(f, j, row, u[2] * g['vec'])))
+                for u in sorted(x for x in fr if x[0] == 'H' and x[1] == row):
+                    c = u[2]
+                    if t.shuffle:
+                        if c < 0:
+                            L.append('  %s = psad_from_left(%s);' % (elem(f, j, row, c), elem(f, j, row, src_col(c))))
+                            L.append('  if (lane == 0) %s = %s[%d];' % (elem(f, j, row, c), rp, c))
+                        else:
+                            L.append('  %s = psad_from_right(%s);' % (elem(f, j, row, c), elem(f, j, row, src_col(c))))
+                            L.append('  if (lane == 31) %s = %s[%d];' % (elem(f, j, row, c), rp, c))
+                    else:
+                        L.append('  %s = %s[%d];' % (elem(f, j, row, c), rp, c))
+    # compute + store
+    L.append('  if (do_store) {')
+    if nd == 3:
+        L.append('    const bool zin = z >= A.it_lo[0] && z < A.it_hi[0];')
+    else:
+        L.append('    const bool zin = true;')
+    out_fields = ir.output_fields
+    for r in range(RY):
+        L.append('    {')
+        L.append('      const long long y = y0 + wy * %d + %d;' % (RY, r))
+        L.append('      if (y >= A.wr_lo[1] && y < A.wr_hi[1]) {')
+        L.append('        const bool yin = zin && y >= A.it_lo[1] && y < A.it_hi[1];')
+        for lhs, _ in ir.main:
+            L.append('        %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
+        for c in range(SX):
+            local = {}
+            for f in tma_fields:
+                for a in ir.read_accesses[f.name]:
+                    dz, dy, dx = _off3(a.offsets)
+                    local[a] = sp.Symbol('((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx))
+            for s in ir.scalars:
+                local[s] = sp.Symbol(_c_ident(s.name))
+            L.append('        {')
+            L.append('          const long long x = x0 + lane * %d + %d;' % (SX, c))
+            L.append('          const bool in = yin && x >= A.it_lo[2] && x < A.it_hi[2];')
+            for lhs, rhs in ir.subexpressions:
+                L.append('          const CT %s = %s;' % (_c_ident(lhs.name), pr.doprint(rhs.xreplace(local))))
+                local[lhs] = sp.Symbol(_c_ident(lhs.name))
+            for lhs, rhs in ir.main:
+                To = _CT[lhs.field.dtype.numpy_dtype]
+                L.append('          o%d[%d] = in ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, To,
+                                                                        pr.doprint(rhs.xreplace(local)), To))
+            L.append('        }')
+        for f in out_fields:
+            fi = fidx[f.name]
+            To = _CT[f.dtype.numpy_dtype]
+            vec = 16 // f.dtype.itemsize
+            L.append('        %s* q%d = reinterpret_cast<%s*>(A.ptr[%d]) + z * A.stride[%d][0] + y * A.stride[%d][1] + x0 + lane * %d;'
+                     % (To, fi, To, fi, fi, fi, SX))
+            for v in range(SX // vec):
+                L.append('        if (x0 + lane * %d + %d <= A.shape[2]) psad_stg_vec<%s>(q%d + %d, &o%d[%d]);'
+                         % (SX, (v + 1) * vec, To, fi, v * vec, fi, v * vec))
+        L.append('      }')
+        L.append('    }')
+    L.append('  }')
+    # rotate the window
+    for j in range(D):
+        for f in tma_fields:
+            g = geo[f.name]
+            for u in sorted(carried[f.name][j]):
+                if u[0] == 'U':
+                    for c in range(u[2] * g['vec'], (u[2] + 1) * g['vec']):
+                        L.append('  %s = %s;' % (elem(f, j, u[1], c), elem(f, j + 1, u[1], c)))
+                else:
+                    L.append('  %s = %s;' % (elem(f, j, u[1], u[2]), elem(f, j + 1, u[1], u[2])))
+    L.append('}')
+    L.append('')
+    L.append('#define PSAD_KERNEL_NAME %s' % name)
+    L.append('#include "psad_march.cuh"')
+    L.append('')
+
+    def fplan(f):
+        g = geo.get(f.name)
+        is_in = f in ir.input_fields
+        return dict(elem_size=f.dtype.itemsize, is_input=int(is_in), is_output=int(f in ir.output_fields), index_size=1,
+                    tma=int(is_in), box=(g['boxw'], g['boxh'], 1) if is_in else (0, 0, 0))
+
+    plan = dict(kind=1, ndim=nd, n_fields=len(fields), n_scalars=len(scalars), threads=THREADS, smem_bytes=smem_bytes,
+                tile_x=TX, tile_y=TY, chunk=t.chunk, ctas_per_sm=0, boundary=1 if ir.boundary == 'zeros' else 0,
+                ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
+    ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
+    ek.geometry = dict(TX=TX, TY=TY, RY=RY, SX=SX, STAGES=STAGES, STAGE_BYTES=STAGE_BYTES, HZ=(HZL, HZH),
+                       threads=THREADS, min_ctas=min_ctas)
+    return ek
+
+
+def emit_kernel(ir: StencilKernelIR, variant='auto', tuning=None) -> EmittedKernel:
+    if variant == 'generic':
+        return emit_generic(ir)
+    if variant == 'march':
+        return emit_march(ir, tuning)
+    if march_ineligible_reason(ir) is None:
+        try:
+            return emit_march(ir, tuning)
+        except ValueError:
+            pass
+    return emit_generic(ir)

@@ -1,0 +1,204 @@
+"""ctypes binding of the C ABI in ``include/psad.h`` (``csrc/libpsad.so``).
+
+This is the only place Python talks to native code.  There is no fallback: if the shared library has not been
+built, or a call fails, a ``RuntimeError`` carrying ``psad_last_error()`` is raised.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, 'csrc')
+KERNEL_DIR = os.path.join(CSRC_DIR, 'kernels')
+LIB_PATH = os.path.join(CSRC_DIR, 'libpsad.so')
+DEFAULT_CACHE_DIR = os.environ.get('PSAD_CACHE_DIR', os.path.join(_HERE, '_cubin_cache'))
+
+PSAD_MAX_FIELDS = 12
+PSAD_MAX_SCALARS = 16
+PSAD_ABI_VERSION = 1
+
+
+class FieldPlan(ctypes.Structure):
+    _fields_ = [('elem_size', ctypes.c_int32), ('is_input', ctypes.c_int32), ('is_output', ctypes.c_int32),
+                ('index_size', ctypes.c_int32), ('tma', ctypes.c_int32), ('box', ctypes.c_int32 * 3),
+                ('reserved', ctypes.c_int32 * 4)]
+
+
+class Plan(ctypes.Structure):
+    _fields_ = [('abi_version', ctypes.c_int32), ('kind', ctypes.c_int32), ('ndim', ctypes.c_int32),
+                ('n_fields', ctypes.c_int32), ('n_scalars', ctypes.c_int32), ('threads', ctypes.c_int32),
+                ('smem_bytes', ctypes.c_int32), ('tile_x', ctypes.c_int32), ('tile_y', ctypes.c_int32),
+                ('chunk', ctypes.c_int32), ('ctas_per_sm', ctypes.c_int32), ('boundary', ctypes.c_int32),
+                ('ghost_layers', ctypes.c_int32), ('reserved', ctypes.c_int32 * 8),
+                ('field', FieldPlan * PSAD_MAX_FIELDS)]
+
+
+class FieldArg(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('shape', ctypes.c_int64 * 3), ('stride', ctypes.c_int64 * 4)]
+
+
+class Range(ctypes.Structure):
+    _fields_ = [('iter_lo', ctypes.c_int64 * 3), ('iter_hi', ctypes.c_int64 * 3),
+                ('write_lo', ctypes.c_int64 * 3), ('write_hi', ctypes.c_int64 * 3)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build_library(force=False, verbose=False):
+    """Compile ``csrc/psad_runtime.cpp`` into ``csrc/libpsad.so`` (plain g++: all device code goes through NVRTC)."""
+    src = os.path.join(CSRC_DIR, 'psad_runtime.cpp')
+    deps = [src, os.path.join(_HERE, '..', 'include', 'psad.h'), os.path.join(KERNEL_DIR, 'psad_args.h')]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ['g++', '-O2', '-fPIC', '-shared', '-std=c++17', '-Wall', '-o', LIB_PATH + '.tmp', src, '-ldl', '-lpthread']
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    os.replace(LIB_PATH + '.tmp', LIB_PATH)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'pystencils_autodiff_b200: native runtime %s is missing. Build it with '
+                '`python -c "import __graft_entry__ as g; g.build()"` (there is no CPU/PyTorch fallback).' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.psad_last_error.restype = ctypes.c_char_p
+        L.psad_launch_count.restype = ctypes.c_uint64
+        L.psad_init.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        L.psad_compile.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
+                                   ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p)]
+        L.psad_free.argtypes = [ctypes.c_void_p]
+        L.psad_kernel_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
+                                         ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.POINTER(Plan),
+                                         ctypes.POINTER(ctypes.c_void_p)]
+        L.psad_kernel_destroy.argtypes = [ctypes.c_void_p]
+        L.psad_kernel_attributes.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 4
+        L.psad_kernel_launch.argtypes = [ctypes.c_void_p, ctypes.POINTER(FieldArg), ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(Range),
+                                         ctypes.c_void_p]
+        L.psad_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
+        L.psad_nccl_unique_id.argtypes = [ctypes.c_void_p]
+        L.psad_nccl_comm_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.psad_nccl_comm_destroy.argtypes = [ctypes.c_void_p]
+        L.psad_halo_exchange.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        if L.psad_abi_version() != PSAD_ABI_VERSION:
+            raise RuntimeError('libpsad.so ABI version mismatch: rebuild it')
+        rc = L.psad_init(KERNEL_DIR.encode(), DEFAULT_CACHE_DIR.encode())
+        if rc:
+            raise RuntimeError('psad_init failed: %s' % L.psad_last_error().decode())
+        _lib = L
+        return _lib
+
+
+def check(rc, what=''):
+    if rc:
+        raise RuntimeError('%s failed (code %d): %s' % (what or 'libpsad call', rc, lib().psad_last_error().decode()))
+
+
+def make_plan(p):
+    plan = Plan()
+    plan.abi_version = PSAD_ABI_VERSION
+    for k in ('kind', 'ndim', 'n_fields', 'n_scalars', 'threads', 'smem_bytes', 'tile_x', 'tile_y', 'chunk',
+              'ctas_per_sm', 'boundary', 'ghost_layers'):
+        setattr(plan, k, int(p[k]))
+    for i, f in enumerate(p['fields']):
+        fp = plan.field[i]
+        for k in ('elem_size', 'is_input', 'is_output', 'index_size', 'tma'):
+            setattr(fp, k, int(f[k]))
+        for d in range(3):
+            fp.box[d] = int(f['box'][d])
+    return plan
+
+
+def _options(options):
+    arr = (ctypes.c_char_p * max(1, len(options)))(*[o.encode() for o in options])
+    return arr, len(options)
+
+
+def compile_source(source, cache_key, options=()):
+    """NVRTC -> sm_100a cubin in the cache (works without a GPU).  Returns ``(cache_hit, log)``."""
+    L = lib()
+    arr, n = _options(list(options))
+    hit = ctypes.c_int(0)
+    log = ctypes.c_void_p()
+    rc = L.psad_compile(source.encode(), cache_key.encode(), arr, n, ctypes.byref(hit), ctypes.byref(log))
+    text = ''
+    if log.value:
+        text = ctypes.string_at(log.value).decode(errors='replace')
+        L.psad_free(log)
+    check(rc, 'psad_compile')
+    return bool(hit.value), text
+
+
+def cubin_path(cache_key):
+    return os.path.join(DEFAULT_CACHE_DIR, cache_key + '.cubin')
+
+
+class NativeKernel:
+    """Owns one ``psad_kernel_t``."""
+
+    def __init__(self, emitted):
+        L = lib()
+        self.emitted = emitted
+        self._plan = make_plan(emitted.plan)
+        arr, n = _options(list(emitted.options))
+        handle = ctypes.c_void_p()
+        check(L.psad_kernel_create(emitted.source.encode(), emitted.name.encode(), emitted.cache_key.encode(), arr, n,
+                                   ctypes.byref(self._plan), ctypes.byref(handle)), 'psad_kernel_create(%s)' % emitted.name)
+        self._handle = handle
+        self._scal = (ctypes.c_double * PSAD_MAX_SCALARS)()
+
+    def attributes(self):
+        vals = [ctypes.c_int(0) for _ in range(4)]
+        check(lib().psad_kernel_attributes(self._handle, *[ctypes.byref(v) for v in vals]), 'psad_kernel_attributes')
+        return dict(num_regs=vals[0].value, static_smem=vals[1].value, local_bytes=vals[2].value,
+                    max_ctas_per_sm=vals[3].value)
+
+    def launch(self, field_args, scalars, stream, rng=None):
+        """field_args: list of ``(ptr, shape, strides)`` in plan order; scalars: list of floats; stream: int handle."""
+        n = len(field_args)
+        fa = (FieldArg * n)()
+        for i, (ptr, shape, strides) in enumerate(field_args):
+            fa[i].ptr = ptr
+            for d in range(3):
+                fa[i].shape[d] = shape[d] if d < len(shape) else 1
+            for d in range(4):
+                fa[i].stride[d] = strides[d] if d < len(strides) else 0
+        for i, s in enumerate(scalars):
+            self._scal[i] = float(s)
+        r = None
+        if rng is not None:
+            r = Range()
+            for d in range(len(rng['iter_lo'])):
+                r.iter_lo[d], r.iter_hi[d] = rng['iter_lo'][d], rng['iter_hi'][d]
+                r.write_lo[d], r.write_hi[d] = rng['write_lo'][d], rng['write_hi'][d]
+            r = ctypes.byref(r)
+        check(lib().psad_kernel_launch(self._handle, fa, n, self._scal, len(scalars), r, ctypes.c_void_p(stream)),
+              'psad_kernel_launch(%s)' % self.emitted.name)
+
+    def __del__(self):
+        try:
+            if self._handle:
+                lib().psad_kernel_destroy(self._handle)
+        except Exception:
+            pass
+
+
+def launch_count():
+    return int(lib().psad_launch_count())
+
+
+def device_info():
+    vals = [ctypes.c_int(0) for _ in range(4)]
+    smem = ctypes.c_size_t(0)
+    check(lib().psad_device_info(*[ctypes.byref(v) for v in vals], ctypes.byref(smem)), 'psad_device_info')
+    return dict(device=vals[0].value, sm_count=vals[1].value, cc=(vals[2].value, vals[3].value), smem_optin=smem.value)

@@ -1,0 +1,94 @@
+"""GPU parity: CUDA kernels (through the torch_native Function and the C ABI) vs the numpy oracle.
+
+Tolerances (BASELINE.json north_star): norm-wise relative error <= 1e-6 for float32 fields, <= 1e-12 for float64.
+"""
+import numpy as np
+import pytest
+
+from oracle import forward_backward
+from pystencils_autodiff_b200.configs import make_config
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'float32': 1e-6, 'float64': 1e-12}
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+def run_op(op, shape, lo, hi, seed, variant=None):
+    import torch
+    dev = torch.device('cuda:0')
+    rng = np.random.default_rng(seed)
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    ins = {f.name: rng.uniform(lo, hi, size=shape).astype(f.dtype.numpy_dtype) for f in op.forward_input_fields}
+    grads = {f.name: rng.normal(size=shape).astype(f.dtype.numpy_dtype) for f in op.forward_output_fields}
+    tens = [torch.from_numpy(ins[f.name]).to(dev).requires_grad_(True) for f in op.forward_input_fields]
+    if variant is not None:
+        fn.forward_kernel._select_variant = lambda tensors: variant
+        fn.backward_kernel._select_variant = lambda tensors: variant
+    outs = fn.apply(*tens)
+    torch.autograd.backward(outs, [torch.from_numpy(grads[f.name]).to(dev) for f in op.forward_output_fields])
+    ref_out, ref_din = forward_backward(op, ins, grads)
+    res = {}
+    for f, o in zip(op.forward_output_fields, outs):
+        res[f.name] = _rel(o.detach().cpu().numpy(), ref_out[f.name])
+    for f, t in zip(op.forward_input_fields, tens):
+        res['diff' + f.name] = _rel(t.grad.cpu().numpy(), ref_din['diff' + f.name])
+    return res, fn
+
+
+CASES = [
+    # name, shape, dtype, value range
+    ('c1', (20, 30), 'float32', (0.5, 1.5)),
+    ('c1', (20, 32), 'float64', (0.5, 1.5)),
+    ('c2', (96, 256), 'float32', (-1, 1)),
+    ('c2', (70, 132), 'float32', (-1, 1)),     # ragged: partial tiles in both directions
+    ('c2', (33, 20), 'float64', (-1, 1)),
+    ('c3', (40, 48, 256), 'float32', (-1, 1)),
+    ('c3', (19, 21, 36), 'float32', (-1, 1)),   # ragged
+    ('c3', (9, 10, 11), 'float32', (-1, 1)),    # unaligned pitch -> generic
+    ('c4', (12, 20, 132), 'float64', (-1, 1)),
+    ('c5', (3, 40, 136), 'float32', (0, 1)),
+]
+
+
+@pytest.mark.parametrize('bh', [None, 'zeros'])
+@pytest.mark.parametrize('name,shape,dtype,rng', CASES)
+def test_forward_backward_matches_oracle(name, shape, dtype, rng, bh):
+    op = make_config(name, shape=shape, dtype=dtype, boundary_handling=bh)
+    res, fn = run_op(op, shape, rng[0], rng[1], seed=1)
+    tol = TOL[dtype] * (50 if name == 'c5' else 1)  # TV: sqrt/div chains, norm-wise 5e-5 in fp32 arithmetic
+    for k, v in res.items():
+        assert v <= tol, (name, shape, bh, k, v, fn.forward_kernel.last_variant, fn.backward_kernel.last_variant)
+
+
+@pytest.mark.parametrize('bh', [None, 'zeros'])
+@pytest.mark.parametrize('name,shape,dtype,rng', [c for c in CASES if c[0] != 'c1'])
+def test_generic_variant_matches_oracle(name, shape, dtype, rng, bh):
+    op = make_config(name, shape=shape, dtype=dtype, boundary_handling=bh)
+    res, fn = run_op(op, shape, rng[0], rng[1], seed=2, variant='generic')
+    tol = TOL[dtype] * (50 if name == 'c5' else 1)
+    for k, v in res.items():
+        assert v <= tol, (name, shape, bh, k, v)
+
+
+def test_march_variant_is_used_for_aligned_shapes():
+    op = make_config('c3', shape=(16, 32, 128), dtype='float32')
+    res, fn = run_op(op, (16, 32, 128), -1, 1, seed=3)
+    assert fn.forward_kernel.last_variant == 'march'
+    assert fn.backward_kernel.last_variant == 'march'
+
+
+@pytest.mark.parametrize('name,shape', [('c2', (12, 16)), ('c3', (6, 6, 8)), ('c4', (5, 6, 8))])
+def test_gradcheck_zeros_boundary(name, shape):
+    """Same gate as the reference (tests/test_tfmad.py:186-231: gradcheck, atol=1e-4, float64, 'zeros') but on
+    random non-zero inputs."""
+    import torch
+    op = make_config(name, shape=shape, dtype='float64', boundary_handling='zeros')
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    torch.manual_seed(0)
+    tens = tuple(torch.randn(*shape, dtype=torch.float64, device='cuda', requires_grad=True)
+                 for _ in op.forward_input_fields)
+    assert torch.autograd.gradcheck(fn.apply, tens, atol=1e-4, raise_exception=True)
