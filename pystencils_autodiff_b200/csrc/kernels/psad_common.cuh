@@ -22,6 +22,9 @@ PSAD_DEV void psad_mbar_arrive_expect_tx(psad_u64* bar, psad_u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(psad_smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+PSAD_DEV void psad_mbar_arrive(psad_u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(psad_smem_u32(bar)) : "memory");
+}
 PSAD_DEV void psad_mbar_wait(psad_u64* bar, psad_u32 parity) {
   asm volatile(
       "{\n"

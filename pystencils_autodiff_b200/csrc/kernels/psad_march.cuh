@@ -3,16 +3,21 @@
 // One persistent CTA per resident slot walks a static round-robin list of work items.  A work item is an (y, x)
 // tile of TY x TX cells marched along z over a chunk of planes (3-D), or a column of TX cells marched over row
 // tiles of TY rows (2-D).  For every step of the march one haloed box per input field is staged by TMA
-// (cp.async.bulk.tensor, zero fill outside the array = the reference's 'zeros' boundary handling) into a ring of
-// STAGES shared-memory slots; completion is signalled on one mbarrier per slot.  One elected thread issues the
-// loads LA = STAGES - (HZL + HZH) - 1 steps ahead of the consumers, across work-item boundaries, so the queue of
-// outstanding HBM requests never drains.  The per-step arithmetic — register windows along z, 128-bit shared
-// loads, warp-shuffle x-halos, 128-bit streaming stores — is emitted per stencil by emit.py as psad_step().
+// (cp.async.bulk.tensor; zero fill outside the array = the reference's 'zeros' boundary handling) into a ring of
+// STAGES shared-memory slots.
+//
+// Warp specialisation: the last warp of the CTA is the producer — one elected lane streams the boxes of all the
+// CTA's work items, back to back across item boundaries, and blocks only on the per-slot `empty` mbarrier.  The
+// other warps are consumers: each waits on the slot's `full` mbarrier (TMA complete_tx), runs the per-step body
+// psad_step() emitted for the stencil (register window along z, 128-bit shared loads, warp-shuffle x-halos,
+// 128-bit streaming stores) and arrives on the `empty` barrier of the slot it will not read from shared memory
+// again.  There is no CTA-wide barrier in the steady state, so consumer warps drift apart by up to the ring depth
+// and the queue of outstanding HBM requests never drains.
 //
 // The including translation unit defines, before this header:
-//   namespace cfg { NDIM, TX, TY, RY, SX, THREADS, MIN_CTAS, STAGES, HZL, HZH, NTMA, STAGE_BYTES,
-//                   F_OFF[], F_BYTES[], F_ORGX[], F_ORGY[], TX_BYTES }
-//   struct PsadCarry;  psad_step(...);  PSAD_KERNEL_NAME
+//   namespace cfg { NDIM, TX, TY, THREADS (consumer threads), MIN_CTAS, STAGES, HZL, HZH, JREL, NP, NTMA,
+//                   STAGE_BYTES, TX_BYTES, F_OFF[], F_ORGX[], F_ORGY[] }
+//   struct PsadCarry;  psad_item_begin(...);  psad_step(...);  PSAD_KERNEL_NAME
 #ifndef PSAD_MARCH_CUH
 #define PSAD_MARCH_CUH
 
@@ -21,30 +26,30 @@ struct PsadTmaps {
 };
 
 struct PsadItem {
-  long long x0, y0;        // tile origin (y0 only meaningful for NDIM == 3)
-  long long p_first, p_last;  // first / last plane (3-D) or row-tile (2-D) to stage
-  long long z0;            // first output plane of the item
+  int x0, y0;            // tile origin (y0 only meaningful for NDIM == 3)
+  int p_first, p_last;   // first / last plane (3-D) or row-tile (2-D) to stage
+  int z0;                // first output plane of the item
 };
 
 PSAD_DEV PsadItem psad_decode_item(const PsadArgs& A, long long item) {
   PsadItem it;
-  const long long tx = item % A.tiles_x;
-  long long rest = item / A.tiles_x;
+  const int tx = (int)(item % A.tiles_x);
+  const long long rest = item / A.tiles_x;
   it.x0 = tx * cfg::TX;
   if (cfg::NDIM == 3) {
-    const long long ty = rest % A.tiles_y;
-    const long long c = rest / A.tiles_y;
+    const int ty = (int)(rest % A.tiles_y);
+    const int c = (int)(rest / A.tiles_y);
     it.y0 = ty * cfg::TY;
-    it.z0 = A.wr_lo[0] + c * A.chunk;
-    long long z1 = it.z0 + A.chunk;
-    if (z1 > A.wr_hi[0]) z1 = A.wr_hi[0];
+    it.z0 = (int)A.wr_lo[0] + c * A.chunk;
+    int z1 = it.z0 + A.chunk;
+    if (z1 > (int)A.wr_hi[0]) z1 = (int)A.wr_hi[0];
     it.p_first = it.z0 - cfg::HZL;
     it.p_last = z1 - 1 + cfg::HZH;
   } else {
-    const long long c = rest;
+    const int c = (int)rest;
     it.y0 = 0;
     it.z0 = c * A.chunk;
-    long long k1 = it.z0 + A.chunk;
+    int k1 = it.z0 + A.chunk;
     if (k1 > A.tiles_y) k1 = A.tiles_y;
     it.p_first = it.z0;
     it.p_last = k1 - 1;
@@ -52,103 +57,97 @@ PSAD_DEV PsadItem psad_decode_item(const PsadArgs& A, long long item) {
   return it;
 }
 
-// Producer side: stage plane / row-tile `p` of item `it` into ring slot `slot`.
-PSAD_DEV void psad_issue(const PsadTmaps& TM, unsigned char* ring, psad_u64* full, int slot, const PsadItem& it,
-                         long long p) {
-  psad_mbar_arrive_expect_tx(&full[slot], cfg::TX_BYTES);
-  unsigned char* base = ring + (long long)slot * cfg::STAGE_BYTES;
-#pragma unroll
-  for (int f = 0; f < cfg::NTMA; ++f) {
-    if (cfg::NDIM == 3) {
-      psad_tma_load_3d(base + cfg::F_OFF[f], &TM.m[f], &full[slot], (int)it.x0 + cfg::F_ORGX[f],
-                       (int)it.y0 + cfg::F_ORGY[f], (int)p);
-    } else {
-      psad_tma_load_2d(base + cfg::F_OFF[f], &TM.m[f], &full[slot], (int)it.x0 + cfg::F_ORGX[f],
-                       (int)(p * cfg::TY) + cfg::F_ORGY[f]);
-    }
-  }
-}
-
-extern "C" __global__ void __launch_bounds__(cfg::THREADS, cfg::MIN_CTAS)
+extern "C" __global__ void __launch_bounds__(cfg::THREADS + 32, cfg::MIN_CTAS)
 PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ PsadTmaps TM) {
   extern __shared__ __align__(1024) unsigned char psad_smem[];
   unsigned char* ring = psad_smem;
   psad_u64* full = reinterpret_cast<psad_u64*>(psad_smem + (long long)cfg::STAGES * cfg::STAGE_BYTES);
+  psad_u64* empty = full + cfg::STAGES;
 
   constexpr int D = cfg::HZL + cfg::HZH;
-  constexpr int LA = cfg::STAGES - D - 1;
-  static_assert(LA >= 1, "ring too small");
+  constexpr int NWARPS = cfg::THREADS / 32;        // consumer warps
+  constexpr int REL_BACK = D - cfg::JREL;          // the slot released at a step holds the plane staged REL_BACK steps ago
+  static_assert(cfg::STAGES >= REL_BACK + 2, "ring too small");
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int wy = tid >> 5;
+  const int warp = tid >> 5;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < cfg::STAGES; ++s) psad_mbar_init(&full[s], 1);
+    for (int s = 0; s < cfg::STAGES; ++s) {
+      psad_mbar_init(&full[s], 1);
+      psad_mbar_init(&empty[s], NWARPS);
+    }
     psad_fence_barrier_init();
-#pragma unroll
-    for (int f = 0; f < cfg::NTMA; ++f) psad_tma_prefetch_desc(&TM.m[f]);
   }
   __syncthreads();
 
-  // ---- producer cursor (thread 0 only): next (item, plane) to stage and the ring slot it goes to
-  long long pc_item = blockIdx.x;
-  PsadItem pc_it;
-  long long pc_p = 0;
-  int pc_slot = 0;
-  bool pc_valid = pc_item < A.n_items;
-  if (tid == 0 && pc_valid) {
-    pc_it = psad_decode_item(A, pc_item);
-    pc_p = pc_it.p_first;
+  if (warp == NWARPS) {
+    // ================= producer warp =================
+    if (lane == 0) {
+#pragma unroll
+      for (int f = 0; f < cfg::NTMA; ++f) psad_tma_prefetch_desc(&TM.m[f]);
+      int slot = 0;
+      psad_u32 parity = 1;  // the first pass over the ring does not wait (barrier phase -1 counts as complete)
 #pragma unroll 1
-    for (int i = 0; i < LA && pc_valid; ++i) {
-      psad_issue(TM, ring, full, pc_slot, pc_it, pc_p);
-      pc_slot = (pc_slot + 1 == cfg::STAGES) ? 0 : pc_slot + 1;
-      if (++pc_p > pc_it.p_last) {
-        pc_item += gridDim.x;
-        pc_valid = pc_item < A.n_items;
-        if (pc_valid) {
-          pc_it = psad_decode_item(A, pc_item);
-          pc_p = pc_it.p_first;
+      for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+        const PsadItem it = psad_decode_item(A, item);
+#pragma unroll 1
+        for (int p = it.p_first; p <= it.p_last; ++p) {
+          psad_mbar_wait(&empty[slot], parity);
+          psad_mbar_arrive_expect_tx(&full[slot], cfg::TX_BYTES);
+          unsigned char* base = ring + slot * cfg::STAGE_BYTES;
+#pragma unroll
+          for (int f = 0; f < cfg::NTMA; ++f) {
+            if (cfg::NDIM == 3) {
+              psad_tma_load_3d(base + cfg::F_OFF[f], &TM.m[f], &full[slot], it.x0 + cfg::F_ORGX[f],
+                               it.y0 + cfg::F_ORGY[f], p);
+            } else {
+              psad_tma_load_2d(base + cfg::F_OFF[f], &TM.m[f], &full[slot], it.x0 + cfg::F_ORGX[f],
+                               p * cfg::TY + cfg::F_ORGY[f]);
+            }
+          }
+          if (++slot == cfg::STAGES) {
+            slot = 0;
+            parity ^= 1;
+          }
         }
       }
     }
+    return;
   }
 
-  // ---- consumers
+  // ================= consumer warps =================
   int slot = 0;          // ring slot of the newest plane of this step
-  psad_u32 parity = 0;   // phase parity of that slot
+  psad_u32 parity = 0;   // phase parity of that slot's full barrier
+  int warm = REL_BACK;   // steps until the first slot release (stream start only)
+  int ph = 0;            // step index mod cfg::NP: which register-window slot receives the newest plane
   PsadCarry R;
 #pragma unroll 1
   for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
     const PsadItem it = psad_decode_item(A, item);
+    if (cfg::NDIM == 3) psad_item_begin(A, R, lane, warp, it.y0, it.x0);
 #pragma unroll 1
-    for (long long p = it.p_first; p <= it.p_last; ++p) {
-      __syncthreads();  // every thread is done with the previous step: its oldest slot may be refilled
-      if (tid == 0 && pc_valid) {
-        psad_issue(TM, ring, full, pc_slot, pc_it, pc_p);
-        pc_slot = (pc_slot + 1 == cfg::STAGES) ? 0 : pc_slot + 1;
-        if (++pc_p > pc_it.p_last) {
-          pc_item += gridDim.x;
-          pc_valid = pc_item < A.n_items;
-          if (pc_valid) {
-            pc_it = psad_decode_item(A, pc_item);
-            pc_p = pc_it.p_first;
-          }
-        }
-      }
+    for (int p = it.p_first; p <= it.p_last; ++p) {
       psad_mbar_wait(&full[slot], parity);
-      const long long zo = p - cfg::HZH;  // output plane (3-D) / row tile (2-D) of this step
+      const int zo = p - cfg::HZH;  // output plane (3-D) / row tile (2-D) of this step
+      // the slot whose plane is read from shared memory for the last time in this step
+      int rel = slot - REL_BACK;
+      if (rel < 0) rel += cfg::STAGES;
+      psad_u64* rel_bar = (warm == 0) ? &empty[rel] : (psad_u64*)0;
+      if (warm > 0) --warm;
       if (cfg::NDIM == 3) {
-        psad_step(A, ring, slot, R, lane, wy, zo >= it.z0, zo, it.y0, it.x0);
+        psad_step(A, ring, slot, R, lane, warp, zo >= it.z0, zo, it.y0, it.x0, rel_bar, ph);
       } else {
-        psad_step(A, ring, slot, R, lane, wy, true, 0, zo * cfg::TY, it.x0);
+        psad_item_begin(A, R, lane, warp, zo * cfg::TY, it.x0);
+        psad_step(A, ring, slot, R, lane, warp, true, 0, zo * cfg::TY, it.x0, rel_bar, ph);
       }
       if (++slot == cfg::STAGES) {
         slot = 0;
         parity ^= 1;
       }
+      if (++ph == cfg::NP) ph = 0;
     }
   }
 }

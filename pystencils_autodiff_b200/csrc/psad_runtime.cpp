@@ -301,6 +301,7 @@ struct psad_kernel {
   CUmodule module = nullptr;
   CUfunction fn = nullptr;
   int sm_count = 0;
+  int occupancy = 1;  // resident CTAs per SM for this kernel (march: persistent grid = sm_count * occupancy)
   std::string name;
 };
 
@@ -332,6 +333,10 @@ extern "C" int psad_kernel_create(const char* source, const char* kernel_name, c
   CUdevice dev;
   g_drv.cuCtxGetDevice(&dev);
   g_drv.cuDeviceGetAttribute(&k->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
+  int occ = 0;
+  if (g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k->fn, plan->threads, (size_t)plan->smem_bytes) == 0 && occ > 0)
+    k->occupancy = occ;
+  if (plan->ctas_per_sm > 0 && plan->ctas_per_sm < k->occupancy) k->occupancy = plan->ctas_per_sm;
   *out = k;
   return 0;
 }
@@ -426,18 +431,36 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
     A.tiles_x = (int)cdiv(A.shape[2], P.tile_x);
     A.tiles_y = (int)cdiv(A.shape[1], P.tile_y);
     long long span = (nd == 3) ? (A.wr_hi[0] - A.wr_lo[0]) : A.tiles_y;
-    // balance: pick the number of chunks so that the static round-robin fills the persistent grid evenly
-    long long chunk = P.chunk > 0 ? P.chunk : span;
-    if (chunk > span) chunk = span;
-    long long n_chunks = cdiv(span, chunk);
-    chunk = cdiv(span, n_chunks);
+    const long long tiles = (long long)A.tiles_x * (nd == 3 ? A.tiles_y : 1);
+    const long long cap = (long long)k->sm_count * k->occupancy;
+    long long n_chunks;
+    if (P.chunk > 0) {
+      n_chunks = cdiv(span, P.chunk);
+    } else {
+      // Static round-robin over a persistent grid: pick the chunk count that minimises the steps of the busiest
+      // CTA, ceil(items / grid) * (chunk + warm-up planes).  Long chunks amortise the HZL+HZH warm-up planes,
+      // many chunks even out the tail.
+      const long long warm = (nd == 3) ? P.reserved[0] : 0;
+      long long best = -1, best_nc = 1;
+      const long long max_nc = span < 512 ? span : 512;
+      for (long long nc = 1; nc <= max_nc; ++nc) {
+        const long long ch = cdiv(span, nc);
+        if (cdiv(span, ch) != nc) continue;
+        if (nd == 3 && ch < 8 && nc > 1) break;
+        const long long cost = cdiv(tiles * nc, cap) * (ch + warm);
+        if (best < 0 || cost < best) { best = cost; best_nc = nc; }
+      }
+      n_chunks = best_nc;
+    }
+    long long chunk = cdiv(span, n_chunks);
     n_chunks = cdiv(span, chunk);
     A.chunk = (int)chunk;
     A.n_chunks = (int)n_chunks;
-    A.n_items = (long long)A.tiles_x * (nd == 3 ? A.tiles_y : 1) * n_chunks;
-    long long cap = (long long)k->sm_count * (P.ctas_per_sm > 0 ? P.ctas_per_sm : 1);
+    A.n_items = tiles * n_chunks;
     grid = (unsigned)(A.n_items < cap ? A.n_items : cap);
     int n_tma = 0;
+    // L2 promotion of TMA requests: 0 none, 1 64B, 2 128B, 3 256B (PSAD_L2PROMO overrides for experiments)
+    static const int l2promo = getenv("PSAD_L2PROMO") ? atoi(getenv("PSAD_L2PROMO")) : 3;
     for (int f = 0; f < n_fields; ++f) {
       const psad_field_plan_t& fp = P.field[f];
       if (A.stride[f][2] != 1) return fail(PSAD_ERR_INVALID, "%s: field %d is not contiguous along x", k->name.c_str(), f);
@@ -454,7 +477,7 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
         if (box[d] < 1 || box[d] > 256) return fail(PSAD_ERR_INVALID, "TMA box dim %d = %u out of range", d, box[d]);
       CUresult r = g_drv.cuTensorMapEncodeTiled(&TM.m[n_tma], fp.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                                                 (unsigned)nd, A.ptr[f], gdim, gstr, box, estr,
-                                                /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion 256B*/ 3, /*oob fill: zeros*/ 0);
+                                                /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion*/ l2promo, /*oob fill: zeros*/ 0);
       if (r != 0) return cu_fail(r, "cuTensorMapEncodeTiled");
       ++n_tma;
     }
@@ -465,6 +488,9 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   }
   (void)n_params;
   if (grid == 0) return 0;
+  if (getenv("PSAD_DEBUG"))
+    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d\n", k->name.c_str(), grid,
+            P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy);
   CUresult r = g_drv.cuLaunchKernel(k->fn, grid, 1, 1, (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
   if (r != 0) return cu_fail(r, "cuLaunchKernel");
   g_launches.fetch_add(1);

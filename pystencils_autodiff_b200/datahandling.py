@@ -1,0 +1,428 @@
+"""Slab-decomposed data handling with NCCL ghost-layer exchange.
+
+The reference has no distributed code: ``GraphDataHandling`` only *records* ``Communication(field, stencil, gpu)``
+markers (/root/reference/src/pystencils_autodiff/graph_datahandling.py:87-91,305-316) while pystencils' serial
+data handling does an in-process periodic copy, and ``PyTorchDataHandling.run_kernel`` simply calls the kernel with
+all registered arrays (framework_integration/datahandling.py:185-188).  This module is where that marker becomes a
+real exchange:
+
+* every field is split along dim 0 (the slowest stride) into one slab per rank / GPU, stored with ``g`` ghost planes
+  on each side — a ghost slab is one contiguous block, so faces are sent and received in place, no pack kernels;
+* ``synchronization_function`` exchanges the boundary planes with the +-1 neighbours with grouped
+  ``ncclSend``/``ncclRecv`` on a dedicated stream (C ABI: ``psad_halo_exchange``), or with ``torch.distributed``
+  point-to-point ops (``backend='torch'``, which is what the CPU/gloo tests drive);
+* kernels run on sub-ranges of the slab: interior planes while the halos are in flight, the ``g`` boundary planes
+  on each side after the receive has completed (``cudaStreamWaitEvent``);
+* because the adjoint is in gather form (TF-MAD) the backward pass needs the *same* exchange on ``diff<out>`` and
+  nothing else — no reverse accumulation, no atomics.
+
+Global boundary: ``'zeros'`` — the outermost ghost planes are never received and stay zero, which is exactly the
+out-of-bounds-is-zero rule; ``None`` — the iteration range of the first / last rank is clipped to the global
+interior.
+"""
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+
+from . import runtime
+from .backends._torch_native import CompiledKernel, numpy_dtype_to_torch
+
+__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'SlabStencilOp']
+
+
+class SlabDecomposition:
+    """Pure index logic of the 1-D decomposition along dim 0."""
+
+    def __init__(self, global_shape, rank, world_size, ghost_layers):
+        self.global_shape = tuple(int(s) for s in global_shape)
+        self.rank, self.world_size, self.g = int(rank), int(world_size), int(ghost_layers)
+        n0 = self.global_shape[0]
+        base, rem = divmod(n0, world_size)
+        self.counts = [base + (1 if r < rem else 0) for r in range(world_size)]
+        self.starts = [sum(self.counts[:r]) for r in range(world_size)]
+        self.n_local = self.counts[rank]
+        self.start = self.starts[rank]
+        if world_size > 1 and min(self.counts) < max(1, 2 * self.g):
+            raise ValueError('slabs of %d planes are too thin for %d ghost layers' % (min(self.counts), self.g))
+
+    @property
+    def lo_rank(self):
+        return self.rank - 1 if self.rank > 0 else -1
+
+    @property
+    def hi_rank(self):
+        return self.rank + 1 if self.rank < self.world_size - 1 else -1
+
+    @property
+    def local_shape(self):
+        """Shape of the local array including ghost planes."""
+        return (self.n_local + 2 * self.g,) + self.global_shape[1:]
+
+    @property
+    def owned(self):
+        return slice(self.g, self.g + self.n_local)
+
+    def ranges(self, boundary, ghost_width_of_kernel, ndim):
+        """(interior, lo, hi) launch ranges in local coordinates (``psad_range_t`` dicts); lo/hi may be None.
+
+        ``boundary``: 'zeros' | 'none'; ``ghost_width_of_kernel``: iteration margin of the kernel in 'none' mode."""
+        g, n = self.g, self.n_local
+        shape = self.local_shape[:ndim]
+        full_lo = [0] * ndim
+        full_hi = list(shape)
+        it_lo, it_hi = list(full_lo), list(full_hi)
+        if boundary == 'none' and ghost_width_of_kernel > 0:
+            m = ghost_width_of_kernel
+            for d in range(1, ndim):
+                it_lo[d], it_hi[d] = m, shape[d] - m
+            glo = max(m, self.start) - self.start + g
+            ghi = min(self.global_shape[0] - m, self.start + n) - self.start + g
+            it_lo[0], it_hi[0] = glo, max(glo, ghi)
+        else:
+            it_lo[0], it_hi[0] = g, g + n
+
+        def rng(z0, z1):
+            if z1 <= z0:
+                return None
+            return dict(iter_lo=[max(it_lo[0], z0)] + it_lo[1:], iter_hi=[max(max(it_lo[0], z0), min(it_hi[0], z1))] + it_hi[1:],
+                        write_lo=[z0] + full_lo[1:], write_hi=[z1] + full_hi[1:])
+
+        if self.world_size == 1 or g == 0:
+            return rng(g, g + n), None, None
+        lo_w = g if self.lo_rank >= 0 else 0
+        hi_w = g if self.hi_rank >= 0 else 0
+        interior = rng(g + lo_w, g + n - hi_w)
+        lo = rng(g, g + lo_w) if lo_w else None
+        hi = rng(g + n - hi_w, g + n) if hi_w else None
+        return interior, lo, hi
+
+
+class HaloExchanger:
+    """Neighbour exchange of ghost planes.  ``backend``: 'nccl' (C ABI, ``psad_halo_exchange``) or 'torch'
+    (``torch.distributed`` P2P, any backend incl. gloo on CPU tensors)."""
+
+    def __init__(self, decomposition, backend='nccl', group=None):
+        self.dec = decomposition
+        self.backend = backend
+        self.group = group
+        self._comm = None
+        if decomposition.world_size > 1 and backend == 'nccl':
+            self._init_nccl()
+
+    def _init_nccl(self):
+        import torch
+        import torch.distributed as dist
+        L = runtime.lib()
+        buf = (ctypes.c_ubyte * 128)()
+        if self.dec.rank == 0:
+            runtime.check(L.psad_nccl_unique_id(buf), 'psad_nccl_unique_id')
+        t = torch.tensor(list(buf), dtype=torch.uint8, device='cuda' if dist.get_backend(self.group) == 'nccl' else 'cpu')
+        dist.broadcast(t, src=0, group=self.group)
+        data = bytes(t.cpu().tolist())
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(data)
+        comm = ctypes.c_void_p()
+        runtime.check(L.psad_nccl_comm_create(buf, self.dec.rank, self.dec.world_size, ctypes.byref(comm)),
+                      'psad_nccl_comm_create')
+        self._comm = comm
+
+    def exchange(self, tensor, stream=None):
+        """Fill the ghost planes of ``tensor`` (local array incl. ghosts, contiguous) from the neighbours."""
+        dec = self.dec
+        g, n = dec.g, dec.n_local
+        if dec.world_size == 1 or g == 0:
+            return
+        lo_send, lo_recv = tensor[g:2 * g], tensor[0:g]
+        hi_send, hi_recv = tensor[n:n + g], tensor[n + g:n + 2 * g]
+        if self.backend == 'nccl':
+            nbytes = lo_send.numel() * lo_send.element_size()
+            runtime.check(runtime.lib().psad_halo_exchange(
+                self._comm, lo_send.data_ptr(), lo_recv.data_ptr(), hi_send.data_ptr(), hi_recv.data_ptr(),
+                nbytes, dec.lo_rank, dec.hi_rank, ctypes.c_void_p(stream)), 'psad_halo_exchange')
+        else:
+            import torch.distributed as dist
+            ops = []
+            if dec.lo_rank >= 0:
+                ops.append(dist.P2POp(dist.isend, lo_send.contiguous(), dec.lo_rank, self.group))
+                ops.append(dist.P2POp(dist.irecv, lo_recv, dec.lo_rank, self.group))
+            if dec.hi_rank >= 0:
+                ops.append(dist.P2POp(dist.isend, hi_send.contiguous(), dec.hi_rank, self.group))
+                ops.append(dist.P2POp(dist.irecv, hi_recv, dec.hi_rank, self.group))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def close(self):
+        if self._comm is not None:
+            runtime.lib().psad_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
+class SlabDataHandling:
+    """Array registry with the reference's data-handling vocabulary (``add_array``, ``fields``, ``run_kernel``,
+    ``synchronization_function``, ``swap``, ``fill``, ``gather_array``; graph_datahandling.py:202-327,
+    framework_integration/datahandling.py:54-200) on top of slab-decomposed CUDA tensors.  ``call_queue`` records
+    what was executed with the reference's event names (``KernelCall``, ``Communication``, ``Swap``)."""
+
+    def __init__(self, domain_size, rank=0, world_size=1, default_ghost_layers=1, device=None, backend='nccl',
+                 group=None):
+        import torch
+        self.torch = torch
+        self.dec = SlabDecomposition(domain_size, rank, world_size, default_ghost_layers)
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        self.device = torch.device(device)
+        self.exchanger = HaloExchanger(self.dec, backend, group)
+        self.gpu_arrays = OrderedDict()
+        self.fields = OrderedDict()
+        self.call_queue = []
+        self._comm_stream = None
+        self._ev_ready = None
+        self._ev_halo = None
+
+    # -- arrays ------------------------------------------------------------------------------------------------
+    @property
+    def dim(self):
+        return len(self.dec.global_shape)
+
+    @property
+    def shape(self):
+        return self.dec.global_shape
+
+    def add_array(self, name, values_per_cell=1, dtype=np.float32, **_):
+        from .field import Field
+        if name in self.gpu_arrays:
+            raise ValueError('GPU Field with this name already exists')
+        tail = () if values_per_cell in (1, (1,), ()) else (tuple(values_per_cell) if hasattr(values_per_cell, '__len__')
+                                                              else (int(values_per_cell),))
+        arr = self.torch.zeros(self.dec.local_shape + tail, dtype=numpy_dtype_to_torch(dtype), device=self.device)
+        self.gpu_arrays[name] = arr
+        self.fields[name] = Field.create_fixed_size(name, self.dec.local_shape + tail, index_dimensions=len(tail),
+                                                    dtype=dtype)
+        return self.fields[name]
+
+    def add_arrays(self, description, dtype=np.float32):
+        return tuple(self.add_array(n.strip(), dtype=dtype) for n in description.split(','))
+
+    def add_array_like(self, name, name_of_template_field):
+        t = self.gpu_arrays[name_of_template_field]
+        return self.add_array(name, dtype=np.dtype(str(t.dtype).replace('torch.', '')))
+
+    def fill(self, array_name, val, **_):
+        self.gpu_arrays[array_name][self.dec.owned] = val
+
+    def owned(self, name):
+        return self.gpu_arrays[name][self.dec.owned]
+
+    def swap(self, name1, name2, gpu=True):
+        self.call_queue.append(('Swap', name1, name2))
+        self.gpu_arrays[name1], self.gpu_arrays[name2] = self.gpu_arrays[name2], self.gpu_arrays[name1]
+
+    def gather_array(self, name):
+        """Global array on every rank (host numpy), ghost planes stripped."""
+        import torch.distributed as dist
+        local = self.owned(name).contiguous()
+        if self.dec.world_size == 1:
+            return local.cpu().numpy()
+        parts = [self.torch.empty((c,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+                 for c in self.dec.counts]
+        dist.all_gather(parts, local) if len(set(self.dec.counts)) == 1 else self._all_gather_uneven(parts, local)
+        return self.torch.cat(parts, 0).cpu().numpy()
+
+    def _all_gather_uneven(self, parts, local):
+        import torch.distributed as dist
+        for r in range(self.dec.world_size):
+            if r == self.dec.rank:
+                parts[r].copy_(local)
+            dist.broadcast(parts[r], src=r)
+
+    # -- communication ---------------------------------------------------------------------------------------------
+    def _streams(self):
+        if self._comm_stream is None:
+            self._comm_stream = self.torch.cuda.Stream(device=self.device)
+            self._ev_ready = self.torch.cuda.Event()
+            self._ev_halo = self.torch.cuda.Event()
+        return self._comm_stream
+
+    def synchronization_function(self, names, stencil=None, target='gpu', **_):
+        """Returns a callable that exchanges the ghost planes of ``names`` (reference: graph_datahandling.py:305-316
+        records ``Communication(field, stencil, gpu)`` and then runs pystencils' serial copy)."""
+        if isinstance(names, str):
+            names = [names]
+
+        def sync():
+            for n in names:
+                self.call_queue.append(('Communication', n, stencil, target == 'gpu'))
+                self.start_exchange(n)
+            self.finish_exchange()
+        return sync
+
+    def start_exchange(self, name):
+        """Asynchronous: exchange on the communication stream, ordered after everything already queued on the
+        current stream."""
+        if self.dec.world_size == 1 or self.dec.g == 0:
+            return
+        t = self.gpu_arrays[name]
+        if t.is_cuda:
+            comm = self._streams()
+            cur = self.torch.cuda.current_stream(self.device)
+            self._ev_ready.record(cur)
+            comm.wait_event(self._ev_ready)
+            if self.exchanger.backend == 'nccl':
+                self.exchanger.exchange(t, comm.cuda_stream)
+            else:
+                with self.torch.cuda.stream(comm):
+                    self.exchanger.exchange(t)
+            self._ev_halo.record(comm)
+        else:
+            self.exchanger.exchange(t)
+
+    def finish_exchange(self):
+        """Make the current stream wait for the halos (device-side dependency only, no host sync)."""
+        if self.dec.world_size == 1 or self.dec.g == 0 or self._comm_stream is None:
+            return
+        self.torch.cuda.current_stream(self.device).wait_event(self._ev_halo)
+
+    # -- kernels ---------------------------------------------------------------------------------------------------
+    def run_kernel(self, kernel, halo_fields=(), **kwargs):
+        """``kernel(**arrays, **kwargs)`` on the owned planes.  ``halo_fields``: inputs whose ghost planes must be
+        fresh — their exchange is overlapped with the interior planes of this kernel."""
+        if not isinstance(kernel, CompiledKernel):
+            raise TypeError('run_kernel expects a CompiledKernel (AutoDiffOp.forward_kernel_gpu / backward_kernel_gpu)')
+        self.call_queue.append(('KernelCall', kernel.function_name))
+        arrays = {f.name: self.gpu_arrays[f.name] for f in kernel.fields}
+        ir = kernel.ir
+        interior, lo, hi = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
+        for n in halo_fields:
+            self.call_queue.append(('Communication', n, None, True))
+            self.start_exchange(n)
+        if interior is not None:
+            kernel(**arrays, **kwargs, _range=interior)
+        if lo is not None or hi is not None:
+            self.finish_exchange()
+            for r in (lo, hi):
+                if r is not None:
+                    kernel(**arrays, **kwargs, _range=r)
+        elif halo_fields:
+            self.finish_exchange()
+
+
+class SlabStencilOp:
+    """Forward + adjoint of one ``AutoDiffOp`` on this rank's slab — what ``bench.py`` times.
+
+    ``local_shape`` is the owned (ghost-free) shape per rank; the global field is ``world_size`` such slabs stacked
+    along dim 0."""
+
+    def __init__(self, op, local_shape, rank=0, world_size=1, device=None, backend='nccl', tuning=None):
+        import torch
+        self.torch = torch
+        self.op = op
+        self.rank, self.world = rank, world_size
+        self.device = device
+        self.fwd = CompiledKernel(op.forward_ast_gpu, tuning)
+        self.bwd = CompiledKernel(op.backward_ast_gpu, tuning)
+        g = 0
+        if world_size > 1:
+            for ir in (op.forward_ast_gpu, op.backward_ast_gpu):
+                g = max(g, max(ir.max_halo[0]))
+        global_shape = (local_shape[0] * world_size,) + tuple(local_shape[1:])
+        self.dh = SlabDataHandling(global_shape, rank, world_size, g, device, backend)
+        self.exchange_kind = ('ncclSend/ncclRecv via psad_halo_exchange on a comm stream, overlapped with interior planes'
+                              if backend == 'nccl' else 'torch.distributed P2P')
+        self.local_shape = tuple(local_shape)
+        names = OrderedDict()
+        for f in list(op.forward_fields) + list(op.backward_fields):
+            names.setdefault(f.name, f)
+        for n, f in names.items():
+            self.dh.add_array(n, dtype=f.dtype.numpy_dtype)
+        fwd_ir, bwd_ir = op.forward_ast_gpu, op.backward_ast_gpu
+        self.fwd_halo = [f.name for f in fwd_ir.input_fields if max(fwd_ir.halo(f.name)[0]) > 0] if g else []
+        self.bwd_halo = [f.name for f in bwd_ir.input_fields if max(bwd_ir.halo(f.name)[0]) > 0] if g else []
+        self.fwd_scalars = {s: 1.0 for s in self.fwd.scalars}
+        self.bwd_scalars = {s: 1.0 for s in self.bwd.scalars}
+        self._fn = None
+        self._pinned = None
+
+    def randomize(self, generator):
+        """Synthetic inputs: forward inputs ~ U(0.1, 1), upstream gradients ~ N(0, 1)."""
+        for f in self.op.forward_input_fields:
+            self.dh.owned(f.name).copy_(self.torch.rand(self.local_shape, generator=generator, device=self.device,
+                                                        dtype=self.dh.gpu_arrays[f.name].dtype) * 0.9 + 0.1)
+        for f in self.op.backward_input_fields:
+            if f not in self.op.forward_input_fields:
+                self.dh.owned(f.name).copy_(self.torch.randn(self.local_shape, generator=generator, device=self.device,
+                                                             dtype=self.dh.gpu_arrays[f.name].dtype))
+
+    def forward(self):
+        self.dh.run_kernel(self.fwd, halo_fields=self.fwd_halo, **self.fwd_scalars)
+
+    def backward(self):
+        self.dh.run_kernel(self.bwd, halo_fields=self.bwd_halo, **self.bwd_scalars)
+
+    def variants(self):
+        return {'forward': self.fwd.last_variant, 'adjoint': self.bwd.last_variant}
+
+    # -- end-to-end with host buffers ----------------------------------------------------------------------------
+    def end_to_end(self, steps, barrier):
+        """Same metric through the public operator API with HOST (pinned) buffers: every step copies the forward
+        inputs and the upstream gradients host->device, runs forward + adjoint, and copies the outputs and the
+        input gradients device->host.  world_size == 1: ``Function.apply`` + ``torch.autograd.backward``;
+        world_size > 1: the slab operator (same kernels + halo exchange)."""
+        torch = self.torch
+        op = self.op
+        in_fields = list(op.forward_input_fields)
+        out_fields = list(op.forward_output_fields)
+        dt = {f.name: self.dh.gpu_arrays[f.name].dtype for f in in_fields + out_fields}
+        esize = {n: torch.empty((), dtype=d).element_size() for n, d in dt.items()}
+        cells = int(np.prod(self.local_shape))
+        # two pinned staging buffers (one per direction), reused for every field: synthetic data, honest byte counts
+        big = max(esize.values()) * cells
+        if self._pinned is None:
+            self._pinned = (torch.empty(big, dtype=torch.uint8, pin_memory=True),
+                            torch.empty(big, dtype=torch.uint8, pin_memory=True))
+            self._pinned[0].random_(0, 64)
+        h_in, h_out = self._pinned
+
+        def host_view(buf, name):
+            return buf[:esize[name] * cells].view(dt[name]).view(self.local_shape)
+
+        h2d = sum(esize[f.name] * cells for f in in_fields) + sum(esize[f.name] * cells for f in out_fields)
+        d2h = h2d
+        if self.world == 1:
+            if self._fn is None:
+                self._fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+            fn = self._fn
+
+            def step():
+                ins = [host_view(h_in, f.name).to(self.device, non_blocking=True).requires_grad_(True) for f in in_fields]
+                grads = [host_view(h_in, f.name).to(self.device, non_blocking=True) for f in out_fields]
+                outs = fn.apply(*ins)
+                torch.autograd.backward(outs, grads)
+                for f, o in zip(out_fields, outs):
+                    host_view(h_out, f.name).copy_(o.detach(), non_blocking=True)
+                for f, t in zip(in_fields, ins):
+                    host_view(h_out, f.name).copy_(t.grad, non_blocking=True)
+        else:
+            grad_names = [f.name for f in op.backward_input_fields if f not in op.forward_input_fields]
+            dnames = [f.name for f in op.backward_output_fields]
+
+            def step():
+                for f in in_fields:
+                    self.dh.owned(f.name).copy_(host_view(h_in, f.name), non_blocking=True)
+                for n, f in zip(grad_names, out_fields):
+                    self.dh.owned(n).copy_(host_view(h_in, f.name), non_blocking=True)
+                self.forward()
+                self.backward()
+                for f in out_fields:
+                    host_view(h_out, f.name).copy_(self.dh.owned(f.name), non_blocking=True)
+                for n, f in zip(dnames, in_fields):
+                    host_view(h_out, f.name).copy_(self.dh.owned(n), non_blocking=True)
+
+        step()
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            step()
+        end.record()
+        barrier()
+        return dict(ms_per_step=start.elapsed_time(end) / steps, h2d=h2d, d2h=d2h)

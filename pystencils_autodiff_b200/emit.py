@@ -27,7 +27,7 @@ from .field import Field
 from .ir import StencilKernelIR
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '1'
+EMITTER_VERSION = '3'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -201,9 +201,11 @@ class MarchTuning:
     sx: int = 0
     ry: int = 0
     ty: int = 0
-    lookahead: int = 3
+    lookahead: int = 3     # staged planes in flight ahead of the consumers (measured optimum on B200: 3)
+    stages: int = 0        # ring slots (0 = slots still being read + lookahead)
     chunk: int = 0
     min_ctas: int = 0
+    ctas_per_sm: int = 0   # cap on resident CTAs per SM (0 = whatever fits)
     carry: bool = True     # keep staged elements in registers while their plane moves through the stencil
     shuffle: bool = True   # x-halo elements from neighbouring lanes instead of shared memory
 
@@ -256,9 +258,8 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     if TY % RY:
         raise ValueError('ty must be a multiple of ry')
     THREADS = 32 * (TY // RY)
-    if THREADS > 1024:
+    if THREADS + 32 > 1024:
         raise ValueError('tile too tall: %d threads' % THREADS)
-    STAGES = D + 1 + max(1, t.lookahead)
 
     tma_fields = [f for f in fields if f in ir.input_fields]   # plan order: the runtime numbers tensor maps this way
     geo = {}
@@ -281,10 +282,6 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                            boxh=boxh, bytes=nbytes, off=off, T=_CT[f.dtype.numpy_dtype])
         off += -(-nbytes // 128) * 128
     STAGE_BYTES = off
-    smem_bytes = STAGES * STAGE_BYTES + 8 * STAGES
-    if smem_bytes > 227 * 1024:
-        raise ValueError('ring does not fit in shared memory (%d bytes)' % smem_bytes)
-
     # ---- register-window analysis ------------------------------------------------------------------------------
     # unit = ('U', row, v): aligned 16-byte vector v of the thread's own strip in tile row `row` (relative to the
     # thread's first row);  ('H', row, c): single halo element at strip column c (<0 or >=SX).
@@ -324,130 +321,181 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                 * (geo[f.name]['es'] // 4) for f in tma_fields for j in range(D + 1))
     words += sum(SX * (lhs.field.dtype.itemsize // 4) for lhs, _ in ir.main)
     est_regs = min(255, words + 48)
-    min_ctas = t.min_ctas or max(1, min(2048 // THREADS, (227 * 1024) // smem_bytes, 65536 // (THREADS * est_regs)))
+
+    # The window is addressed by *physical* plane slot k = (plane index) mod NP.  In phase PH = step mod NP the
+    # plane at stencil position j lives in slot (PH + j + 1) mod NP, so nothing has to be moved between steps: the
+    # step body is emitted NP times, once per phase, with the slot numbers baked in.
+    any_carry = any(carried[f.name][j] for f in tma_fields for j in range(D + 1))
+    NP = D + 1 if any_carry else 1
+    phase = [0]
 
     def arr(f, j, row):
         g = geo[f.name]
-        return 'R.f%d_p%d_r%d' % (g['ti'], j, row + g['hy'][0])
+        k = (phase[0] + j + 1) % NP if NP > 1 else j
+        return 'R.f%d_k%d_r%d' % (g['ti'], k, row + g['hy'][0])
 
     def elem(f, j, row, c):
         return '%s[%d]' % (arr(f, j, row), c + geo[f.name]['hx'][0])
 
     # ---- source -------------------------------------------------------------------------------------------------
+    jrel = min([j for j in range(D + 1) if any(fresh[f.name][j] for f in tma_fields)] or [D])
+    # ring = planes still read from shared memory (D - jrel + 1) + `lookahead` planes in flight ahead of them
+    STAGES = t.stages or (D - jrel + 1 + max(1, t.lookahead))
+    if STAGES < D - jrel + 2:
+        raise ValueError('ring too small')
+    smem_bytes = STAGES * STAGE_BYTES + 16 * STAGES
+    if smem_bytes > 227 * 1024:
+        raise ValueError('ring does not fit in shared memory (%d bytes)' % smem_bytes)
+    min_ctas = t.min_ctas or max(1, min(2048 // (THREADS + 32), (227 * 1024) // smem_bytes, 65536 // ((THREADS + 32) * est_regs)))
+    out_fields = ir.output_fields
     L = _header(ir, 'march')
     L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT, 'namespace cfg {',
-          'constexpr int NDIM = %d, TX = %d, TY = %d, RY = %d, SX = %d;' % (nd, TX, TY, RY, SX),
-          'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d;' % (THREADS, min_ctas, STAGES, HZL, HZH),
+          'constexpr int NDIM = %d, TX = %d, TY = %d;' % (nd, TX, TY),
+          'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d, JREL = %d, NP = %d;'
+          % (THREADS, min_ctas, STAGES, HZL, HZH, jrel, NP),
           'constexpr int NTMA = %d, STAGE_BYTES = %d, TX_BYTES = %d;' % (len(tma_fields), STAGE_BYTES,
                                                                          sum(geo[f.name]['bytes'] for f in tma_fields)),
           '__device__ constexpr int F_OFF[NTMA] = {%s};' % ', '.join(str(geo[f.name]['off']) for f in tma_fields),
           '__device__ constexpr int F_ORGX[NTMA] = {%s};' % ', '.join(str(-geo[f.name]['padl']) for f in tma_fields),
           '__device__ constexpr int F_ORGY[NTMA] = {%s};' % ', '.join(str(-geo[f.name]['hy'][0]) for f in tma_fields),
           '}  // namespace cfg', '']
-    # carry struct
+    # carry struct: register window + per-item masks / row pointers
     L.append('struct PsadCarry {')
     for f in tma_fields:
         g = geo[f.name]
-        rows = sorted({(j, u[1]) for j in range(D + 1) for u in held[f.name][j]})
         W = g['hx'][0] + SX + g['hx'][1]
-        for j, row in rows:
-            L.append('  %s f%d_p%d_r%d[%d];  // %s, plane %+d, row %+d' % (g['T'], g['ti'], j, row + g['hy'][0], W, f.name,
-                                                                        j - HZL, row))
+        if NP > 1:
+            all_rows = sorted({u[1] for j in range(D + 1) for u in held[f.name][j]})
+            for k in range(NP):
+                for row in all_rows:
+                    L.append('  %s f%d_k%d_r%d[%d];  // %s, window slot %d, row %+d' % (g['T'], g['ti'], k, row + g['hy'][0], W,
+                                                                                     f.name, k, row))
+        else:
+            for j, row in sorted({(j, u[1]) for j in range(D + 1) for u in held[f.name][j]}):
+                L.append('  %s f%d_k%d_r%d[%d];  // %s, plane %+d, row %+d' % (g['T'], g['ti'], j, row + g['hy'][0], W, f.name,
+                                                                            j - HZL, row))
+    L.append('  unsigned xmask, ymask_wr, ymask_it;  // per item: cells of this thread inside the iteration / write range')
+    L.append('  int xs, zlo, zhi;')
+    for f in out_fields:
+        L.append('  %s* o%d;  // %s: this thread\'s first cell at z = 0' % (_CT[f.dtype.numpy_dtype], fidx[f.name], f.name))
     L.append('};')
     L.append('')
-    L.append('PSAD_DEV void psad_step(const PsadArgs& A, const unsigned char* ring, int slot, PsadCarry& R, int lane,')
-    L.append('                        int wy, bool do_store, long long z, long long y0, long long x0)')
+    L.append('PSAD_DEV void psad_item_begin(const PsadArgs& A, PsadCarry& R, int lane, int wy, int y0, int x0)')
     L.append('{')
-    for i, s in enumerate(scalars):
-        L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s), i))
-    for j in range(D + 1):
-        if any(fresh[f.name][j] for f in tma_fields):
-            back = D - j
-            if back == 0:
-                L.append('  const unsigned char* st%d = ring + (long long)slot * cfg::STAGE_BYTES;' % j)
-            else:
-                L.append('  const unsigned char* st%d = ring + (long long)(slot >= %d ? slot - %d : slot - %d + cfg::STAGES) * cfg::STAGE_BYTES;'
-                         % (j, back, back, back))
-    # fresh loads
-    for j in range(D, -1, -1):
-        for f in tma_fields:
-            g = geo[f.name]
-            fr = fresh[f.name][j]
-            if not fr:
-                continue
-            rows = sorted({u[1] for u in fr})
-            for row in rows:
-                rp = 'p%d_%d_%d' % (g['ti'], j, row + g['hy'][0])
-                L.append('  const %s* %s = reinterpret_cast<const %s*>(st%d + %d) + (wy * %d + %d) * %d + %d + lane * %d;'
-                         % (g['T'], rp, g['T'], j, g['off'], RY, row + g['hy'][0], g['boxw'], g['padl'], SX))
-                for u in sorted(x for x in fr if x[0] == 'U' and x[1] == row):
-                    L.append('  psad_lds_vec<%s>(%s + %d, &%s);' % (g['T'], rp, u[2] * g['vec'], elem(f, j, row, u[2] * g['vec'])))
-                for u in sorted(x for x in fr if x[0] == 'H' and x[1] == row):
-                    c = u[2]
-                    if t.shuffle:
-                        if c < 0:
-                            L.append('  %s = psad_from_left(%s);' % (elem(f, j, row, c), elem(f, j, row, src_col(c))))
-                            L.append('  if (lane == 0) %s = %s[%d];' % (elem(f, j, row, c), rp, c))
-                        else:
-                            L.append('  %s = psad_from_right(%s);' % (elem(f, j, row, c), elem(f, j, row, src_col(c))))
-                            L.append('  if (lane == 31) %s = %s[%d];' % (elem(f, j, row, c), rp, c))
-                    else:
-                        L.append('  %s = %s[%d];' % (elem(f, j, row, c), rp, c))
-    # compute + store
-    L.append('  if (do_store) {')
-    if nd == 3:
-        L.append('    const bool zin = z >= A.it_lo[0] && z < A.it_hi[0];')
-    else:
-        L.append('    const bool zin = true;')
-    out_fields = ir.output_fields
-    for r in range(RY):
-        L.append('    {')
-        L.append('      const long long y = y0 + wy * %d + %d;' % (RY, r))
-        L.append('      if (y >= A.wr_lo[1] && y < A.wr_hi[1]) {')
-        L.append('        const bool yin = zin && y >= A.it_lo[1] && y < A.it_hi[1];')
-        for lhs, _ in ir.main:
-            L.append('        %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
-        for c in range(SX):
-            local = {}
-            for f in tma_fields:
-                for a in ir.read_accesses[f.name]:
-                    dz, dy, dx = _off3(a.offsets)
-                    local[a] = sp.Symbol('((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx))
-            for s in ir.scalars:
-                local[s] = sp.Symbol(_c_ident(s.name))
-            L.append('        {')
-            L.append('          const long long x = x0 + lane * %d + %d;' % (SX, c))
-            L.append('          const bool in = yin && x >= A.it_lo[2] && x < A.it_hi[2];')
-            for lhs, rhs in ir.subexpressions:
-                L.append('          const CT %s = %s;' % (_c_ident(lhs.name), pr.doprint(rhs.xreplace(local))))
-                local[lhs] = sp.Symbol(_c_ident(lhs.name))
-            for lhs, rhs in ir.main:
-                To = _CT[lhs.field.dtype.numpy_dtype]
-                L.append('          o%d[%d] = in ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, To,
-                                                                        pr.doprint(rhs.xreplace(local)), To))
-            L.append('        }')
-        for f in out_fields:
-            fi = fidx[f.name]
-            To = _CT[f.dtype.numpy_dtype]
-            vec = 16 // f.dtype.itemsize
-            L.append('        %s* q%d = reinterpret_cast<%s*>(A.ptr[%d]) + z * A.stride[%d][0] + y * A.stride[%d][1] + x0 + lane * %d;'
-                     % (To, fi, To, fi, fi, fi, SX))
-            for v in range(SX // vec):
-                L.append('        if (x0 + lane * %d + %d <= A.shape[2]) psad_stg_vec<%s>(q%d + %d, &o%d[%d]);'
-                         % (SX, (v + 1) * vec, To, fi, v * vec, fi, v * vec))
-        L.append('      }')
-        L.append('    }')
+    L.append('  const int xs = x0 + lane * %d;' % SX)
+    L.append('  const int ys = y0 + wy * %d;' % RY)
+    L.append('  R.xs = xs;')
+    L.append('  R.zlo = (int)A.it_lo[0];')
+    L.append('  R.zhi = (int)A.it_hi[0];')
+    L.append('  unsigned xm = 0, ymw = 0, ymi = 0;')
+    L.append('#pragma unroll')
+    L.append('  for (int c = 0; c < %d; ++c) xm |= (xs + c >= (int)A.it_lo[2] && xs + c < (int)A.it_hi[2]) ? (1u << c) : 0u;' % SX)
+    L.append('#pragma unroll')
+    L.append('  for (int r = 0; r < %d; ++r) {' % RY)
+    L.append('    ymw |= (ys + r >= (int)A.wr_lo[1] && ys + r < (int)A.wr_hi[1]) ? (1u << r) : 0u;')
+    L.append('    ymi |= (ys + r >= (int)A.it_lo[1] && ys + r < (int)A.it_hi[1]) ? (1u << r) : 0u;')
     L.append('  }')
-    # rotate the window
-    for j in range(D):
-        for f in tma_fields:
-            g = geo[f.name]
-            for u in sorted(carried[f.name][j]):
-                if u[0] == 'U':
-                    for c in range(u[2] * g['vec'], (u[2] + 1) * g['vec']):
-                        L.append('  %s = %s;' % (elem(f, j, u[1], c), elem(f, j + 1, u[1], c)))
+    L.append('  R.xmask = xm; R.ymask_wr = ymw; R.ymask_it = ymi;')
+    for f in out_fields:
+        fi = fidx[f.name]
+        L.append('  R.o%d = reinterpret_cast<%s*>(A.ptr[%d]) + (long long)ys * A.stride[%d][1] + xs;'
+                 % (fi, _CT[f.dtype.numpy_dtype], fi, fi))
+    L.append('}')
+    L.append('')
+    for ph in range(NP):
+        phase[0] = ph
+        L.append('PSAD_DEV void psad_step_ph%d(const PsadArgs& A, const unsigned char* ring, int slot, PsadCarry& R, int lane,' % ph)
+        L.append('                        int wy, bool do_store, int z, int y0, int x0, psad_u64* rel_bar)')
+        L.append('{')
+        for i, s_ in enumerate(scalars):
+            L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s_), i))
+        for j in range(D + 1):
+            if any(fresh[f.name][j] for f in tma_fields):
+                back = D - j
+                if back == 0:
+                    L.append('  const unsigned char* st%d = ring + slot * cfg::STAGE_BYTES;' % j)
                 else:
-                    L.append('  %s = %s;' % (elem(f, j, u[1], u[2]), elem(f, j + 1, u[1], u[2])))
+                    L.append('  const unsigned char* st%d = ring + (slot >= %d ? slot - %d : slot - %d + cfg::STAGES) * cfg::STAGE_BYTES;'
+                             % (j, back, back, back))
+        # fresh loads
+        for j in range(D, -1, -1):
+            for f in tma_fields:
+                g = geo[f.name]
+                fr = fresh[f.name][j]
+                if not fr:
+                    continue
+                rows = sorted({u[1] for u in fr})
+                for row in rows:
+                    rp = 'p%d_%d_%d' % (g['ti'], j, row + g['hy'][0])
+                    L.append('  const %s* %s = reinterpret_cast<const %s*>(st%d + %d) + (wy * %d + %d) * %d + %d + lane * %d;'
+                             % (g['T'], rp, g['T'], j, g['off'], RY, row + g['hy'][0], g['boxw'], g['padl'], SX))
+                    for u in sorted(x for x in fr if x[0] == 'U' and x[1] == row):
+                        L.append('  psad_lds_vec<%s>(%s + %d, &%s);' % (g['T'], rp, u[2] * g['vec'], elem(f, j, row, u[2] * g['vec'])))
+                    for u in sorted(x for x in fr if x[0] == 'H' and x[1] == row):
+                        c = u[2]
+                        if t.shuffle:
+                            if c < 0:
+                                L.append('  %s = psad_from_left(%s);' % (elem(f, j, row, c), elem(f, j, row, src_col(c))))
+                                L.append('  if (lane == 0) %s = %s[%d];' % (elem(f, j, row, c), rp, c))
+                            else:
+                                L.append('  %s = psad_from_right(%s);' % (elem(f, j, row, c), elem(f, j, row, src_col(c))))
+                                L.append('  if (lane == 31) %s = %s[%d];' % (elem(f, j, row, c), rp, c))
+                        else:
+                            L.append('  %s = %s[%d];' % (elem(f, j, row, c), rp, c))
+        # this warp will not touch the oldest still-read slot again: hand it back to the producer
+        L.append('  __syncwarp();')
+        L.append('  if (lane == 0 && rel_bar) psad_mbar_arrive(rel_bar);')
+        # compute + store
+        L.append('  if (do_store) {')
+        if nd == 3:
+            L.append('    const unsigned zm = (z >= R.zlo && z < R.zhi) ? R.ymask_it : 0u;')
+        else:
+            L.append('    const unsigned zm = R.ymask_it;')
+        for r in range(RY):
+            L.append('    if ((R.ymask_wr >> %d) & 1u) {' % r)
+            L.append('      const unsigned m = ((zm >> %d) & 1u) ? R.xmask : 0u;' % r)
+            for lhs, _ in ir.main:
+                L.append('      %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
+            for c in range(SX):
+                local = {}
+                for f in tma_fields:
+                    for a in ir.read_accesses[f.name]:
+                        dz, dy, dx = _off3(a.offsets)
+                        local[a] = sp.Symbol('((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx))
+                for s_ in ir.scalars:
+                    local[s_] = sp.Symbol(_c_ident(s_.name))
+                L.append('      {')
+                for lhs, rhs in ir.subexpressions:
+                    L.append('        const CT %s = %s;' % (_c_ident(lhs.name), pr.doprint(rhs.xreplace(local))))
+                    local[lhs] = sp.Symbol(_c_ident(lhs.name))
+                for lhs, rhs in ir.main:
+                    To = _CT[lhs.field.dtype.numpy_dtype]
+                    L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To,
+                                                                                       pr.doprint(rhs.xreplace(local)), To))
+                L.append('      }')
+            for f in out_fields:
+                fi = fidx[f.name]
+                To = _CT[f.dtype.numpy_dtype]
+                vec = 16 // f.dtype.itemsize
+                zterm = ' + (long long)z * A.stride[%d][0]' % fi if nd == 3 else ''
+                L.append('      %s* q%d = R.o%d%s + %d * A.stride[%d][1];' % (To, fi, fi, zterm, r, fi))
+                for v in range(SX // vec):
+                    L.append('      if (R.xs + %d <= (int)A.shape[2]) psad_stg_vec<%s>(q%d + %d, &o%d[%d]);'
+                             % ((v + 1) * vec, To, fi, v * vec, fi, v * vec))
+            L.append('    }')
+        L.append('  }')
+        L.append('}')
+        L.append('')
+    L.append('PSAD_DEV void psad_step(const PsadArgs& A, const unsigned char* ring, int slot, PsadCarry& R, int lane,')
+    L.append('                        int wy, bool do_store, int z, int y0, int x0, psad_u64* rel_bar, int ph)')
+    L.append('{')
+    if NP == 1:
+        L.append('  psad_step_ph0(A, ring, slot, R, lane, wy, do_store, z, y0, x0, rel_bar);')
+    else:
+        L.append('  switch (ph) {')
+        for ph in range(NP):
+            L.append('    case %d: psad_step_ph%d(A, ring, slot, R, lane, wy, do_store, z, y0, x0, rel_bar); break;' % (ph, ph))
+        L.append('  }')
     L.append('}')
     L.append('')
     L.append('#define PSAD_KERNEL_NAME %s' % name)
@@ -460,8 +508,8 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
         return dict(elem_size=f.dtype.itemsize, is_input=int(is_in), is_output=int(f in ir.output_fields), index_size=1,
                     tma=int(is_in), box=(g['boxw'], g['boxh'], 1) if is_in else (0, 0, 0))
 
-    plan = dict(kind=1, ndim=nd, n_fields=len(fields), n_scalars=len(scalars), threads=THREADS, smem_bytes=smem_bytes,
-                tile_x=TX, tile_y=TY, chunk=t.chunk, ctas_per_sm=0, boundary=1 if ir.boundary == 'zeros' else 0,
+    plan = dict(kind=1, ndim=nd, n_fields=len(fields), n_scalars=len(scalars), threads=THREADS + 32, smem_bytes=smem_bytes,
+                tile_x=TX, tile_y=TY, chunk=t.chunk, ctas_per_sm=t.ctas_per_sm, warmup=D, boundary=1 if ir.boundary == 'zeros' else 0,
                 ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
     ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
     ek.geometry = dict(TX=TX, TY=TY, RY=RY, SX=SX, STAGES=STAGES, STAGE_BYTES=STAGE_BYTES, HZ=(HZL, HZH),

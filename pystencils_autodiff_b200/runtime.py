@@ -110,6 +110,7 @@ def make_plan(p):
     for k in ('kind', 'ndim', 'n_fields', 'n_scalars', 'threads', 'smem_bytes', 'tile_x', 'tile_y', 'chunk',
               'ctas_per_sm', 'boundary', 'ghost_layers'):
         setattr(plan, k, int(p[k]))
+    plan.reserved[0] = int(p.get('warmup', 0))
     for i, f in enumerate(p['fields']):
         fp = plan.field[i]
         for k in ('elem_size', 'is_input', 'is_output', 'index_size', 'tma'):

@@ -29,7 +29,7 @@ def main():
     for kv in os.environ.get('PSAD_TUNE', '').split(','):
         if kv:
             k, v = kv.split('=')
-            tun[k] = int(v)
+            tun[k] = bool(int(v)) if k in ("carry", "shuffle") else int(v)
     tuning = MarchTuning(**tun) if tun else None
     op = make_config(name, shape=shape)
     dev = torch.device('cuda:0')
@@ -41,7 +41,7 @@ def main():
         tensors = {f.name: torch.rand(shape, dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=dev) + 0.5
                    for f in k.fields}
         scal = {s: 1.0 for s in k.scalars}
-        for variant in k.variants:
+        for variant in (["march"] if os.environ.get("PSAD_MARCH_ONLY") and "march" in k.variants else k.variants):
             med, best = time_kernel(k, tensors, scal, variant=variant)
             bpc = ir.bytes_per_cell()
             attrs = k.native(variant).attributes()
