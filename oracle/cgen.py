@@ -57,7 +57,7 @@ def generate_c(assignments, boundary_handling=None, function_name='kernel', open
     ``strides[f*4 + d]`` in elements."""
     ac = coerce_assignments(assignments)
     mode = _mode(boundary_handling)
-    reads = sorted([s for s in ac.free_symbols if isinstance(s, Field.Access)], key=str)
+    reads = sorted(set().union(*[a.rhs.atoms(Field.Access) for a in ac.all_assignments]), key=str)
     writes = [a.lhs for a in ac.main_assignments]
     scalars = sorted([s for s in ac.free_symbols if not isinstance(s, Field.Access)], key=str)
     out_fields = sorted({w.field for w in writes}, key=str)
@@ -172,6 +172,6 @@ def compile_c(assignments, boundary_handling=None, function_name='kernel', flavo
         tmp = so_path + '.tmp%d' % os.getpid()
         subprocess.check_call(['gcc'] + flags + ['-shared', '-o', tmp, c_path, '-lm'])
         os.replace(tmp, so_path)
-    reads = [s for s in ac.free_symbols if isinstance(s, Field.Access)]
+    reads = set().union(*[a.rhs.atoms(Field.Access) for a in ac.all_assignments])
     fields = {a.field for a in reads} | {a.lhs.field for a in ac.main_assignments}
     return CompiledCKernel(so_path, function_name, field_names, scalar_names, src, fields)

@@ -42,7 +42,8 @@ def _mode(boundary_handling):
 
 
 def _accesses(ac):
-    reads = sorted([s for s in ac.free_symbols if isinstance(s, Field.Access)], key=str)
+    # every access on a right-hand side, including a ``+=`` form's read of its own output (_autodiff.py:110-113)
+    reads = sorted(set().union(*[a.rhs.atoms(Field.Access) for a in ac.all_assignments]), key=str)
     writes = [a.lhs for a in ac.main_assignments]
     return reads, writes
 
@@ -150,7 +151,7 @@ def evaluate_literal(assignments, arrays, scalars=None, compute_dtype=np.float64
         return v.astype(compute_dtype)
 
     env = dict(ctr)
-    for s in ac.free_symbols:
+    for s in set(ac.free_symbols) | set(_accesses(ac)[0]):
         if isinstance(s, Field.Access):
             env[s] = access_value(s)
         elif s not in ctr:
@@ -198,7 +199,7 @@ def evaluate_loops(assignments, arrays, boundary_handling=None, scalars=None):
     for a in ac.main_assignments:
         f = a.lhs.field
         out.setdefault(f.name, np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=f.dtype.numpy_dtype))
-    all_syms = sorted(ac.free_symbols, key=str)
+    all_syms = sorted(set(ac.free_symbols) | set(reads), key=str)
     sub_fns = [(a.lhs, sp.lambdify(sorted(a.rhs.free_symbols, key=str), a.rhs, modules='math'),
                 sorted(a.rhs.free_symbols, key=str)) for a in ac.subexpressions]
     main_fns = [(a.lhs, sp.lambdify(sorted(a.rhs.free_symbols, key=str), a.rhs, modules='math'),

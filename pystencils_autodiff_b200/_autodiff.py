@@ -223,6 +223,14 @@ class AutoDiffOp:
         self._forward_output_fields = sorted(forward_assignments.bound_fields, key=by_name)
         self._backward_input_fields = sorted(self._backward_assignments.free_fields, key=by_name)
         self._backward_output_fields = sorted(self._backward_assignments.bound_fields, key=by_name)
+        if diff_mode == DiffModes.TRANSPOSED and not backward_assignments:
+            # the reference derives the lists from its field map in this mode (:430-437): adjoints of the forward
+            # outputs are "the" backward inputs (forward fields read by the coefficients are not listed) — kept,
+            # but in sorted instead of Python-set order
+            fmap = self._backward_field_map
+            self._backward_input_fields = [fmap[f] for f in self._forward_output_fields]
+            self._backward_output_fields = [fmap[f] for f in self._forward_input_fields
+                                            if not _is_constant(f, self._constant_fields)]
 
     # -- dunder --------------------------------------------------------------------------------------------
     def __hash__(self):

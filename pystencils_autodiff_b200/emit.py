@@ -27,7 +27,7 @@ from .field import Field
 from .ir import StencilKernelIR
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '3'
+EMITTER_VERSION = '5'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -41,7 +41,7 @@ class EmittedKernel:
     fields: List[Field]            # plan order: outputs then inputs
     scalars: List[str]
     plan: Dict = dc_field(default_factory=dict)
-    options: List[str] = dc_field(default_factory=list)
+    options: List[str] = dc_field(default_factory=lambda: ['-fmad=false'])
 
     @property
     def cache_key(self):
@@ -64,6 +64,65 @@ class _CudaPrinter(C99CodePrinter):
         super().__init__(settings={'type_aliases': alias})
         self._one = '1.0F' if np.dtype(compute_dtype) == np.float32 else '1.0'
         self._sqrt = 'sqrtf' if np.dtype(compute_dtype) == np.float32 else 'sqrt'
+        self.symmap = {}   # symbol -> C text; the *expression* (and so the order of every sum) stays in terms of the
+        #                    original access symbols, whatever register / variable they are mapped to
+
+    def _print_Symbol(self, expr):
+        if expr in self.symmap:
+            return self.symmap[expr]
+        return super()._print_Symbol(expr)
+
+    def print_with(self, expr, symmap):
+        self.symmap = symmap
+        try:
+            return self.doprint(expr)
+        finally:
+            self.symmap = {}
+
+    # Sums are printed as explicit fused-multiply-add chains and the kernels are compiled with -fmad=false, so the
+    # rounding of every cell is fixed by this printer and not by the compiler's per-instance contraction choices
+    # (the step body is instantiated once per window phase; all instances must agree bit for bit, and so must
+    # sharded and unsharded runs).  Long sums are split into independent accumulators to give the FMA pipes ILP.
+    def _print_Add(self, expr, order=None):
+        terms = list(sp.Add.make_args(expr))
+        if len(terms) < 2:
+            return super()._print_Add(expr, order=order)
+        terms.sort(key=lambda t_: sp.default_sort_key(t_))
+        n_acc = 1 if len(terms) <= 4 else (2 if len(terms) <= 9 else 4)
+        chains = [terms[i::n_acc] for i in range(n_acc)]
+        parts = [self._fma_chain(ch) for ch in chains if ch]
+        while len(parts) > 1:
+            parts = ['(%s + %s)' % (parts[i], parts[i + 1]) if i + 1 < len(parts) else parts[i]
+                     for i in range(0, len(parts), 2)]
+        return parts[0]
+
+    def _fma_chain(self, terms):
+        fma = 'fmaf' if self._one.endswith('F') else 'fma'
+        acc = None
+        for t_ in terms:
+            c, rest = t_.as_coeff_Mul()
+            if acc is None:
+                acc = self._print(t_)
+                if t_.is_Add:
+                    acc = '(%s)' % acc
+                continue
+            if rest == 1:
+                acc = '(%s + %s)' % (acc, self._print(c))
+            elif c == 1 and not rest.is_Mul:
+                acc = '(%s + %s)' % (acc, self._paren(rest))
+            elif c == -1 and not rest.is_Mul:
+                acc = '(%s - %s)' % (acc, self._paren(rest))
+            else:
+                if c != 1:
+                    a, b = c, rest
+                else:
+                    a, b = rest.args[0], sp.Mul(*rest.args[1:])
+                acc = '%s(%s, %s, %s)' % (fma, self._print(a), self._print(b), acc)
+        return acc
+
+    def _paren(self, e):
+        s_ = self._print(e)
+        return '(%s)' % s_ if (e.is_Add or e.is_Mul) else s_
 
     def _print_Pow(self, expr):
         b, e = expr.base, expr.exp
@@ -166,14 +225,14 @@ def emit_generic(ir: StencilKernelIR, threads=256) -> EmittedKernel:
                 L.append('      const CT %s = (%s) ? (CT)%s : (CT)0;' % (var, ' && '.join(conds), addr))
             else:
                 L.append('      const CT %s = (CT)%s;' % (var, addr))
-            local[a] = sp.Symbol(var)
+            local[a] = var
     for s in ir.scalars:
-        local[s] = sp.Symbol(_c_ident(s.name))
+        local[s] = _c_ident(s.name)
     for lhs, rhs in ir.subexpressions:
-        L.append('      const CT %s = %s;' % (_c_ident(lhs.name), pr.doprint(rhs.xreplace(local))))
-        local[lhs] = sp.Symbol(_c_ident(lhs.name))
+        L.append('      const CT %s = %s;' % (_c_ident(lhs.name), pr.print_with(rhs, local)))
+        local[lhs] = _c_ident(lhs.name)
     for k, (lhs, rhs) in enumerate(ir.main):
-        L.append('      o_%d = %s;' % (k, pr.doprint(rhs.xreplace(local))))
+        L.append('      o_%d = %s;' % (k, pr.print_with(rhs, local)))
     L.append('    }')
     for k, lhs in enumerate(outs):
         fi = fidx[lhs.field.name]
@@ -207,7 +266,8 @@ class MarchTuning:
     min_ctas: int = 0
     ctas_per_sm: int = 0   # cap on resident CTAs per SM (0 = whatever fits)
     carry: bool = True     # keep staged elements in registers while their plane moves through the stencil
-    shuffle: bool = True   # x-halo elements from neighbouring lanes instead of shared memory
+    shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
+    #                                  (default: yes for 4-byte fields, no for 8-byte fields — measured)
 
 
 def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
@@ -235,6 +295,9 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     if reason:
         raise ValueError('march variant not applicable: ' + reason)
     t = tuning or MarchTuning()
+    if t.shuffle is None:
+        import dataclasses
+        t = dataclasses.replace(t, shuffle=max(f.dtype.itemsize for f in ir.all_fields) == 4)
     name = _kernel_name(ir, 'march')
     CT = _CT[ir.compute_dtype]
     pr = _CudaPrinter(ir.compute_dtype)
@@ -245,7 +308,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     max_esize = max(f.dtype.itemsize for f in fields)
 
     # ---- geometry ------------------------------------------------------------------------------------------
-    SX = t.sx or 4                         # 4 cells per thread: one LDS.128 for fp32, two for fp64
+    SX = t.sx or (4 if max_esize == 4 else 2)   # cells per thread along x: one 16-byte vector of the widest type
     if (SX * min(f.dtype.itemsize for f in fields)) % 16:
         raise ValueError('sx*itemsize must be a multiple of 16 bytes')
     TX = 32 * SX
@@ -253,8 +316,14 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     mh3 = [(0, 0)] * (3 - nd) + list(mh)
     HZL, HZH = (mh3[0] if nd == 3 else (0, 0))
     D = HZL + HZH
-    RY = t.ry or (2 if max_esize == 4 else 1)
-    TY = t.ty or ((16 if nd == 3 else 32) if max_esize == 4 else 8)
+    # measured on B200 (scripts/sweep.py, profiles/): fp32 3-D 32x128 tiles / 2 rows per thread, fp32 2-D 16x128 / 1 row,
+    # fp64 16x64 tiles (sx=2) / 1 row
+    if max_esize == 4:
+        RY = t.ry or (2 if nd == 3 else 1)
+        TY = t.ty or (32 if nd == 3 else 16)
+    else:
+        RY = t.ry or 1
+        TY = t.ty or 16
     if TY % RY:
         raise ValueError('ty must be a multiple of ry')
     THREADS = 32 * (TY // RY)
@@ -461,17 +530,17 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                 for f in tma_fields:
                     for a in ir.read_accesses[f.name]:
                         dz, dy, dx = _off3(a.offsets)
-                        local[a] = sp.Symbol('((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx))
+                        local[a] = '((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx)
                 for s_ in ir.scalars:
-                    local[s_] = sp.Symbol(_c_ident(s_.name))
+                    local[s_] = _c_ident(s_.name)
                 L.append('      {')
                 for lhs, rhs in ir.subexpressions:
-                    L.append('        const CT %s = %s;' % (_c_ident(lhs.name), pr.doprint(rhs.xreplace(local))))
-                    local[lhs] = sp.Symbol(_c_ident(lhs.name))
+                    L.append('        const CT %s = %s;' % (_c_ident(lhs.name), pr.print_with(rhs, local)))
+                    local[lhs] = _c_ident(lhs.name)
                 for lhs, rhs in ir.main:
                     To = _CT[lhs.field.dtype.numpy_dtype]
                     L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To,
-                                                                                       pr.doprint(rhs.xreplace(local)), To))
+                                                                                       pr.print_with(rhs, local), To))
                 L.append('      }')
             for f in out_fields:
                 fi = fidx[f.name]

@@ -148,7 +148,9 @@ def lower_assignments(assignments, boundary_handling=None, function_name='kernel
         raise ValueError('no main assignments')
 
     clean = AssignmentCollection({l: r for l, r in main}, {l: r for l, r in subexpressions})
-    reads = sorted([s for s in clean.free_symbols if isinstance(s, Field.Access)], key=str)
+    # every access on a right-hand side — including a ``+=`` form's read of its own output, which pystencils'
+    # ``free_symbols`` (rhs symbols minus bound symbols) does not list
+    reads = sorted(set().union(*[r.atoms(Field.Access) for _, r in subexpressions + main]), key=str)
     writes = [l for l, _ in main]
     bound = {l for l, _ in subexpressions} | set(writes)
     scalars = sorted([s for s in clean.free_symbols if not isinstance(s, Field.Access)], key=str)

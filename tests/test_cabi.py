@@ -1,0 +1,87 @@
+"""The C-ABI shared library: loads without a GPU, exports every symbol include/psad.h declares, compiles cubins for
+sm_100a with NVRTC on a CPU-only machine, and fails loudly (no fallback) when asked to run without a driver."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pystencils_autodiff_b200 import runtime
+from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+from pystencils_autodiff_b200.configs import make_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    with open(os.path.join(ROOT, 'include', 'psad.h')) as fh:
+        text = fh.read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(psad_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(runtime.LIB_PATH)
+    names = _declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), 'libpsad.so does not export %s' % n
+
+
+def test_abi_version_and_struct_layout():
+    L = runtime.lib()
+    assert L.psad_abi_version() == runtime.PSAD_ABI_VERSION
+    # psad_field_plan_t: 12 int32; psad_plan_t: 21 int32 + 12 field plans; psad_field_arg_t: ptr + 7 int64
+    assert ctypes.sizeof(runtime.FieldPlan) == 12 * 4
+    assert ctypes.sizeof(runtime.Plan) == 21 * 4 + 12 * 48
+    assert ctypes.sizeof(runtime.FieldArg) == 8 + 7 * 8
+    assert ctypes.sizeof(runtime.Range) == 12 * 8
+
+
+def test_nvrtc_compiles_sm100a_cubin_without_gpu(tmp_path):
+    op = make_config('c3', shape=(16, 16, 128))
+    k = CompiledKernel(op.forward_ast_gpu)
+    assert k.variants == ['generic', 'march']
+    for v in k.variants:
+        ek = k.emitted(v)
+        key = ek.cache_key + '_t'
+        hit, log = runtime.compile_source(ek.source, key, list(ek.options) + ['--ptxas-options=-v'])
+        path = runtime.cubin_path(key)
+        assert os.path.getsize(path) > 1000
+        with open(path, 'rb') as fh:
+            assert fh.read(4) == b'\x7fELF'
+        if not hit:
+            assert 'sm_100a' in log
+        hit2, _ = runtime.compile_source(ek.source, key, list(ek.options) + ['--ptxas-options=-v'])
+        assert hit2
+        os.remove(path)
+
+
+def test_compile_error_is_reported_not_swallowed():
+    with pytest.raises(RuntimeError) as e:
+        runtime.compile_source('extern "C" __global__ void k() { this is not cuda; }', 'broken_kernel_test')
+    assert 'NVRTC' in str(e.value) and 'error' in str(e.value)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    op = make_config('c2', shape=(16, 32))
+    k = CompiledKernel(op.forward_ast_gpu)
+    with pytest.raises(RuntimeError) as e:
+        k.native('generic')
+    assert 'libcuda' in str(e.value) or 'driver' in str(e.value).lower()
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    with pytest.raises(Exception):
+        fn.apply(torch.zeros(16, 32))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'pystencils_autodiff_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cpp', '.cuh', '.h')):
+                with open(os.path.join(dirpath, f)) as fh:
+                    text = fh.read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f

@@ -1,0 +1,103 @@
+"""Slab decomposition + ghost-plane exchange on CPU: world_size 2 (and 3), gloo backend.
+
+The kernels themselves need a GPU; here the *host logic* (decomposition, ranges, exchange, global-boundary
+handling) is driven with the oracle as the per-slab evaluator: exchange ghosts, evaluate the local padded array,
+keep the owned planes, compare with the oracle on the global array."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, bh, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import evaluate
+        from pystencils_autodiff_b200.configs import make_config
+        from pystencils_autodiff_b200.datahandling import SlabDataHandling
+        gshape = {'c2': (12, 9), 'c3': (12, 5, 6), 'c4': (9, 5, 6)}[name]
+        op_g = make_config(name, shape=gshape, dtype='float64', boundary_handling=bh)
+        g = max(op_g.forward_ast_gpu.max_halo[0])
+        dh = SlabDataHandling(gshape, rank, world, g, device='cpu', backend='torch')
+        rng = np.random.default_rng(5)
+        glob_u = rng.normal(size=gshape)
+        glob_go = rng.normal(size=gshape)
+        dh.add_array('u', dtype=np.float64)
+        dh.add_array('diffout', dtype=np.float64)
+        sl = slice(dh.dec.start, dh.dec.start + dh.dec.n_local)
+        dh.owned('u').copy_(torch.from_numpy(glob_u[sl]))
+        dh.owned('diffout').copy_(torch.from_numpy(glob_go[sl]))
+        dh.synchronization_function(['u', 'diffout'])()
+        assert [c[0] for c in dh.call_queue] == ['Communication', 'Communication']
+        # local evaluation on the padded slab (array ends act as zero boundary = never-received ghost planes)
+        op_l = make_config(name, shape=dh.dec.local_shape, dtype='float64', boundary_handling=bh)
+        res = {}
+        for key, asg, src in (('out', op_l.forward_assignments, 'u'), ('diffu', op_l.backward_assignments, 'diffout')):
+            local = evaluate(asg, {src: dh.gpu_arrays[src].numpy()}, 'zeros')[key][dh.dec.owned]
+            ref = evaluate(getattr(op_g, 'forward_assignments' if key == 'out' else 'backward_assignments'),
+                           {src: glob_u if src == 'u' else glob_go}, bh)[key][sl]
+            if bh is None:
+                # 'none': the kernel launch ranges clip the iteration space to the global interior
+                ir = op_l.forward_ast_gpu if key == 'out' else op_l.backward_ast_gpu
+                interior, lo, hi = dh.dec.ranges('none', ir.ghost_layers, ir.ndim)
+                mask = np.zeros(dh.dec.local_shape, dtype=bool)
+                for r in (interior, lo, hi):
+                    if r is not None:
+                        mask[tuple(slice(a, b) for a, b in zip(r['iter_lo'], r['iter_hi']))] = True
+                local = np.where(mask[dh.dec.owned], local, 0.0)
+            res[key] = float(np.abs(local - ref).max())
+        # the write ranges of the three launches tile the owned planes exactly once
+        ir = op_l.forward_ast_gpu
+        cover = np.zeros(dh.dec.local_shape[0], dtype=int)
+        for r in dh.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim):
+            if r is not None:
+                cover[r['write_lo'][0]:r['write_hi'][0]] += 1
+        assert list(cover[dh.dec.owned]) == [1] * dh.dec.n_local and cover.sum() == dh.dec.n_local
+        gathered = dh.gather_array('u')
+        res['gather'] = float(np.abs(gathered - glob_u).max())
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('name,bh,world', [('c3', 'zeros', 2), ('c3', None, 2), ('c2', 'zeros', 2), ('c4', 'zeros', 3),
+                                           ('c4', None, 3)])
+def test_sharded_equals_global(name, bh, world):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + (hash((name, bh, world)) % 300)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, bh, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=10) for _ in range(world))
+    for r in range(world):
+        for k, v in results[r].items():
+            assert v < 1e-14, (r, k, v)
+
+
+def test_decomposition_ranges():
+    from pystencils_autodiff_b200.datahandling import SlabDecomposition
+    d = SlabDecomposition((10, 8, 8), rank=1, world_size=3, ghost_layers=1)
+    assert d.counts == [4, 3, 3] and d.start == 4 and d.local_shape == (5, 8, 8)
+    assert (d.lo_rank, d.hi_rank) == (0, 2)
+    interior, lo, hi = d.ranges('zeros', 0, 3)
+    assert interior['write_lo'][0] == 2 and interior['write_hi'][0] == 3
+    assert (lo['write_lo'][0], lo['write_hi'][0]) == (1, 2) and (hi['write_lo'][0], hi['write_hi'][0]) == (3, 4)
+    first = SlabDecomposition((10, 8, 8), rank=0, world_size=3, ghost_layers=1)
+    interior, lo, hi = first.ranges('none', 1, 3)
+    assert lo is None and hi is not None
+    assert interior['iter_lo'] == [2, 1, 1] and interior['write_lo'] == [1, 0, 0]   # global plane 0 is border: zero
+    with pytest.raises(ValueError):
+        SlabDecomposition((4, 8, 8), rank=0, world_size=4, ghost_layers=1)

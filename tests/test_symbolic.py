@@ -1,0 +1,173 @@
+"""Symbolic layer: the reference's known answers + golden strings produced by the reference's own code.
+
+Reference tests mirrored: tests/test_autodiff.py:8-50, README.rst:55-86, tests/test_tfmad.py:12-53,341-401.
+"""
+import json
+import os
+import pickle
+
+import pytest
+import sympy as sp
+
+import pystencils_autodiff_b200 as ps
+from pystencils_autodiff_b200 import DiffModes
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'reference_symbolic.json')
+
+
+def test_simple_2d_check_assignment_collection():
+    z, y, x = ps.fields("z, y, x: [2d]")
+    forward_assignments = ps.AssignmentCollection([ps.Assignment(z[0, 0], x[0, 0] * sp.log(x[0, 0] * y[0, 0]))], [])
+    jac = ps.get_jacobian_of_assignments(forward_assignments, [x[0, 0], y[0, 0]])
+    assert jac.shape == (len(forward_assignments.bound_symbols), len(forward_assignments.free_symbols))
+    assert repr(jac) == 'Matrix([[log(x_C*y_C) + 1, x_C/y_C]])'
+    for diff_mode in DiffModes:
+        ps.create_backward_assignments(forward_assignments, diff_mode=diff_mode)
+        ps.create_backward_assignments(ps.create_backward_assignments(forward_assignments), diff_mode=diff_mode)
+    result1 = ps.create_backward_assignments(forward_assignments, diff_mode=DiffModes.TRANSPOSED)
+    result2 = ps.create_backward_assignments(forward_assignments, diff_mode=DiffModes.TF_MAD)
+    assert result1 == result2
+
+
+def test_simple_2d_check_raw_assignments():
+    z, y, x = ps.fields("z, y, x: [2d]")
+    forward_assignments = [ps.Assignment(z[0, 0], x[0, 0] * sp.log(x[0, 0] * y[0, 0]))]
+    jac = ps.get_jacobian_of_assignments(forward_assignments, [x[0, 0], y[0, 0]])
+    assert jac.shape == (1, 2)
+    assert repr(jac) == 'Matrix([[log(x_C*y_C) + 1, x_C/y_C]])'
+    for diff_mode in DiffModes:
+        ps.create_backward_assignments(forward_assignments, diff_mode=diff_mode)
+
+
+def test_readme_printed_forms():
+    z, y, x = ps.fields("z, y, x: [20,30]")
+    fa = ps.AssignmentCollection({z[0, 0]: x[0, 0] * sp.log(x[0, 0] * y[0, 0])})
+    assert str(fa) == 'Subexpressions:\nMain Assignments:\n\tz[0,0] ← x_C*log(x_C*y_C)\n'
+    ba = ps.create_backward_assignments(fa)
+    assert str(ba) == ('Subexpressions:\nMain Assignments:\n'
+                       '\t\\hat{x}[0,0] ← diffz_C*(log(x_C*y_C) + 1)\n'
+                       '\t\\hat{y}[0,0] ← diffz_C*x_C/y_C\n')
+    op = ps.AutoDiffOp(fa)
+    assert [f.name for f in op.forward_input_fields] == ['x', 'y']
+    assert [f.name for f in op.backward_input_fields] == ['diffz', 'x', 'y']
+    assert [f.name for f in op.backward_output_fields] == ['diffx', 'diffy']
+    assert str(op).startswith('Forward:')
+
+
+def test_tfmad_fd_stencil_known_answer():
+    """SURVEY.md Appendix A-6 (stencil of tests/test_tfmad.py:195-200)."""
+    a, b, out = ps.fields("a, b, out: float64[5,7]")
+    cont = 2 * ps.fd.Diff(a, 0) - 1.5 * ps.fd.Diff(a, 1) - ps.fd.Diff(b, 0) + 3 * ps.fd.Diff(b, 1)
+    asg = ps.Assignment(out.center(), ps.fd.Discretization2ndOrder(dx=1)(cont) + 1.2 * a.center())
+    op = ps.AutoDiffOp(ps.AssignmentCollection([asg], []), diff_mode='transposed-forward')
+    d = {x.lhs.field.name: x.rhs for x in op.backward_assignments.main_assignments}
+    do = op.backward_input_fields[0]
+    assert do.name == 'diffout'
+    exp_a = do[-1, 0] - do[1, 0] - 0.75 * do[0, -1] + 0.75 * do[0, 1] + 1.2 * do[0, 0]
+    exp_b = -0.5 * do[-1, 0] + 0.5 * do[1, 0] + 1.5 * do[0, -1] - 1.5 * do[0, 1]
+    assert sp.simplify(d['diffa'] - exp_a) == 0
+    assert sp.simplify(d['diffb'] - exp_b) == 0
+
+
+def test_tfmad_two_outputs_curl():
+    """tests/test_tfmad.py:341-401: scalar input, vector (index-dimension) output."""
+    u = ps.Field.create_fixed_size('curl_input', (20, 30), index_dimensions=0)
+    c = ps.Field.create_fixed_size('curl', (20, 30, 2), index_dimensions=1)
+    disc = ps.fd.Discretization2ndOrder(dx=1)
+    fa = ps.AssignmentCollection([ps.Assignment(c.center(0), disc(ps.fd.Diff(u, 0))),
+                                  ps.Assignment(c.center(1), disc(ps.fd.Diff(u, 1)))], [])
+    op = ps.AutoDiffOp(fa, diff_mode='transposed-forward')
+    (bw,) = op.backward_assignments.main_assignments
+    dc = op.backward_input_fields[0]
+    expected = (dc[-1, 0](0) - dc[1, 0](0)) / 2 + (dc[0, -1](1) - dc[0, 1](1)) / 2
+    assert sp.simplify(bw.rhs - expected) == 0
+
+
+def test_transposed_mode_rejects_overlapping_writes():
+    u, out = ps.fields("u, out: [2d]")
+    fa = [ps.Assignment(out.center, u[1, 0] + u[-1, 0])]
+    # two reads of u at different offsets -> two scatter writes to diffu at different offsets: still exclusive
+    # per (field, index) check fails because both write the same field/index
+    with pytest.raises(AssertionError):
+        ps.create_backward_assignments(fa, diff_mode='transposed')
+
+
+def test_valid_boundary_handling_is_rejected():
+    u, out = ps.fields("u, out: [2d]")
+    with pytest.raises(NotImplementedError):
+        ps.AutoDiffOp([ps.Assignment(out.center, u[1, 0])], boundary_handling='valid')
+
+
+def test_constant_fields_default_is_not_mutated():
+    """The reference grows its mutable default argument; we must not."""
+    u, out = ps.fields("u, out: [2d]")
+    a = ps.AutoDiffOp([ps.Assignment(out.center, u[1, 0])])
+    b = ps.AutoDiffOp([ps.Assignment(out.center, u[1, 0])])
+    assert a.constant_fields == b.constant_fields == ['indexVector']
+
+
+def test_pickle_roundtrip():
+    u, out = ps.fields("u, out: float32[8,8]")
+    op = ps.AutoDiffOp([ps.Assignment(out.center, u[1, 0] * 2 + u[0, 0])], boundary_handling='zeros', op_name='p')
+    op2 = pickle.loads(pickle.dumps(op))
+    assert op2.backward_assignments == op.backward_assignments
+    assert op2.forward_assignments == op.forward_assignments
+    assert op2.boundary_handling == 'zeros'
+
+
+def test_no_cpu_path():
+    u, out = ps.fields("u, out: float32[8,8]")
+    op = ps.AutoDiffOp([ps.Assignment(out.center, u[1, 0])])
+    with pytest.raises(NotImplementedError):
+        op.forward_kernel_cpu
+    with pytest.raises(NotImplementedError):
+        op.create_tensorflow_op(backend='torch_native', use_cuda=False)
+    with pytest.raises(NotImplementedError):
+        op.create_tensorflow_op(backend='tensorflow')
+    with pytest.raises(AssertionError):
+        op.create_tensorflow_op(backend='jax')
+
+
+def test_field_description_parser_and_access_names():
+    a, b = ps.fields("a, b: float32[3,4,5]")
+    assert a.dtype.numpy_dtype.name == 'float32' and a.spatial_shape == (3, 4, 5)
+    assert a[1, 0, 0].name == 'a_E' and a[-1, 0, 0].name == 'a_W'
+    assert a[0, 1, 0].name == 'a_N' and a[0, -1, 0].name == 'a_S'
+    assert a[0, 0, 1].name == 'a_T' and a[0, 0, -1].name == 'a_B'
+    assert a[1, 1, 0].name == 'a_NE' and a[-2, 0, 0].name == 'a_2W' and a.center.name == 'a_C'
+    g = ps.fields("g: [2D]")
+    assert not g.has_fixed_shape and g.spatial_dimensions == 2 and g.dtype.numpy_dtype.name == 'float64'
+    v = ps.fields("v(3): float32[4,4]")
+    assert v.index_dimensions == 1 and v.index_shape == (3,) and v.center(1).name == 'v_C^1'
+    import numpy as np
+    arr = np.zeros((6, 7), dtype=np.float32)
+    f = ps.fields(x=arr)
+    assert f.shape == (6, 7) and f.dtype.numpy_dtype == np.float32
+
+
+# ---- golden strings from the reference's own _autodiff.py / transformations.py (tests/golden/make_reference_golden.py)
+def _golden_cases():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_reference_golden import cases, resolve_kwargs
+    return cases(), resolve_kwargs
+
+
+with open(GOLDEN) as _fh:
+    _GOLD = json.load(_fh)
+
+
+@pytest.mark.parametrize('name', sorted(_GOLD))
+def test_matches_reference_symbolic_output(name):
+    cases, resolve_kwargs = _golden_cases()
+    factory, spec, _ = cases[name]
+    fa = factory()
+    op = ps.AutoDiffOp(fa, **resolve_kwargs(spec, fa))
+    g = _GOLD[name]
+    assert str(op.forward_assignments) == g['forward']
+    assert str(op.backward_assignments) == g['backward']
+    assert [f.name for f in op.forward_input_fields] == g['forward_input_fields']
+    assert [f.name for f in op.forward_output_fields] == g['forward_output_fields']
+    assert sorted(f.name for f in op.backward_input_fields) == g['backward_input_fields']
+    assert sorted(f.name for f in op.backward_output_fields) == g['backward_output_fields']
+    assert str(ps.add_fixed_constant_boundary_handling(op.backward_assignments)) == g['backward_zeros']
