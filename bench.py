@@ -33,7 +33,7 @@ CPU_SAMPLE_SHAPE = {'c2': (4096, 4096), 'c3': (384, 384, 384), 'c4': (192, 192, 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -243,7 +243,7 @@ def main_ours(args):
     ms_step = ms_total / args.steps
     value = cells * world / (ms_step * 1e-3) / 1e6
 
-    # ---- end to end through the public operator API with HOST buffers (N=1 path: Function.apply + autograd) ------
+    # ---- end to end through the public API with HOST buffers (copies inside the timed region) -------------------
     e2e = slab.end_to_end(args.e2e_steps, barrier)
     if world > 1:
         t = torch.tensor([e2e['ms_per_step']], device=dev, dtype=torch.float64)
@@ -280,7 +280,9 @@ def main_ours(args):
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
                 'ms_per_step': e2e['ms_per_step'], 'steps': args.e2e_steps,
-                'api': 'AutoDiffOp.create_tensorflow_op(backend="torch_native").apply + autograd, pinned host buffers'},
+                'api': ('HostStreamedOp(AutoDiffOp)(host_in, host_out): pinned host fields streamed through the GPU in plane '
+                        'chunks, H2D / forward+adjoint kernels / D2H overlapped on three streams') if world == 1 else
+                       'SlabStencilOp: H2D of the slab, halo exchange + kernels, D2H of outputs and input gradients'},
         'gpu_launches': launches,
     }
     if not args.no_cpu_baseline:

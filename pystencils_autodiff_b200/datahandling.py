@@ -28,7 +28,7 @@ import numpy as np
 from . import runtime
 from .backends._torch_native import CompiledKernel, numpy_dtype_to_torch
 
-__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'SlabStencilOp']
+__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'SlabStencilOp', 'HostStreamedOp']
 
 
 class SlabDecomposition:
@@ -67,35 +67,41 @@ class SlabDecomposition:
         """(interior, lo, hi) launch ranges in local coordinates (``psad_range_t`` dicts); lo/hi may be None.
 
         ``boundary``: 'zeros' | 'none'; ``ghost_width_of_kernel``: iteration margin of the kernel in 'none' mode."""
-        g, n = self.g, self.n_local
-        shape = self.local_shape[:ndim]
-        full_lo = [0] * ndim
-        full_hi = list(shape)
-        it_lo, it_hi = list(full_lo), list(full_hi)
-        if boundary == 'none' and ghost_width_of_kernel > 0:
-            m = ghost_width_of_kernel
-            for d in range(1, ndim):
-                it_lo[d], it_hi[d] = m, shape[d] - m
-            glo = max(m, self.start) - self.start + g
-            ghi = min(self.global_shape[0] - m, self.start + n) - self.start + g
-            it_lo[0], it_hi[0] = glo, max(glo, ghi)
-        else:
-            it_lo[0], it_hi[0] = g, g + n
+        return slab_ranges(self.global_shape, self.start, self.n_local, self.g, self.lo_rank >= 0, self.hi_rank >= 0,
+                           boundary, ghost_width_of_kernel, ndim)
 
-        def rng(z0, z1):
-            if z1 <= z0:
-                return None
-            return dict(iter_lo=[max(it_lo[0], z0)] + it_lo[1:], iter_hi=[max(max(it_lo[0], z0), min(it_hi[0], z1))] + it_hi[1:],
-                        write_lo=[z0] + full_lo[1:], write_hi=[z1] + full_hi[1:])
 
-        if self.world_size == 1 or g == 0:
-            return rng(g, g + n), None, None
-        lo_w = g if self.lo_rank >= 0 else 0
-        hi_w = g if self.hi_rank >= 0 else 0
-        interior = rng(g + lo_w, g + n - hi_w)
-        lo = rng(g, g + lo_w) if lo_w else None
-        hi = rng(g + n - hi_w, g + n) if hi_w else None
-        return interior, lo, hi
+def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndim):
+    """Launch ranges for the slab owning global planes ``[start, start+n)``, stored with ``g`` ghost planes.
+
+    Returns ``(interior, lo, hi)``: the planes that do not depend on the ghost planes of a neighbour, and the ``g``
+    planes next to each existing neighbour (None where there is none).  Cells inside ``[iter_lo, iter_hi)`` are
+    evaluated, the other cells of ``[write_lo, write_hi)`` are set to 0 (``boundary='none'``: the global border)."""
+    shape = (n + 2 * g,) + tuple(global_shape[1:ndim])
+    full_lo = [0] * ndim
+    full_hi = list(shape)
+    it_lo, it_hi = list(full_lo), list(full_hi)
+    if boundary == 'none' and margin > 0:
+        for d in range(1, ndim):
+            it_lo[d], it_hi[d] = margin, shape[d] - margin
+        glo = max(margin, start) - start + g
+        ghi = min(global_shape[0] - margin, start + n) - start + g
+        it_lo[0], it_hi[0] = glo, max(glo, ghi)
+    else:
+        it_lo[0], it_hi[0] = g, g + n
+
+    def rng(z0, z1):
+        if z1 <= z0:
+            return None
+        lo = max(it_lo[0], z0)
+        return dict(iter_lo=[lo] + it_lo[1:], iter_hi=[max(lo, min(it_hi[0], z1))] + it_hi[1:],
+                    write_lo=[z0] + full_lo[1:], write_hi=[z1] + full_hi[1:])
+
+    lo_w = g if has_lo else 0
+    hi_w = g if has_hi else 0
+    if lo_w == 0 and hi_w == 0:
+        return rng(g, g + n), None, None
+    return rng(g + lo_w, g + n - hi_w), (rng(g, g + lo_w) if lo_w else None), (rng(g + n - hi_w, g + n) if hi_w else None)
 
 
 class HaloExchanger:
@@ -374,13 +380,13 @@ class SlabStencilOp:
         dt = {f.name: self.dh.gpu_arrays[f.name].dtype for f in in_fields + out_fields}
         esize = {n: torch.empty((), dtype=d).element_size() for n, d in dt.items()}
         cells = int(np.prod(self.local_shape))
-        # two pinned staging buffers (one per direction), reused for every field: synthetic data, honest byte counts
+        # world > 1: two pinned staging buffers (one per direction), reused for every field: synthetic data, honest byte counts
         big = max(esize.values()) * cells
-        if self._pinned is None:
+        if self._pinned is None and self.world > 1:
             self._pinned = (torch.empty(big, dtype=torch.uint8, pin_memory=True),
                             torch.empty(big, dtype=torch.uint8, pin_memory=True))
             self._pinned[0].random_(0, 64)
-        h_in, h_out = self._pinned
+        h_in, h_out = self._pinned if self._pinned is not None else (None, None)
 
         def host_view(buf, name):
             return buf[:esize[name] * cells].view(dt[name]).view(self.local_shape)
@@ -388,19 +394,21 @@ class SlabStencilOp:
         h2d = sum(esize[f.name] * cells for f in in_fields) + sum(esize[f.name] * cells for f in out_fields)
         d2h = h2d
         if self.world == 1:
+            # host-resident fields streamed through the GPU in chunks of planes (HostStreamedOp): the public call for
+            # host buffers; H2D, kernels and D2H of consecutive chunks overlap on three streams
             if self._fn is None:
-                self._fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
-            fn = self._fn
+                self._fn = HostStreamedOp(op, self.local_shape, self.device)
+                fields = self._fn.fields
+                self._host = {n: torch.empty(self.local_shape, dtype=self.dh.gpu_arrays[n].dtype, pin_memory=True)
+                              for n in fields}
+                for n in self._fn.input_names:
+                    self._host[n].copy_(self.dh.owned(n))
+            streamed = self._fn
+            h_in = {n: self._host[n] for n in streamed.input_names}
+            h_out = {n: self._host[n] for n in streamed.output_names}
 
             def step():
-                ins = [host_view(h_in, f.name).to(self.device, non_blocking=True).requires_grad_(True) for f in in_fields]
-                grads = [host_view(h_in, f.name).to(self.device, non_blocking=True) for f in out_fields]
-                outs = fn.apply(*ins)
-                torch.autograd.backward(outs, grads)
-                for f, o in zip(out_fields, outs):
-                    host_view(h_out, f.name).copy_(o.detach(), non_blocking=True)
-                for f, t in zip(in_fields, ins):
-                    host_view(h_out, f.name).copy_(t.grad, non_blocking=True)
+                streamed(h_in, h_out)
         else:
             grad_names = [f.name for f in op.backward_input_fields if f not in op.forward_input_fields]
             dnames = [f.name for f in op.backward_output_fields]
@@ -425,4 +433,104 @@ class SlabStencilOp:
             step()
         end.record()
         barrier()
+        if self.world == 1:
+            h2d, d2h = self._fn.h2d_bytes, self._fn.d2h_bytes
         return dict(ms_per_step=start.elapsed_time(end) / steps, h2d=h2d, d2h=d2h)
+
+
+class HostStreamedOp:
+    """Forward + adjoint of an ``AutoDiffOp`` on fields that live in (pinned) HOST memory, streamed through the GPU.
+
+    The reference's Function copies whole tensors with ``.cuda()`` inside ``forward`` (backends/_torch_native.py:47-49),
+    which serialises H2D, compute and D2H.  Here the fields are cut into chunks of planes along dim 0 (the same slab
+    decomposition as the multi-GPU path, with the chunks of one GPU playing the role of the ranks): chunk k+1 is
+    uploaded on a copy-in stream while chunk k is computed and chunk k-1 is downloaded on a copy-out stream, so the
+    PCIe link runs in both directions at once and the kernels hide behind it.  Ghost planes come straight from the
+    host array (contiguous), global boundary handling is the same range logic as ``SlabDecomposition``.
+    """
+
+    def __init__(self, op, shape, device=None, chunk_planes=None, stages=3, tuning=None):
+        import torch
+        self.torch = torch
+        self.op = op
+        self.shape = tuple(int(s) for s in shape)
+        self.device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+        self.fwd = CompiledKernel(op.forward_ast_gpu, tuning)
+        self.bwd = CompiledKernel(op.backward_ast_gpu, tuning)
+        self.g = max(max(ir.max_halo[0]) for ir in (op.forward_ast_gpu, op.backward_ast_gpu))
+        plane_bytes = int(np.prod(self.shape[1:])) * max(f.dtype.itemsize for f in op.forward_fields)
+        if chunk_planes is None:
+            chunk_planes = max(4 * max(1, self.g), min(self.shape[0], (192 << 20) // max(1, plane_bytes)))
+        self.chunk = int(min(chunk_planes, self.shape[0]))
+        self.n_chunks = -(-self.shape[0] // self.chunk)
+        self.stages = int(stages)
+        fields = OrderedDict()
+        for f in list(op.forward_fields) + list(op.backward_fields):
+            fields.setdefault(f.name, f)
+        self.fields = fields
+        written = {f.name for f in op.forward_output_fields} | {f.name for f in op.backward_output_fields}
+        self.input_names = [n for n in fields if n not in written]
+        self.output_names = [n for n in fields if n in written]
+        buf_shape = (self.chunk + 2 * self.g,) + self.shape[1:]
+        self.buffers = [{n: torch.empty(buf_shape, dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=self.device)
+                         for n, f in fields.items()} for _ in range(self.stages)]
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(self.stages)]
+        self.ev_cmp = [torch.cuda.Event() for _ in range(self.stages)]
+        self.ev_out = [torch.cuda.Event() for _ in range(self.stages)]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _ranges(self, kernel, k, n_k):
+        ir = kernel.ir   # the chunk's ghost planes are filled from the host array, so one launch covers it
+        return slab_ranges(self.shape, k * self.chunk, n_k, self.g, False, False, ir.boundary, ir.ghost_layers, ir.ndim)[0]
+
+    def __call__(self, host_in, host_out):
+        """``host_in``: name -> pinned CPU tensor for every input field (forward inputs and ``diff<out>`` gradients);
+        ``host_out``: name -> pinned CPU tensor receiving every output (forward outputs and ``diff<in>``)."""
+        torch = self.torch
+        g, C, N0 = self.g, self.chunk, self.shape[0]
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for s_ in (self.s_in, self.s_cmp, self.s_out):
+            s_.wait_event(start)
+        self.h2d_bytes = self.d2h_bytes = 0
+        for k in range(self.n_chunks):
+            st = k % self.stages
+            buf = self.buffers[st]
+            z0 = k * C
+            n_k = min(C, N0 - z0)
+            lo, hi = max(0, z0 - g), min(N0, z0 + n_k + g)
+            with torch.cuda.stream(self.s_in):
+                if k >= self.stages:
+                    self.s_in.wait_event(self.ev_out[st])      # the buffer's previous chunk has been downloaded
+                    self.s_in.wait_event(self.ev_cmp[st])
+                for n in self.input_names:
+                    dst = buf[n]
+                    off = lo - (z0 - g)
+                    if off > 0:
+                        dst[:off].zero_()                       # planes below the domain: the 'zeros' boundary
+                    dst[off:off + (hi - lo)].copy_(host_in[n][lo:hi], non_blocking=True)
+                    if off + (hi - lo) < n_k + 2 * g:
+                        dst[off + (hi - lo):n_k + 2 * g].zero_()
+                    self.h2d_bytes += (hi - lo) * host_in[n][0].numel() * host_in[n].element_size()
+                self.ev_in[st].record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(self.ev_in[st])
+                if k >= self.stages:
+                    self.s_cmp.wait_event(self.ev_out[st])
+                for kern in (self.fwd, self.bwd):
+                    views = {f.name: buf[f.name][:n_k + 2 * g] for f in kern.fields}
+                    kern(**views, **{s: 1.0 for s in kern.scalars}, _range=self._ranges(kern, k, n_k))
+                self.ev_cmp[st].record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_cmp[st])
+                for n in self.output_names:
+                    host_out[n][z0:z0 + n_k].copy_(buf[n][g:g + n_k], non_blocking=True)
+                    self.d2h_bytes += n_k * host_out[n][0].numel() * host_out[n].element_size()
+                self.ev_out[st].record(self.s_out)
+        done = torch.cuda.Event()
+        done.record(self.s_out)
+        cur.wait_event(done)
+        cur.wait_event(self.ev_cmp[(self.n_chunks - 1) % self.stages])

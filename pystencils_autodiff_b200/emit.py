@@ -27,7 +27,7 @@ from .field import Field
 from .ir import StencilKernelIR
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '5'
+EMITTER_VERSION = '6'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -266,6 +266,7 @@ class MarchTuning:
     min_ctas: int = 0
     ctas_per_sm: int = 0   # cap on resident CTAs per SM (0 = whatever fits)
     carry: bool = True     # keep staged elements in registers while their plane moves through the stencil
+    plane_sums: bool = True  # 3-D: evaluate in-plane sub-sums shared by several z-offsets once per plane and carry them
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes for 4-byte fields, no for 8-byte fields — measured)
 
@@ -351,6 +352,65 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                            boxh=boxh, bytes=nbytes, off=off, T=_CT[f.dtype.numpy_dtype])
         off += -(-nbytes // 128) * 128
     STAGE_BYTES = off
+    # ---- plane partial sums --------------------------------------------------------------------------------------
+    # rhs = sum_dz G_dz(accesses of plane z+dz) + rest.  Where G_a and G_b are the same expression up to the z shift
+    # (e.g. the z-1 and z+1 planes of a symmetric stencil), the value Q(plane) is computed once per cell when the plane
+    # enters the window at the highest of these positions and carried down in registers; the raw elements of that
+    # plane are then not needed at the lower positions at all.
+    q_classes = []           # [{canon: expr at dz=0, members: [dz...], hi: dz}]
+    main_exprs = []          # per main assignment: expression over accesses and Q symbols
+    raw_accesses = {f.name: set() for f in tma_fields}
+
+    def _zshift(expr, dz):
+        return expr.xreplace({a: a.get_shifted(*([dz] + [0] * (nd - 1))) for a in expr.atoms(Field.Access)})
+
+    use_q = bool(t.plane_sums and t.carry and nd == 3 and D > 0 and not ir.subexpressions)
+    for lhs, rhs in ir.main:
+        rest = []
+        groups = {}
+        if use_q:
+            for term in sp.Add.make_args(rhs):
+                dzs = {int(a.offsets[0]) for a in term.atoms(Field.Access)}
+                if len(dzs) == 1:
+                    groups.setdefault(dzs.pop(), []).append(term)
+                else:
+                    rest.append(term)
+        else:
+            rest = [rhs]
+        by_canon = {}
+        for dz, terms in groups.items():
+            g_expr = sp.Add(*terms)
+            by_canon.setdefault(_zshift(g_expr, -dz), []).append(dz)
+        new_terms = list(rest)
+        for canon, members in by_canon.items():
+            n_acc = len(canon.atoms(Field.Access))
+            if len(members) >= 2 and n_acc >= 2:
+                ci = None
+                for i_, qc in enumerate(q_classes):
+                    if qc['canon'] == canon:
+                        ci = i_
+                        qc['members'] = sorted(set(qc['members']) | set(members))
+                if ci is None:
+                    q_classes.append(dict(canon=canon, members=sorted(members)))
+                    ci = len(q_classes) - 1
+                new_terms += [sp.Symbol('psadQ_%d_%d' % (ci, dz + HZL)) for dz in members]
+            else:
+                new_terms += [_zshift(canon, dz) for dz in members]
+        main_exprs.append((lhs, sp.Add(*new_terms)))
+    for qc in q_classes:
+        qc['hi'] = max(qc['members'])
+        qc['lo'] = min(qc['members'])
+        qc['expr_hi'] = _zshift(qc['canon'], qc['hi'])
+    for _, e in main_exprs:
+        for a in e.atoms(Field.Access):
+            raw_accesses[a.field.name].add(a)
+    for qc in q_classes:
+        for a in qc['expr_hi'].atoms(Field.Access):
+            raw_accesses[a.field.name].add(a)
+    for lhs_, e in ir.subexpressions:
+        for a in e.atoms(Field.Access):
+            raw_accesses[a.field.name].add(a)
+
     # ---- register-window analysis ------------------------------------------------------------------------------
     # unit = ('U', row, v): aligned 16-byte vector v of the thread's own strip in tile row `row` (relative to the
     # thread's first row);  ('H', row, c): single halo element at strip column c (<0 or >=SX).
@@ -360,7 +420,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     need = {f.name: [set() for _ in range(D + 1)] for f in tma_fields}
     for f in tma_fields:
         g = geo[f.name]
-        for a in ir.read_accesses[f.name]:
+        for a in sorted(raw_accesses[f.name], key=str):
             dz, dy, dx = _off3(a.offsets)
             j = dz + HZL
             for r in range(RY):
@@ -389,12 +449,13 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                      (range(u[2] * geo[f.name]['vec'], (u[2] + 1) * geo[f.name]['vec']) if u[0] == 'U' else [u[2]])})
                 * (geo[f.name]['es'] // 4) for f in tma_fields for j in range(D + 1))
     words += sum(SX * (lhs.field.dtype.itemsize // 4) for lhs, _ in ir.main)
+    words += sum((qc['hi'] - qc['lo'] + 1) * RY * SX * (np.dtype(ir.compute_dtype).itemsize // 4) for qc in q_classes)
     est_regs = min(255, words + 48)
 
     # The window is addressed by *physical* plane slot k = (plane index) mod NP.  In phase PH = step mod NP the
     # plane at stencil position j lives in slot (PH + j + 1) mod NP, so nothing has to be moved between steps: the
     # step body is emitted NP times, once per phase, with the slot numbers baked in.
-    any_carry = any(carried[f.name][j] for f in tma_fields for j in range(D + 1))
+    any_carry = any(carried[f.name][j] for f in tma_fields for j in range(D + 1)) or bool(q_classes)
     NP = D + 1 if any_carry else 1
     phase = [0]
 
@@ -443,6 +504,11 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
             for j, row in sorted({(j, u[1]) for j in range(D + 1) for u in held[f.name][j]}):
                 L.append('  %s f%d_k%d_r%d[%d];  // %s, plane %+d, row %+d' % (g['T'], g['ti'], j, row + g['hy'][0], W, f.name,
                                                                             j - HZL, row))
+    for ci, qc in enumerate(q_classes):
+        for k in range(D + 1):
+            for r in range(RY):
+                L.append('  CT q%d_k%d_r%d[%d];  // plane sum %d (planes %s), window slot %d, row %d' % (ci, k, r, SX, ci,
+                                                                                                  qc['members'], k, r))
     L.append('  unsigned xmask, ymask_wr, ymask_it;  // per item: cells of this thread inside the iteration / write range')
     L.append('  int xs, zlo, zhi;')
     for f in out_fields:
@@ -514,6 +580,27 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
         # this warp will not touch the oldest still-read slot again: hand it back to the producer
         L.append('  __syncwarp();')
         L.append('  if (lane == 0 && rel_bar) psad_mbar_arrive(rel_bar);')
+        # plane sums of the plane that just entered the window (needed by later steps: not gated by do_store)
+        def qelem(ci, j, r, c):
+            return 'R.q%d_k%d_r%d[%d]' % (ci, (phase[0] + j + 1) % NP, r, c)
+
+        def cell_map(r, c):
+            local = {}
+            for f in tma_fields:
+                for a in raw_accesses[f.name]:
+                    dz, dy, dx = _off3(a.offsets)
+                    local[a] = '((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx)
+            for s_ in ir.scalars:
+                local[s_] = _c_ident(s_.name)
+            for ci, qc in enumerate(q_classes):
+                for dz in qc['members']:
+                    local[sp.Symbol('psadQ_%d_%d' % (ci, dz + HZL))] = qelem(ci, dz + HZL, r, c)
+            return local
+
+        for ci, qc in enumerate(q_classes):
+            for r in range(RY):
+                for c in range(SX):
+                    L.append('  %s = %s;' % (qelem(ci, qc['hi'] + HZL, r, c), pr.print_with(qc['expr_hi'], cell_map(r, c))))
         # compute + store
         L.append('  if (do_store) {')
         if nd == 3:
@@ -526,18 +613,12 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
             for lhs, _ in ir.main:
                 L.append('      %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
             for c in range(SX):
-                local = {}
-                for f in tma_fields:
-                    for a in ir.read_accesses[f.name]:
-                        dz, dy, dx = _off3(a.offsets)
-                        local[a] = '((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx)
-                for s_ in ir.scalars:
-                    local[s_] = _c_ident(s_.name)
+                local = cell_map(r, c)
                 L.append('      {')
                 for lhs, rhs in ir.subexpressions:
                     L.append('        const CT %s = %s;' % (_c_ident(lhs.name), pr.print_with(rhs, local)))
                     local[lhs] = _c_ident(lhs.name)
-                for lhs, rhs in ir.main:
+                for lhs, rhs in main_exprs:
                     To = _CT[lhs.field.dtype.numpy_dtype]
                     L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To,
                                                                                        pr.print_with(rhs, local), To))
