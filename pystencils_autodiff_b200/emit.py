@@ -25,9 +25,10 @@ from sympy.printing.c import C99CodePrinter
 
 from .field import Field
 from .ir import StencilKernelIR
+from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '6'
+EMITTER_VERSION = '7'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -260,13 +261,16 @@ class MarchTuning:
     sx: int = 0
     ry: int = 0
     ty: int = 0
-    lookahead: int = 3     # staged planes in flight ahead of the consumers (measured optimum on B200: 3)
+    lookahead: int = 0     # staged planes in flight ahead of the consumers (0 = measured optimum: 3 for fp32, 4 for fp64)
     stages: int = 0        # ring slots (0 = slots still being read + lookahead)
     chunk: int = 0
     min_ctas: int = 0
     ctas_per_sm: int = 0   # cap on resident CTAs per SM (0 = whatever fits)
     carry: bool = True     # keep staged elements in registers while their plane moves through the stencil
     plane_sums: bool = True  # 3-D: evaluate in-plane sub-sums shared by several z-offsets once per plane and carry them
+    linopt: bool = True      # shared partial sums across the cells of a thread for linear plane sums (linopt.py)
+    arrival: Optional[bool] = None  # evaluate EVERY per-plane group of the sum when its plane arrives and carry only
+    #                                 scalars (no raw values); default: when the stencil has more than 9 accesses
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes for 4-byte fields, no for 8-byte fields — measured)
 
@@ -309,7 +313,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     max_esize = max(f.dtype.itemsize for f in fields)
 
     # ---- geometry ------------------------------------------------------------------------------------------
-    SX = t.sx or (4 if max_esize == 4 else 2)   # cells per thread along x: one 16-byte vector of the widest type
+    SX = t.sx or 4   # cells per thread along x: one 16-byte vector for 4-byte types, two for 8-byte types
     if (SX * min(f.dtype.itemsize for f in fields)) % 16:
         raise ValueError('sx*itemsize must be a multiple of 16 bytes')
     TX = 32 * SX
@@ -318,13 +322,15 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     HZL, HZH = (mh3[0] if nd == 3 else (0, 0))
     D = HZL + HZH
     # measured on B200 (scripts/sweep.py, profiles/): fp32 3-D 32x128 tiles / 2 rows per thread, fp32 2-D 16x128 / 1 row,
-    # fp64 16x64 tiles (sx=2) / 1 row
+    # fp64 14x128 tiles / 2 rows
     if max_esize == 4:
         RY = t.ry or (2 if nd == 3 else 1)
         TY = t.ty or (32 if nd == 3 else 16)
     else:
-        RY = t.ry or 1
-        TY = t.ty or 16
+        # 7 consumer warps + the producer warp = 8 warps: ptxas budgets registers for the CTA size rounded up to 4
+        # warps, so 8+1 warps would be capped at 168 registers and spill (the 27-point window needs ~240)
+        RY = t.ry or 2
+        TY = t.ty or 7 * RY
     if TY % RY:
         raise ValueError('ty must be a multiple of ry')
     THREADS = 32 * (TY // RY)
@@ -365,6 +371,8 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
         return expr.xreplace({a: a.get_shifted(*([dz] + [0] * (nd - 1))) for a in expr.atoms(Field.Access)})
 
     use_q = bool(t.plane_sums and t.carry and nd == 3 and D > 0 and not ir.subexpressions)
+    n_reads = sum(len(v) for v in ir.read_accesses.values())
+    arrival = use_q and (t.arrival if t.arrival is not None else n_reads > 9)
     for lhs, rhs in ir.main:
         rest = []
         groups = {}
@@ -384,7 +392,9 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
         new_terms = list(rest)
         for canon, members in by_canon.items():
             n_acc = len(canon.atoms(Field.Access))
-            if len(members) >= 2 and n_acc >= 2:
+            if arrival and members == [HZH]:
+                new_terms += [_zshift(canon, HZH)]      # used in the step it arrives: nothing to carry
+            elif (arrival and n_acc >= 1) or (len(members) >= 2 and n_acc >= 2):
                 ci = None
                 for i_, qc in enumerate(q_classes):
                     if qc['canon'] == canon:
@@ -398,7 +408,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                 new_terms += [_zshift(canon, dz) for dz in members]
         main_exprs.append((lhs, sp.Add(*new_terms)))
     for qc in q_classes:
-        qc['hi'] = max(qc['members'])
+        qc['hi'] = HZH if arrival else max(qc['members'])
         qc['lo'] = min(qc['members'])
         qc['expr_hi'] = _zshift(qc['canon'], qc['hi'])
     for _, e in main_exprs:
@@ -470,7 +480,8 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     # ---- source -------------------------------------------------------------------------------------------------
     jrel = min([j for j in range(D + 1) if any(fresh[f.name][j] for f in tma_fields)] or [D])
     # ring = planes still read from shared memory (D - jrel + 1) + `lookahead` planes in flight ahead of them
-    STAGES = t.stages or (D - jrel + 1 + max(1, t.lookahead))
+    lookahead = t.lookahead or (3 if max_esize == 4 else 4)   # measured optima (fp32 3-D: sharp at 3; fp64 27-pt: 4)
+    STAGES = t.stages or (D - jrel + 1 + max(1, lookahead))
     if STAGES < D - jrel + 2:
         raise ValueError('ring too small')
     smem_bytes = STAGES * STAGE_BYTES + 16 * STAGES
@@ -597,10 +608,46 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                     local[sp.Symbol('psadQ_%d_%d' % (ci, dz + HZL))] = qelem(ci, dz + HZL, r, c)
             return local
 
-        for ci, qc in enumerate(q_classes):
-            for r in range(RY):
-                for c in range(SX):
-                    L.append('  %s = %s;' % (qelem(ci, qc['hi'] + HZL, r, c), pr.print_with(qc['expr_hi'], cell_map(r, c))))
+        for hi in sorted({qc['hi'] for qc in q_classes}):
+            # all plane sums evaluated at this position, for all cells of the thread, over shared element symbols
+            elem_sym, targets = {}, []
+            for ci, qc in enumerate(q_classes):
+                if qc['hi'] != hi:
+                    continue
+                for r in range(RY):
+                    for c in range(SX):
+                        sub = {}
+                        for a in qc['expr_hi'].atoms(Field.Access):
+                            dz, dy, dx = _off3(a.offsets)
+                            g = geo[a.field.name]
+                            key = sp.Symbol('E%d_%d_%d' % (g['ti'], r + dy + g['hy'][0], c + dx + g['hx'][0]))
+                            elem_sym[key] = '((CT)%s)' % elem(a.field, dz + HZL, r + dy, c + dx)
+                            sub[a] = key
+                        targets.append(((ci, r, c), qc['expr_hi'].xreplace(sub)))
+            plan = plan_linear(targets, set(elem_sym)) if t.linopt else None
+            if plan is None:
+                for (ci, r, c), _ in targets:
+                    L.append('  %s = %s;' % (qelem(ci, hi + HZL, r, c), pr.print_with(q_classes[ci]['expr_hi'], cell_map(r, c))))
+                continue
+            txt = {str(k): v for k, v in elem_sym.items()}
+            scal = {s_: _c_ident(s_.name) for s_ in ir.scalars}
+            L.append('  {')
+            for nm, a, b in plan.temps:
+                L.append('    const CT %s = %s + %s;' % (nm, txt.get(a, a), txt.get(b, b)))
+            for nm, addends in plan.sums:
+                parts = [txt.get(a, a) for a in addends]
+                while len(parts) > 1:
+                    parts = ['(%s + %s)' % (parts[i], parts[i + 1]) if i + 1 < len(parts) else parts[i]
+                             for i in range(0, len(parts), 2)]
+                L.append('    const CT %s = %s;' % (nm, parts[0]))
+            fma = 'fmaf' if CT == 'float' else 'fma'
+            for (ci, r, c), lst in plan.targets:
+                acc = None
+                for coeff, nm in lst:
+                    cw = pr.print_with(coeff, scal)
+                    acc = '%s * %s' % (cw, txt.get(nm, nm)) if acc is None else '%s(%s, %s, %s)' % (fma, cw, txt.get(nm, nm), acc)
+                L.append('    %s = %s;' % (qelem(ci, hi + HZL, r, c), acc))
+            L.append('  }')
         # compute + store
         L.append('  if (do_store) {')
         if nd == 3:

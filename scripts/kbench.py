@@ -29,7 +29,7 @@ def main():
     for kv in os.environ.get('PSAD_TUNE', '').split(','):
         if kv:
             k, v = kv.split('=')
-            tun[k] = bool(int(v)) if k in ("carry", "shuffle") else int(v)
+            tun[k] = bool(int(v)) if k in ("carry", "shuffle", "plane_sums", "arrival", "linopt") else int(v)
     tuning = MarchTuning(**tun) if tun else None
     op = make_config(name, shape=shape)
     dev = torch.device('cuda:0')
