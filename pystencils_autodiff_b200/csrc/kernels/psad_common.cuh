@@ -81,6 +81,14 @@ template <typename T> PSAD_DEV void psad_stg_vec(T* p, const T* e) {
   __stcs(reinterpret_cast<typename PsadVec<T>::type*>(p), PsadVec<T>::pack(e));
 }
 
+// ---- small integer powers by repeated multiplication (fixed association: ((x*x)*x)*...)
+template <int N, typename T> PSAD_DEV T psad_ipow(T x) {
+  T r = x;
+#pragma unroll
+  for (int i = 1; i < N; ++i) r *= x;
+  return r;
+}
+
 // ---- warp halo exchange: element of the lane to the left / right -----------------------------------------------
 template <typename T> PSAD_DEV T psad_from_left(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <typename T> PSAD_DEV T psad_from_right(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }

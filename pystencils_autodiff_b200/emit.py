@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '7'
+EMITTER_VERSION = '8'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -135,10 +135,15 @@ class _CudaPrinter(C99CodePrinter):
             return '(%s)' % s if int(e) > 0 else '(%s/(%s))' % (self._one, s)
         if e == -1:
             return '(%s/(%s))' % (self._one, self._print(b))
-        if e == sp.Rational(1, 2):
-            return '%s(%s)' % (self._sqrt, self._print(b))
-        if e == sp.Rational(-1, 2):
-            return '(%s/%s(%s))' % (self._one, self._sqrt, self._print(b))
+        if e.is_Rational and e.q == 2 and abs(int(e.p)) <= 9:
+            # half-integer powers through sqrt / rsqrt (CUDA math API, <= 2 ulp) instead of pow(): x**(3/2) = x*sqrt(x),
+            # x**(-3/2) = rsqrt(x)**3.  The backward of anything containing 1/sqrt(...) is full of these.
+            n = int(e.p)
+            if n > 0:
+                root = '%s(%s)' % (self._sqrt, self._print(b))
+                return root if n == 1 else '(%s*%s)' % (root, self._print(sp.Pow(b, (n - 1) // 2)))
+            r = '%s(%s)' % ('rsqrtf' if self._sqrt == 'sqrtf' else 'rsqrt', self._print(b))
+            return r if n == -1 else 'psad_ipow<%d>(%s)' % (-n, r)
         return super()._print_Pow(expr)
 
 

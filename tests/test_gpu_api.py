@@ -1,0 +1,170 @@
+"""GPU: operator-API behaviour (marshalling rules of backends/_torch_native.py) and full-size property checks."""
+import numpy as np
+import pytest
+import sympy as sp
+
+import pystencils_autodiff_b200 as ps
+from oracle import evaluate, forward_backward
+from pystencils_autodiff_b200.configs import make_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_scalar_parameter_through_class_kwargs():
+    """tests/backends/test_torch_native_compilation.py:156-211: z = x*log(a*x*y), a = 5, rand(20,40), all cells."""
+    import torch
+    z, y, x = ps.fields("z, y, x: [20,40]")
+    a = sp.Symbol('a')
+    op = ps.AutoDiffOp(ps.AssignmentCollection({z[0, 0]: x[0, 0] * sp.log(a * x[0, 0] * y[0, 0])}), op_name='scal')
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    fn.class_kwargs['a'] = 5.0
+    rng = np.random.default_rng(0)
+    X, Y, G = rng.random((20, 40)) + 0.1, rng.random((20, 40)) + 0.1, rng.normal(size=(20, 40))
+    xt, yt = _t(X).requires_grad_(True), _t(Y).requires_grad_(True)
+    (out,) = fn.apply(xt, yt)
+    out.backward(_t(G))
+    ref_o, ref_d = forward_backward(op, dict(x=X, y=Y), dict(z=G), scalars=dict(a=5.0))
+    assert np.abs(out.detach().cpu().numpy() - ref_o['z']).max() <= 1e-12 * np.abs(ref_o['z']).max()
+    assert np.abs(xt.grad.cpu().numpy() - ref_d['diffx']).max() <= 1e-12 * np.abs(ref_d['diffx']).max()
+    assert np.abs(yt.grad.cpu().numpy() - ref_d['diffy']).max() <= 1e-12 * np.abs(ref_d['diffy']).max()
+    assert [p.symbol.name for p in fn.forward_parameters] == ['x', 'y']
+    assert fn.call(x=xt, y=yt).shape == (20, 40)
+    assert 'psad_scal_forward_gpu' in fn.code
+    with pytest.raises(TypeError):
+        fn.apply(xt.float(), yt)            # dtype mismatch is an error, not a reinterpretation
+
+
+def test_constant_fields_get_no_gradient_and_outputs_are_a_tuple():
+    import torch
+    x, y, z = ps.fields('x, y, z: float64[12,16]')
+    fa = ps.AssignmentCollection({z.center: x[1, 0] * y[0, 0] + x[0, -1]})
+    op = ps.AutoDiffOp(fa, boundary_handling='zeros', constant_fields=[y])
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    rng = np.random.default_rng(1)
+    X, Y, G = rng.normal(size=(12, 16)), rng.normal(size=(12, 16)), rng.normal(size=(12, 16))
+    xt, yt = _t(X).requires_grad_(True), _t(Y).requires_grad_(True)
+    outs = fn.apply(xt, yt)
+    assert isinstance(outs, tuple) and len(outs) == 1
+    outs[0].backward(_t(G))
+    assert yt.grad is None
+    _, ref = forward_backward(op, dict(x=X, y=Y), dict(z=G))
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), ref['diffx'], rtol=1e-12, atol=1e-13)
+
+
+def test_time_constant_field_accumulate_form():
+    """``diff_f.center += ...`` (_autodiff.py:110-113): the kernel reads its own (zero-initialised) output."""
+    import torch
+    u, out = ps.fields('u, out: float64[10,32]')
+    fa = [ps.Assignment(out.center, 0.5 * u[0, 1] - 2 * u[1, 0] + u[0, 0])]
+    op = ps.AutoDiffOp(fa, boundary_handling='zeros', time_constant_fields=[u])
+    assert 'diffu_C' in str(op.backward_assignments)
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    ut = torch.randn(10, 32, dtype=torch.float64, device='cuda', requires_grad=True)
+    assert torch.autograd.gradcheck(fn.apply, (ut,), atol=1e-4)
+
+
+def test_double_compute_type_for_float_fields():
+    """pystencils' default evaluates float32 fields in double; ``data_type='double'`` reproduces that."""
+    shape = (24, 128)
+    rng = np.random.default_rng(2)
+    U = rng.normal(size=shape).astype(np.float32)
+    res = {}
+    for dt in (None, 'double'):
+        op = make_config('c2', shape=shape, **({'data_type': dt} if dt else {}))
+        fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+        (o,) = fn.apply(_t(U))
+        res[dt] = o.cpu().numpy()
+        assert ('typedef double CT' in fn.code) == (dt == 'double')
+    ref = evaluate(make_config('c2', shape=shape).forward_assignments, dict(u=U), 'zeros')['out']
+    # double arithmetic, one rounding on store: at most 1 ulp of float32 away from the float64 oracle (FMA vs mul+add)
+    assert np.abs(res['double'] - ref).max() <= 1.2e-7 * np.abs(ref).max()
+    assert np.abs(res[None] - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('shape', [(1, 1, 4), (1, 3, 4), (2, 2, 8), (3, 1, 128), (5, 33, 132)])
+@pytest.mark.parametrize('bh', [None, 'zeros'])
+def test_degenerate_shapes(shape, bh):
+    """Arrays thinner than the stencil / the tile, single planes, single rows."""
+    import torch
+    op = make_config('c3', shape=shape, boundary_handling=bh)
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    rng = np.random.default_rng(3)
+    U, G = rng.normal(size=shape).astype(np.float32), rng.normal(size=shape).astype(np.float32)
+    ut = _t(U).requires_grad_(True)
+    (o,) = fn.apply(ut)
+    o.backward(_t(G))
+    ref_o, ref_d = forward_backward(op, dict(u=U), dict(out=G))
+    scale = max(1e-30, np.abs(ref_o['out']).max())
+    assert np.abs(o.detach().cpu().numpy() - ref_o['out']).max() <= 1e-6 * max(scale, 1.0)
+    assert np.abs(ut.grad.cpu().numpy() - ref_d['diffu']).max() <= 1e-6 * max(1.0, np.abs(ref_d['diffu']).max())
+
+
+def test_non_contiguous_inputs_and_non_default_stream():
+    import torch
+    op = make_config('c2', shape=(64, 128))
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    base = torch.randn(128, 64, device='cuda')
+    u = base.t()                                      # non-contiguous view
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        (o1,) = fn.apply(u)
+    s.synchronize()
+    (o2,) = fn.apply(u.contiguous())
+    assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize('name', ['c2', 'c3', 'c4'])
+def test_full_size_adjoint_identity_and_linearity(name):
+    """At the BASELINE sizes the oracle is too slow; use size-independent properties of linear stencils in 'zeros'
+    mode: <A x, y> == <x, A^T y> (the adjoint kernel is the exact transpose) and A(a x1 + x2) == a A x1 + A x2."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    op = make_config(name)
+    shape = tuple(int(s) for s in op.forward_input_fields[0].shape)
+    dt = torch.float32 if name != 'c4' else torch.float64
+    fk, bk = CompiledKernel(op.forward_ast_gpu), CompiledKernel(op.backward_ast_gpu)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(11)
+    x = torch.randn(shape, dtype=dt, device='cuda', generator=g)
+    y = torch.randn(shape, dtype=dt, device='cuda', generator=g)
+    Ax, Aty = torch.empty_like(x), torch.empty_like(x)
+    fk(u=x, out=Ax)
+    bk(diffout=y, diffu=Aty)
+    assert fk.last_variant == 'march' and bk.last_variant == 'march'
+    lhs = torch.dot(Ax.double().flatten(), y.double().flatten()).item()
+    rhs = torch.dot(x.double().flatten(), Aty.double().flatten()).item()
+    tol = 1e-5 if name != 'c4' else 1e-12
+    assert abs(lhs - rhs) <= tol * (abs(lhs) + abs(rhs) + np.sqrt(x.numel()))
+    # linearity
+    x2 = torch.randn(shape, dtype=dt, device='cuda', generator=g)
+    Ax2, Acomb = torch.empty_like(x), torch.empty_like(x)
+    fk(u=x2, out=Ax2)
+    fk(u=0.5 * x + x2, out=Acomb)
+    err = (Acomb - (0.5 * Ax + Ax2)).abs().max().item()
+    assert err <= (2e-6 if name != 'c4' else 1e-14) * 4
+    # checksum of checksums: sum(A x) == <x, A^T 1> (column sums: 1 in the interior, less on the zero boundary)
+    ones, At1 = torch.ones_like(x), torch.empty_like(x)
+    bk(diffout=ones, diffu=At1)
+    lhs, rhs = Ax.double().sum().item(), torch.dot(x.double().flatten(), At1.double().flatten()).item()
+    assert abs(lhs - rhs) <= tol * (abs(lhs) + abs(rhs) + np.sqrt(x.numel()))
+
+
+def test_tv_full_size_is_finite_and_matches_generic_on_a_window():
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    op = make_config('c5', shape=(2, 4096, 4096))
+    fk = CompiledKernel(op.forward_ast_gpu)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(5)
+    u = torch.rand((2, 4096, 4096), device='cuda', generator=g)
+    f = torch.rand((2, 4096, 4096), device='cuda', generator=g)
+    o1, o2 = torch.empty_like(u), torch.empty_like(u)
+    fk(u=u, f=f, g=o1)
+    fk(u=u, f=f, g=o2, _variant='generic')
+    assert torch.isfinite(o1).all()
+    assert (o1 - o2).abs().max().item() <= 5e-5 * o2.abs().max().item()
