@@ -47,7 +47,8 @@ class CompiledKernel:
         self._march_reason = march_ineligible_reason(ir)
         if self._march_reason is None:
             try:
-                self._emitted['march'] = emit_march(ir, tuning)
+                self._emitted['march'] = emit_march(ir, tuning, masked=True)
+                self._emitted['march_nomask'] = emit_march(ir, tuning, masked=False)
             except ValueError as e:
                 self._march_reason = str(e)
         self._emitted['generic'] = emit_generic(ir)
@@ -62,7 +63,7 @@ class CompiledKernel:
 
     @property
     def variants(self):
-        return sorted(self._emitted)
+        return sorted(v for v in self._emitted if v != 'march_nomask')
 
     def emitted(self, variant):
         return self._emitted[variant]
@@ -127,6 +128,15 @@ class CompiledKernel:
                 raise TypeError('%s: missing scalar argument %r' % (self.function_name, s))
             scal.append(float(kwargs[s]))
         variant = _variant or self._select_variant(tensors)
+        if variant == 'march':
+            # the mask-free instance is valid whenever every written cell is also an evaluated cell
+            if _range is not None:
+                same = all(list(_range['iter_lo'][d:d + 1]) == list(_range['write_lo'][d:d + 1]) and
+                           list(_range['iter_hi'][d:d + 1]) == list(_range['write_hi'][d:d + 1]) for d in range(nd))
+            else:
+                same = self.ir.boundary == 'zeros' or self.ir.ghost_layers == 0
+            if same:
+                variant = 'march_nomask'
         field_args = []
         for f, t in zip(self.fields, tensors):
             st = list(t.stride()[:nd]) + [0] * (3 - nd)
@@ -135,7 +145,8 @@ class CompiledKernel:
         with torch.cuda.device(dev):
             stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
             self.native(variant).launch(field_args, scal, stream, _range)
-        self.last_variant = variant
+        self.last_variant = 'march' if variant == 'march_nomask' else variant
+        self.last_instance = variant
         return None
 
 

@@ -12,20 +12,19 @@ typedef unsigned long long psad_u64;
 
 PSAD_DEV psad_u32 psad_smem_u32(const void* p) { return (psad_u32)__cvta_generic_to_shared(p); }
 
-// ---- mbarrier ------------------------------------------------------------------------------------------------
-PSAD_DEV void psad_mbar_init(psad_u64* bar, psad_u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(psad_smem_u32(bar)), "r"(count) : "memory");
+// ---- mbarrier (all addresses are 32-bit shared-window addresses: no generic->shared conversion in the hot loop) ----
+PSAD_DEV void psad_mbar_init(psad_u32 bar, psad_u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 PSAD_DEV void psad_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 PSAD_DEV void psad_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-PSAD_DEV void psad_mbar_arrive_expect_tx(psad_u64* bar, psad_u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(psad_smem_u32(bar)), "r"(bytes)
-               : "memory");
+PSAD_DEV void psad_mbar_arrive_expect_tx(psad_u32 bar, psad_u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-PSAD_DEV void psad_mbar_arrive(psad_u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(psad_smem_u32(bar)) : "memory");
+PSAD_DEV void psad_mbar_arrive(psad_u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-PSAD_DEV void psad_mbar_wait(psad_u64* bar, psad_u32 parity) {
+PSAD_DEV void psad_mbar_wait(psad_u32 bar, psad_u32 parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -34,22 +33,22 @@ PSAD_DEV void psad_mbar_wait(psad_u64* bar, psad_u32 parity) {
       "@P1 bra PSAD_DONE;\n"
       "bra PSAD_WAIT;\n"
       "PSAD_DONE:\n"
-      "}\n" ::"r"(psad_smem_u32(bar)),
+      "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
 
 // ---- TMA tile loads (global -> shared, completion on an mbarrier; out-of-bounds elements are zero-filled) ---
-PSAD_DEV void psad_tma_load_2d(void* smem_dst, const PsadTensorMap* tmap, psad_u64* bar, int c0, int c1) {
+PSAD_DEV void psad_tma_load_2d(psad_u32 smem_dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(psad_smem_u32(smem_dst)), "l"((psad_u64)tmap), "r"(psad_smem_u32(bar)), "r"(c0), "r"(c1)
+      ::"r"(smem_dst), "l"((psad_u64)tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-PSAD_DEV void psad_tma_load_3d(void* smem_dst, const PsadTensorMap* tmap, psad_u64* bar, int c0, int c1, int c2) {
+PSAD_DEV void psad_tma_load_3d(psad_u32 smem_dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(psad_smem_u32(smem_dst)), "l"((psad_u64)tmap), "r"(psad_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      ::"r"(smem_dst), "l"((psad_u64)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 PSAD_DEV void psad_tma_prefetch_desc(const PsadTensorMap* tmap) {

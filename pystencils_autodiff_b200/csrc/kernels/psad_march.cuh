@@ -61,8 +61,9 @@ extern "C" __global__ void __launch_bounds__(cfg::THREADS + 32, cfg::MIN_CTAS)
 PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ PsadTmaps TM) {
   extern __shared__ __align__(1024) unsigned char psad_smem[];
   unsigned char* ring = psad_smem;
-  psad_u64* full = reinterpret_cast<psad_u64*>(psad_smem + (long long)cfg::STAGES * cfg::STAGE_BYTES);
-  psad_u64* empty = full + cfg::STAGES;
+  const psad_u32 ring_s = psad_smem_u32(psad_smem);                        // shared-window address of the ring
+  const psad_u32 full_s = ring_s + cfg::STAGES * cfg::STAGE_BYTES;         // STAGES "full" barriers (8 bytes each)
+  const psad_u32 empty_s = full_s + 8 * cfg::STAGES;                       // STAGES "empty" barriers
 
   constexpr int D = cfg::HZL + cfg::HZH;
   constexpr int NWARPS = cfg::THREADS / 32;        // consumer warps
@@ -76,8 +77,8 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < cfg::STAGES; ++s) {
-      psad_mbar_init(&full[s], 1);
-      psad_mbar_init(&empty[s], NWARPS);
+      psad_mbar_init(full_s + 8 * s, 1);
+      psad_mbar_init(empty_s + 8 * s, NWARPS);
     }
     psad_fence_barrier_init();
   }
@@ -95,16 +96,16 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
         const PsadItem it = psad_decode_item(A, item);
 #pragma unroll 1
         for (int p = it.p_first; p <= it.p_last; ++p) {
-          psad_mbar_wait(&empty[slot], parity);
-          psad_mbar_arrive_expect_tx(&full[slot], cfg::TX_BYTES);
-          unsigned char* base = ring + slot * cfg::STAGE_BYTES;
+          psad_mbar_wait(empty_s + 8 * slot, parity);
+          psad_mbar_arrive_expect_tx(full_s + 8 * slot, cfg::TX_BYTES);
+          const psad_u32 base = ring_s + slot * cfg::STAGE_BYTES;
 #pragma unroll
           for (int f = 0; f < cfg::NTMA; ++f) {
             if (cfg::NDIM == 3) {
-              psad_tma_load_3d(base + cfg::F_OFF[f], &TM.m[f], &full[slot], it.x0 + cfg::F_ORGX[f],
+              psad_tma_load_3d(base + cfg::F_OFF[f], &TM.m[f], full_s + 8 * slot, it.x0 + cfg::F_ORGX[f],
                                it.y0 + cfg::F_ORGY[f], p);
             } else {
-              psad_tma_load_2d(base + cfg::F_OFF[f], &TM.m[f], &full[slot], it.x0 + cfg::F_ORGX[f],
+              psad_tma_load_2d(base + cfg::F_OFF[f], &TM.m[f], full_s + 8 * slot, it.x0 + cfg::F_ORGX[f],
                                p * cfg::TY + cfg::F_ORGY[f]);
             }
           }
@@ -130,12 +131,12 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
     if (cfg::NDIM == 3) psad_item_begin(A, R, lane, warp, it.y0, it.x0);
 #pragma unroll 1
     for (int p = it.p_first; p <= it.p_last; ++p) {
-      psad_mbar_wait(&full[slot], parity);
+      psad_mbar_wait(full_s + 8 * slot, parity);
       const int zo = p - cfg::HZH;  // output plane (3-D) / row tile (2-D) of this step
       // the slot whose plane is read from shared memory for the last time in this step
       int rel = slot - REL_BACK;
       if (rel < 0) rel += cfg::STAGES;
-      psad_u64* rel_bar = (warm == 0) ? &empty[rel] : (psad_u64*)0;
+      const psad_u32 rel_bar = (warm == 0) ? empty_s + 8 * rel : 0u;   // 0 = nothing to release yet
       if (warm > 0) --warm;
       if (cfg::NDIM == 3) {
         psad_step(A, ring, slot, R, lane, warp, zo >= it.z0, zo, it.y0, it.x0, rel_bar, ph);

@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '8'
+EMITTER_VERSION = '9'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -300,7 +300,7 @@ def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
     return None
 
 
-def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> EmittedKernel:
+def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True) -> EmittedKernel:
     reason = march_ineligible_reason(ir)
     if reason:
         raise ValueError('march variant not applicable: ' + reason)
@@ -308,7 +308,9 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     if t.shuffle is None:
         import dataclasses
         t = dataclasses.replace(t, shuffle=max(f.dtype.itemsize for f in ir.all_fields) == 4)
-    name = _kernel_name(ir, 'march')
+    # masked=False: every written cell is inside the iteration range ('zeros' boundary, or a launch range whose
+    # iteration and write parts coincide) -> no per-cell select, no mask bookkeeping
+    name = _kernel_name(ir, 'march' if masked else 'march_nomask')
     CT = _CT[ir.compute_dtype]
     pr = _CudaPrinter(ir.compute_dtype)
     fields = ir.all_fields
@@ -556,7 +558,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
     for ph in range(NP):
         phase[0] = ph
         L.append('PSAD_DEV void psad_step_ph%d(const PsadArgs& A, const unsigned char* ring, int slot, PsadCarry& R, int lane,' % ph)
-        L.append('                        int wy, bool do_store, int z, int y0, int x0, psad_u64* rel_bar)')
+        L.append('                        int wy, bool do_store, int z, int y0, int x0, psad_u32 rel_bar)')
         L.append('{')
         for i, s_ in enumerate(scalars):
             L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s_), i))
@@ -655,13 +657,14 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
             L.append('  }')
         # compute + store
         L.append('  if (do_store) {')
-        if nd == 3:
+        if masked and nd == 3:
             L.append('    const unsigned zm = (z >= R.zlo && z < R.zhi) ? R.ymask_it : 0u;')
-        else:
+        elif masked:
             L.append('    const unsigned zm = R.ymask_it;')
         for r in range(RY):
             L.append('    if ((R.ymask_wr >> %d) & 1u) {' % r)
-            L.append('      const unsigned m = ((zm >> %d) & 1u) ? R.xmask : 0u;' % r)
+            if masked:
+                L.append('      const unsigned m = ((zm >> %d) & 1u) ? R.xmask : 0u;' % r)
             for lhs, _ in ir.main:
                 L.append('      %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
             for c in range(SX):
@@ -672,8 +675,11 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                     local[lhs] = _c_ident(lhs.name)
                 for lhs, rhs in main_exprs:
                     To = _CT[lhs.field.dtype.numpy_dtype]
-                    L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To,
-                                                                                       pr.print_with(rhs, local), To))
+                    if masked:
+                        L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To,
+                                                                                           pr.print_with(rhs, local), To))
+                    else:
+                        L.append('        o%d[%d] = (%s)(%s);' % (fidx[lhs.field.name], c, To, pr.print_with(rhs, local)))
                 L.append('      }')
             for f in out_fields:
                 fi = fidx[f.name]
@@ -689,7 +695,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
         L.append('}')
         L.append('')
     L.append('PSAD_DEV void psad_step(const PsadArgs& A, const unsigned char* ring, int slot, PsadCarry& R, int lane,')
-    L.append('                        int wy, bool do_store, int z, int y0, int x0, psad_u64* rel_bar, int ph)')
+    L.append('                        int wy, bool do_store, int z, int y0, int x0, psad_u32 rel_bar, int ph)')
     L.append('{')
     if NP == 1:
         L.append('  psad_step_ph0(A, ring, slot, R, lane, wy, do_store, z, y0, x0, rel_bar);')
@@ -714,6 +720,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> Emi
                 tile_x=TX, tile_y=TY, chunk=t.chunk, ctas_per_sm=t.ctas_per_sm, warmup=D, boundary=1 if ir.boundary == 'zeros' else 0,
                 ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
     ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
+    ek.masked = masked
     ek.geometry = dict(TX=TX, TY=TY, RY=RY, SX=SX, STAGES=STAGES, STAGE_BYTES=STAGE_BYTES, HZ=(HZL, HZH),
                        threads=THREADS, min_ctas=min_ctas)
     return ek

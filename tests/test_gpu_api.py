@@ -168,3 +168,57 @@ def test_tv_full_size_is_finite_and_matches_generic_on_a_window():
     fk(u=u, f=f, g=o2, _variant='generic')
     assert torch.isfinite(o1).all()
     assert (o1 - o2).abs().max().item() <= 5e-5 * o2.abs().max().item()
+
+
+@pytest.mark.parametrize('name,shape,T', [('c4', (10, 14, 64), 4), ('c3', (12, 18, 128), 3)])
+def test_multi_timestep_unrolled_autograd(name, shape, T):
+    """BASELINE config 4: T unrolled ``op.apply`` calls, loss = sum(out_T * r); gradient w.r.t. the initial field
+    against the oracle chain (forward T times, adjoint T times in reverse)."""
+    import torch
+    op = make_config(name, shape=shape, boundary_handling='zeros')
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    rng = np.random.default_rng(9)
+    dt = op.forward_input_fields[0].dtype.numpy_dtype
+    U0, Rw = rng.normal(size=shape).astype(dt), rng.normal(size=shape).astype(dt)
+    u = _t(U0).requires_grad_(True)
+    x = u
+    for _ in range(T):
+        (x,) = fn.apply(x)
+    loss = (x * _t(Rw)).sum()
+    loss.backward()
+    ref = U0.astype(np.float64)
+    for _ in range(T):
+        ref = evaluate(op.forward_assignments, dict(u=ref.astype(dt)), 'zeros')['out'].astype(np.float64)
+    g = Rw.astype(np.float64)
+    for _ in range(T):
+        g = evaluate(op.backward_assignments, dict(diffout=g.astype(dt)), 'zeros')['diffu'].astype(np.float64)
+    tol = 1e-12 if dt == np.float64 else 2e-6
+    assert np.abs(x.detach().cpu().numpy() - ref).max() <= tol * np.abs(ref).max()
+    assert np.abs(u.grad.cpu().numpy() - g).max() <= tol * np.abs(g).max()
+    # linear stencil: nothing is saved for backward, intermediates can be freed as the chain advances
+    assert fn.backward_kernel.ir.input_fields[0].name == 'diffout' and len(fn.backward_kernel.ir.input_fields) == 1
+
+
+def test_cuda_graph_capture_of_forward_and_adjoint():
+    """Launches go through cuLaunchKernel on torch's current stream, so a step can be captured in a CUDA graph and
+    replayed (launch-bound small fields)."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    op = make_config('c2', shape=(256, 256))
+    fk, bk = CompiledKernel(op.forward_ast_gpu), CompiledKernel(op.backward_ast_gpu)
+    u = torch.randn(256, 256, device='cuda')
+    out, du = torch.empty_like(u), torch.empty_like(u)
+    fk(u=u, out=out)
+    bk(diffout=out, diffu=du)
+    torch.cuda.synchronize()
+    ref = du.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            fk(u=u, out=out)
+            bk(diffout=out, diffu=du)
+    du.zero_()
+    gr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(du, ref)
