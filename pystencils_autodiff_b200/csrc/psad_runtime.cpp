@@ -396,8 +396,9 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
       const int e = 3 - nd + d;
       A.it_lo[e] = range->iter_lo[d]; A.it_hi[e] = range->iter_hi[d];
       A.wr_lo[e] = range->write_lo[d]; A.wr_hi[e] = range->write_hi[d];
-      if (A.wr_lo[e] < 0 || A.wr_hi[e] > A.shape[e] || A.it_lo[e] < A.wr_lo[e] - 64 || A.it_hi[e] > A.wr_hi[e] + 64)
-        return fail(PSAD_ERR_INVALID, "%s: range out of bounds in dim %d", k->name.c_str(), d);
+      if (A.wr_lo[e] < 0 || A.wr_hi[e] > A.shape[e])
+        return fail(PSAD_ERR_INVALID, "%s: write range [%lld, %lld) outside the array extent %lld in dim %d", k->name.c_str(),
+                    A.wr_lo[e], A.wr_hi[e], A.shape[e], d);
     }
   } else if (P.boundary == 0 && P.ghost_layers > 0) {
     for (int d = 0; d < nd; ++d) {

@@ -28,7 +28,7 @@ import numpy as np
 from . import runtime
 from .backends._torch_native import CompiledKernel, numpy_dtype_to_torch
 
-__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'SlabStencilOp', 'HostStreamedOp']
+__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
 
 
 class SlabDecomposition:
@@ -288,6 +288,9 @@ class SlabDataHandling:
             return
         self.torch.cuda.current_stream(self.device).wait_event(self._ev_halo)
 
+    def create_timeloop(self, use_cuda_graph=True):
+        return TimeLoop(self, use_cuda_graph)
+
     # -- kernels ---------------------------------------------------------------------------------------------------
     def run_kernel(self, kernel, halo_fields=(), **kwargs):
         """``kernel(**arrays, **kwargs)`` on the owned planes.  ``halo_fields``: inputs whose ghost planes must be
@@ -310,6 +313,87 @@ class SlabDataHandling:
                     kernel(**arrays, **kwargs, _range=r)
         elif halo_fields:
             self.finish_exchange()
+
+
+class TimeLoop:
+    """Recorded sequence of steps, replayed ``n`` times.
+
+    API of the reference's ``GraphDataHandling.TimeLoop`` (graph_datahandling.py:152-194: ``add_pre_run_function``,
+    ``add_post_run_function``, ``add_single_step_function``, ``add_call``, ``run``).  On one GPU the body of a time step
+    (kernel launches and swaps) is captured once into a **CUDA graph** and replayed, which removes the per-launch host
+    latency for small fields; with more than one rank (halo exchange inside the step) the calls are issued eagerly.
+    """
+
+    def __init__(self, data_handling, use_cuda_graph=True):
+        self.dh = data_handling
+        self._pre, self._post, self._steps = [], [], []
+        self.time_steps_run = 0
+        self._graph = None
+        self._graph_parity = 0
+        self.use_cuda_graph = use_cuda_graph
+
+    def add_pre_run_function(self, f):
+        self._pre.append(f)
+
+    def add_post_run_function(self, f):
+        self._post.append(f)
+
+    def add_single_step_function(self, f):
+        self._steps.append(f)
+        self._graph = None
+
+    def add_call(self, functor, argument_list=None):
+        args = argument_list if argument_list is not None else {}
+        if isinstance(args, dict):
+            args = [args]
+        for a in args:
+            if isinstance(functor, CompiledKernel):
+                halo = a.pop('halo_fields', ()) if isinstance(a, dict) else ()
+                self.add_single_step_function(lambda k=functor, kw=a, h=halo: self.dh.run_kernel(k, halo_fields=h, **kw))
+            else:
+                self.add_single_step_function(lambda f=functor, kw=a: f(**kw))
+
+    def _one_step(self):
+        for f in self._steps:
+            f()
+
+    def run(self, time_steps=1):
+        torch = self.dh.torch
+        for f in self._pre:
+            f()
+        swaps_per_step = None
+        graph_ok = (self.use_cuda_graph and self.dh.dec.world_size == 1 and torch.cuda.is_available()
+                    and all(t.is_cuda for t in self.dh.gpu_arrays.values()))
+        if graph_ok and time_steps >= 4:
+            # warm up (NVRTC / module load must not happen during capture), then capture TWO steps: a step that
+            # swaps buffers is only periodic with period 2
+            n0 = len([c for c in self.dh.call_queue if c[0] == 'Swap'])
+            self._one_step()
+            self._one_step()
+            swaps_per_step = (len([c for c in self.dh.call_queue if c[0] == 'Swap']) - n0) // 2
+            done = 2
+            if self._graph is None:
+                stream = torch.cuda.Stream(self.dh.device)
+                stream.wait_stream(torch.cuda.current_stream(self.dh.device))
+                with torch.cuda.stream(stream):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream):
+                        self._one_step()
+                        self._one_step()
+                torch.cuda.current_stream(self.dh.device).wait_stream(stream)
+                self._graph = g
+            while done + 2 <= time_steps:
+                self._graph.replay()
+                done += 2
+            for _ in range(time_steps - done):
+                self._one_step()
+        else:
+            for _ in range(time_steps):
+                self._one_step()
+        self.time_steps_run += time_steps
+        for f in self._post:
+            f()
+        return swaps_per_step
 
 
 class SlabStencilOp:

@@ -277,7 +277,7 @@ class MarchTuning:
     arrival: Optional[bool] = None  # evaluate EVERY per-plane group of the sum when its plane arrives and carry only
     #                                 scalars (no raw values); default: when the stencil has more than 9 accesses
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
-    #                                  (default: yes for 4-byte fields, no for 8-byte fields — measured)
+    #                                  (default: yes; scalar LDS halos only win for narrow fp64 strips)
 
 
 def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
@@ -307,7 +307,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked
     t = tuning or MarchTuning()
     if t.shuffle is None:
         import dataclasses
-        t = dataclasses.replace(t, shuffle=max(f.dtype.itemsize for f in ir.all_fields) == 4)
+        t = dataclasses.replace(t, shuffle=True)
     # masked=False: every written cell is inside the iteration range ('zeros' boundary, or a launch range whose
     # iteration and write parts coincide) -> no per-cell select, no mask bookkeeping
     name = _kernel_name(ir, 'march' if masked else 'march_nomask')
@@ -329,14 +329,14 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked
     HZL, HZH = (mh3[0] if nd == 3 else (0, 0))
     D = HZL + HZH
     # measured on B200 (scripts/sweep.py, profiles/): fp32 3-D 32x128 tiles / 2 rows per thread, fp32 2-D 16x128 / 1 row,
-    # fp64 14x128 tiles / 2 rows
+    # fp64 21x128 tiles / 3 rows, x-halos by warp shuffle (27-pt: 6.44 TB/s)
     if max_esize == 4:
         RY = t.ry or (2 if nd == 3 else 1)
         TY = t.ty or (32 if nd == 3 else 16)
     else:
         # 7 consumer warps + the producer warp = 8 warps: ptxas budgets registers for the CTA size rounded up to 4
         # warps, so 8+1 warps would be capped at 168 registers and spill (the 27-point window needs ~240)
-        RY = t.ry or 2
+        RY = t.ry or 3
         TY = t.ty or 7 * RY
     if TY % RY:
         raise ValueError('ty must be a multiple of ry')

@@ -222,3 +222,50 @@ def test_cuda_graph_capture_of_forward_and_adjoint():
     gr.replay()
     torch.cuda.synchronize()
     assert torch.equal(du, ref)
+
+
+def test_timeloop_with_swap_and_cuda_graph_replay():
+    """TimeLoop (graph_datahandling.py:152-194 API) over SlabDataHandling: kernel + swap per step, replayed from a
+    CUDA graph, equals the same steps issued eagerly and the oracle chain."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    shape, T = (64, 128), 11
+    op = make_config('c2', shape=shape)
+    kern = CompiledKernel(op.forward_ast_gpu)
+    rng = np.random.default_rng(4)
+    U0 = rng.normal(size=shape).astype(np.float32)
+    results = []
+    for use_graph in (True, False):
+        dh = SlabDataHandling(shape, 0, 1, 0, device='cuda:0')
+        dh.add_arrays('u, out', dtype=np.float32)
+        dh.owned('u').copy_(_t(U0))
+        tl = dh.create_timeloop(use_cuda_graph=use_graph)
+        tl.add_call(kern, {})
+        tl.add_single_step_function(lambda d=dh: d.swap('u', 'out'))
+        tl.run(T)
+        torch.cuda.synchronize()
+        assert tl.time_steps_run == T
+        results.append(dh.owned('u').clone())
+        kinds = [c[0] for c in dh.call_queue]
+        assert kinds.count('KernelCall') >= 2 and 'Swap' in kinds
+    assert torch.equal(results[0], results[1])
+    ref = U0
+    for _ in range(T):
+        ref = evaluate(op.forward_assignments, dict(u=ref), 'zeros')['out']
+    assert np.abs(results[0].cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_tensor_field_front_door():
+    import torch
+    from pystencils_autodiff_b200.field_tensor_conversion import (coerce_to_field, create_field_from_array_like,
+                                                                   is_array_like, torch_tensor_from_field)
+    a, b = torch.zeros((20, 10)), torch.zeros((6, 7), dtype=torch.float64)
+    x, y = ps.fields(x=a, y=b)          # tests/backends/test_torch_native_compilation.py:247-256
+    assert x.shape == (20, 10) and y.dtype.numpy_dtype == np.float64
+    c = torch.zeros((20, 10)).cuda()
+    z = ps.fields(z=c)
+    assert z.shape == (20, 10) and is_array_like(c) and not is_array_like(z)
+    assert coerce_to_field('w', c).name == 'w' and create_field_from_array_like('q', b).strides == (7, 1)
+    t = torch_tensor_from_field(z, init_val=2.0, cuda=True)
+    assert t.is_cuda and t.shape == (20, 10) and float(t[0, 0]) == 2.0
