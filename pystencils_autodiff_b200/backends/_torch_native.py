@@ -55,6 +55,7 @@ class CompiledKernel:
         self.fields = ir.all_fields
         self.scalars = [s.name for s in ir.scalars]
         self.last_variant = None
+        self._torch_dtypes = None
 
     # -- introspection ---------------------------------------------------------------------------------------
     @property
@@ -71,10 +72,16 @@ class CompiledKernel:
     def get_parameters(self):
         return self.ir.get_parameters()
 
-    def native(self, variant):
-        if variant not in self._native:
-            self._native[variant] = runtime.NativeKernel(self._emitted[variant])
-        return self._native[variant]
+    def native(self, variant, device_index=None):
+        """``psad_kernel_t`` of a variant for one device (modules are loaded per CUDA context); must be called with
+        that device current."""
+        if device_index is None:
+            import torch
+            device_index = torch.cuda.current_device()
+        key = (variant, device_index)
+        if key not in self._native:
+            self._native[key] = runtime.NativeKernel(self._emitted[variant])
+        return self._native[key]
 
     def precompile(self):
         """NVRTC-compile every variant into the cubin cache (no GPU needed)."""
@@ -98,6 +105,8 @@ class CompiledKernel:
 
     def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
         import torch
+        if self._torch_dtypes is None:
+            self._torch_dtypes = {f.name: numpy_dtype_to_torch(f.dtype.numpy_dtype) for f in self.fields}
         tensors = []
         for f in self.fields:
             if f.name not in kwargs:
@@ -106,7 +115,7 @@ class CompiledKernel:
             if not isinstance(t, torch.Tensor) or not t.is_cuda:
                 raise TypeError('%s: field %r must be a CUDA tensor (this backend has no CPU path)'
                                 % (self.function_name, f.name))
-            if t.dtype != numpy_dtype_to_torch(f.dtype.numpy_dtype):
+            if t.dtype != self._torch_dtypes[f.name]:
                 raise TypeError('%s: field %r expects dtype %s, got %s' % (self.function_name, f.name,
                                                                           f.dtype.numpy_dtype, t.dtype))
             if t.dim() != f.spatial_dimensions + f.index_dimensions:
@@ -144,7 +153,8 @@ class CompiledKernel:
             field_args.append((t.data_ptr(), tuple(t.shape[:nd]), st))
         with torch.cuda.device(dev):
             stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
-            self.native(variant).launch(field_args, scal, stream, _range)
+            self.native(variant, dev.index if dev.index is not None else torch.cuda.current_device()).launch(
+                field_args, scal, stream, _range)
         self.last_variant = 'march' if variant == 'march_nomask' else variant
         self.last_instance = variant
         return None

@@ -301,6 +301,28 @@ def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
 
 
 def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True) -> EmittedKernel:
+    """Emit the march variant; when the default tile does not fit (several wide-halo fp64 fields), fall back to
+    shallower prefetch and then to smaller tiles — unless the caller pinned those parameters."""
+    import dataclasses
+    t = tuning or MarchTuning()
+    candidates = [t]
+    if not t.lookahead and not t.stages:
+        candidates += [dataclasses.replace(t, lookahead=la) for la in (3, 2)]
+    if not t.ty and not t.ry:
+        for ry, ty in ((2, 14), (1, 15), (1, 7)):
+            candidates += [dataclasses.replace(t, ry=ry, ty=ty, lookahead=t.lookahead or 2)]
+    last = None
+    for cand in candidates:
+        try:
+            return _emit_march(ir, cand, masked)
+        except ValueError as e:
+            last = e
+            if 'shared memory' not in str(e) and 'threads' not in str(e):
+                raise
+    raise last
+
+
+def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True) -> EmittedKernel:
     reason = march_ineligible_reason(ir)
     if reason:
         raise ValueError('march variant not applicable: ' + reason)

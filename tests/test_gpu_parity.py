@@ -118,3 +118,88 @@ def test_host_streamed_equals_resident(name, shape, chunk, bh):
     torch.cuda.synchronize()
     for n in st.output_names:
         assert torch.equal(host[n], dev[n].cpu()), n
+
+
+def _run_raw(asg, arrays_np, bh=None, scalars=None):
+    """Kernel call path (``CompiledKernel(**tensors)``) vs oracle for arbitrary assignment collections."""
+    import torch
+    import pystencils_autodiff_b200 as ps
+    from oracle import evaluate
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.ir import lower_assignments
+    ir = lower_assignments(asg, bh, 'k')
+    k = CompiledKernel(ir)
+    ref = evaluate(asg, arrays_np, bh, scalars)
+    tens = {n: torch.from_numpy(np.ascontiguousarray(a)).cuda() for n, a in arrays_np.items()}
+    for f in ir.output_fields:
+        if f.name not in tens:
+            tens[f.name] = torch.full(ref[f.name].shape, float('nan'), dtype=getattr(torch, ref[f.name].dtype.name),
+                                      device='cuda')
+    k(**{f.name: tens[f.name] for f in k.fields}, **(scalars or {}))
+    return {n: tens[n].cpu().numpy() for n in ref}, ref, k
+
+
+@pytest.mark.parametrize('bh', [None, 'zeros'])
+def test_one_dimensional_field(bh):
+    import pystencils_autodiff_b200 as ps
+    a, b = ps.fields('a, b: float64[257]')
+    asg = ps.AssignmentCollection({b.center: 0.25 * a[-2] - a[1] + a[0] ** 2})
+    got, ref, k = _run_raw(asg, dict(a=np.random.default_rng(0).normal(size=257)), bh)
+    assert k.last_variant == 'generic'
+    np.testing.assert_allclose(got['b'], ref['b'], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize('bh', [None, 'zeros'])
+def test_index_dimension_fields(bh):
+    """Vector fields (one index dimension): the curl of tests/test_tfmad.py:341-401 and its adjoint."""
+    import pystencils_autodiff_b200 as ps
+    u = ps.Field.create_fixed_size('curl_input', (20, 30), index_dimensions=0)
+    c = ps.Field.create_fixed_size('curl', (20, 30, 2), index_dimensions=1)
+    disc = ps.fd.Discretization2ndOrder(dx=1)
+    fa = ps.AssignmentCollection([ps.Assignment(c.center(0), disc(ps.fd.Diff(u, 0))),
+                                  ps.Assignment(c.center(1), disc(ps.fd.Diff(u, 1)))], [])
+    op = ps.AutoDiffOp(fa, boundary_handling=bh)
+    rng = np.random.default_rng(1)
+    got, ref, k = _run_raw(op.forward_assignments, dict(curl_input=rng.normal(size=(20, 30))), bh)
+    assert k.last_variant == 'generic'
+    np.testing.assert_allclose(got['curl'], ref['curl'], rtol=1e-13, atol=1e-13)
+    got, ref, k = _run_raw(op.backward_assignments, dict(diffcurl=rng.normal(size=(20, 30, 2))), bh)
+    np.testing.assert_allclose(got['diffcurl_input'], ref['diffcurl_input'], rtol=1e-13, atol=1e-13)
+
+
+def test_off_centre_write_and_wide_offsets():
+    import pystencils_autodiff_b200 as ps
+    x, y = ps.fields('x, y: float32[40,136]')
+    asg = ps.AssignmentCollection({y[0, 1]: x[0, 0] + 2 * x[-1, 0]})            # off-centre lhs -> generic
+    got, ref, k = _run_raw(asg, dict(x=np.random.default_rng(2).normal(size=(40, 136)).astype(np.float32)))
+    assert k.last_variant == 'generic'
+    np.testing.assert_allclose(got['y'], ref['y'], rtol=1e-6, atol=1e-6)
+    asg = ps.AssignmentCollection({y.center: x[0, 3] - x[0, -4] + x[2, 0] * x[-3, 1]})   # |dx| up to the strip width
+    for bh in (None, 'zeros'):
+        got, ref, k = _run_raw(asg, dict(x=np.random.default_rng(3).normal(size=(40, 136)).astype(np.float32)), bh)
+        assert k.last_variant == 'march'
+        np.testing.assert_allclose(got['y'], ref['y'], rtol=2e-6, atol=2e-6)
+    asg = ps.AssignmentCollection({y.center: x[0, 5] + x[0, 0]})                # wider than the strip -> generic
+    got, ref, k = _run_raw(asg, dict(x=np.random.default_rng(4).normal(size=(40, 136)).astype(np.float32)), 'zeros')
+    assert k.last_variant == 'generic'
+    np.testing.assert_allclose(got['y'], ref['y'], rtol=1e-6, atol=1e-6)
+
+
+def test_asymmetric_3d_stencil_with_two_inputs_and_scalar():
+    """Asymmetric z halo (0 below, 2 above), two input fields with different halos, a scalar parameter, fp64."""
+    import sympy as sp
+    import pystencils_autodiff_b200 as ps
+    a, b, o = ps.fields('a, b, o: float64[9,12,64]')
+    s = sp.Symbol('s')
+    asg = ps.AssignmentCollection({o.center: s * a[2, 0, 0] - a[1, -1, 1] * b[0, 0, 0] + sp.exp(-b[0, 1, 0] ** 2) + a[0, 0, -2]})
+    rng = np.random.default_rng(5)
+    arrays = dict(a=rng.normal(size=(9, 12, 64)), b=rng.normal(size=(9, 12, 64)))
+    for bh in (None, 'zeros'):
+        got, ref, k = _run_raw(asg, arrays, bh, scalars=dict(s=0.75))
+        assert k.last_variant == 'march'
+        np.testing.assert_allclose(got['o'], ref['o'], rtol=1e-12, atol=1e-12)
+        op = ps.AutoDiffOp(asg, boundary_handling=bh)
+        env = dict(arrays, diffo=rng.normal(size=(9, 12, 64)))
+        got, ref, k = _run_raw(op.backward_assignments, env, bh, scalars=dict(s=0.75))
+        for n in ref:
+            np.testing.assert_allclose(got[n], ref[n], rtol=1e-12, atol=1e-12)
