@@ -294,7 +294,10 @@ class SlabDataHandling:
     # -- kernels ---------------------------------------------------------------------------------------------------
     def run_kernel(self, kernel, halo_fields=(), **kwargs):
         """``kernel(**arrays, **kwargs)`` on the owned planes.  ``halo_fields``: inputs whose ghost planes must be
-        fresh — their exchange is overlapped with the interior planes of this kernel."""
+        fresh.  Their exchange runs on the communication stream while the interior planes are computed on the
+        current stream; the ``g`` boundary planes on each side are launched on the communication stream right behind
+        the exchange, so they overlap with (and fill the tail of) the interior launch instead of serialising after it.
+        The current stream then waits for that stream — a device-side dependency, no host synchronisation."""
         if not isinstance(kernel, CompiledKernel):
             raise TypeError('run_kernel expects a CompiledKernel (AutoDiffOp.forward_kernel_gpu / backward_kernel_gpu)')
         self.call_queue.append(('KernelCall', kernel.function_name))
@@ -304,14 +307,19 @@ class SlabDataHandling:
         for n in halo_fields:
             self.call_queue.append(('Communication', n, None, True))
             self.start_exchange(n)
+        side = [r for r in (lo, hi) if r is not None]
+        on_comm = bool(side) and self._comm_stream is not None and all(t.is_cuda for t in arrays.values())
+        if on_comm:
+            for r in side:
+                kernel(**arrays, **kwargs, _range=r, _stream=self._comm_stream.cuda_stream)
+            self._ev_halo.record(self._comm_stream)
         if interior is not None:
             kernel(**arrays, **kwargs, _range=interior)
-        if lo is not None or hi is not None:
+        if side and not on_comm:
             self.finish_exchange()
-            for r in (lo, hi):
-                if r is not None:
-                    kernel(**arrays, **kwargs, _range=r)
-        elif halo_fields:
+            for r in side:
+                kernel(**arrays, **kwargs, _range=r)
+        elif side or halo_fields:
             self.finish_exchange()
 
 

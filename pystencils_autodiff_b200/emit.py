@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '9'
+EMITTER_VERSION = '10'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 
@@ -625,17 +625,24 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
             return 'R.q%d_k%d_r%d[%d]' % (ci, (phase[0] + j + 1) % NP, r, c)
 
         def cell_map(r, c):
-            local = {}
+            # Accesses are first renamed to *absolute* element symbols of the thread's patch (field, plane position,
+            # row, column) and only then mapped to registers.  Every sum is ordered by these names, so an expression
+            # shared by two cells of the thread (the flux at x-1 of cell x is the flux at x of cell x-1) is printed
+            # identically for both and the compiler evaluates it once; the names do not depend on the window phase.
+            subs, local = {}, {}
             for f in tma_fields:
+                g = geo[f.name]
                 for a in raw_accesses[f.name]:
                     dz, dy, dx = _off3(a.offsets)
-                    local[a] = '((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx)
+                    key = sp.Symbol('E%d_%d_%d_%d' % (g['ti'], dz + HZL, r + dy + g['hy'][0], c + dx + g['hx'][0]))
+                    subs[a] = key
+                    local[key] = '((CT)%s)' % elem(f, dz + HZL, r + dy, c + dx)
             for s_ in ir.scalars:
                 local[s_] = _c_ident(s_.name)
             for ci, qc in enumerate(q_classes):
                 for dz in qc['members']:
                     local[sp.Symbol('psadQ_%d_%d' % (ci, dz + HZL))] = qelem(ci, dz + HZL, r, c)
-            return local
+            return subs, local
 
         for hi in sorted({qc['hi'] for qc in q_classes}):
             # all plane sums evaluated at this position, for all cells of the thread, over shared element symbols
@@ -656,7 +663,9 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
             plan = plan_linear(targets, set(elem_sym)) if t.linopt else None
             if plan is None:
                 for (ci, r, c), _ in targets:
-                    L.append('  %s = %s;' % (qelem(ci, hi + HZL, r, c), pr.print_with(q_classes[ci]['expr_hi'], cell_map(r, c))))
+                    subs, local = cell_map(r, c)
+                    L.append('  %s = %s;' % (qelem(ci, hi + HZL, r, c),
+                                             pr.print_with(q_classes[ci]['expr_hi'].xreplace(subs), local)))
                 continue
             txt = {str(k): v for k, v in elem_sym.items()}
             scal = {s_: _c_ident(s_.name) for s_ in ir.scalars}
@@ -690,18 +699,18 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
             for lhs, _ in ir.main:
                 L.append('      %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
             for c in range(SX):
-                local = cell_map(r, c)
+                subs, local = cell_map(r, c)
                 L.append('      {')
                 for lhs, rhs in ir.subexpressions:
-                    L.append('        const CT %s = %s;' % (_c_ident(lhs.name), pr.print_with(rhs, local)))
+                    L.append('        const CT %s = %s;' % (_c_ident(lhs.name), pr.print_with(rhs.xreplace(subs), local)))
                     local[lhs] = _c_ident(lhs.name)
                 for lhs, rhs in main_exprs:
                     To = _CT[lhs.field.dtype.numpy_dtype]
+                    text = pr.print_with(rhs.xreplace(subs), local)
                     if masked:
-                        L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To,
-                                                                                           pr.print_with(rhs, local), To))
+                        L.append('        o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fidx[lhs.field.name], c, c, To, text, To))
                     else:
-                        L.append('        o%d[%d] = (%s)(%s);' % (fidx[lhs.field.name], c, To, pr.print_with(rhs, local)))
+                        L.append('        o%d[%d] = (%s)(%s);' % (fidx[lhs.field.name], c, To, text))
                 L.append('      }')
             for f in out_fields:
                 fi = fidx[f.name]

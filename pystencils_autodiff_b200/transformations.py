@@ -7,8 +7,6 @@ the spatial shape of one accessed field (:20).  The CUDA path does not evaluate 
 same semantics from TMA out-of-bounds zero fill / an index predicate — but the lowering in ``ir.py`` recognises
 it, and the oracle evaluates it literally, which is how the two are cross-checked.
 """
-import itertools
-
 import sympy as sp
 
 from .assignment import Assignment, AssignmentCollection, sympy_cse, coerce_assignments
@@ -38,28 +36,33 @@ class ConditionalFieldAccess(sp.Function):
         return self.args[2] if len(self.args) > 2 else sp.Integer(0)
 
 
+def _out_of_bounds(offsets, counters, shape):
+    """``ctr_k + o_k`` falls outside ``[0, N_k)`` on any axis."""
+    per_axis = []
+    for o, ctr, n in zip(offsets, counters, shape):
+        pos = ctr + o
+        per_axis.append(sp.Or(pos < 0, pos >= n))
+    return sp.Or(*per_axis)
+
+
 def add_fixed_constant_boundary_handling(assignments, with_cse=True):
-    assignments = coerce_assignments(assignments)
-    field_accesses = set().union(itertools.chain.from_iterable(
-        [a.atoms(Field.Access) for a in assignments]))
+    """Guard every relative read with "0 outside the array" (the reference's ``'zeros'`` boundary handling)."""
+    collection = coerce_assignments(assignments)
+    accesses = set()
+    for a in collection.all_assignments:
+        accesses |= a.atoms(Field.Access)
+    if not any(o != 0 for acc in accesses for o in acc.offsets):
+        return collection                      # pointwise kernels need no guard
+    # all fields of a kernel share one spatial shape; take it from the first access in name order
+    shape = min(accesses, key=str).field.spatial_shape
+    counters = list(x_vector(len(shape)))
 
-    if all(all(o == 0 for o in a.offsets) for a in field_accesses):
-        return assignments
-    common_shape = sorted(field_accesses, key=str)[0].field.spatial_shape
-    ndim = len(common_shape)
+    def guard(expr):
+        wrapped = {acc: ConditionalFieldAccess(acc, _out_of_bounds(acc.offsets, counters, shape))
+                   for acc in expr.atoms(Field.Access) if not acc.is_absolute_access}
+        return expr.subs(wrapped)
 
-    def is_out_of_bound(access, shape):
-        return sp.Or(*[sp.Or(a < 0, a >= s) for a, s in zip(access, shape)])
-
-    safe_assignments = [Assignment(
-        assignment.lhs, assignment.rhs.subs({
-            a: ConditionalFieldAccess(a, is_out_of_bound(sp.Matrix(a.offsets) + x_vector(ndim), common_shape))
-            for a in assignment.rhs.atoms(Field.Access) if not a.is_absolute_access
-        })) for assignment in assignments.all_assignments]
-
-    main = [a for a in safe_assignments if isinstance(a.lhs, Field.Access)]
-    sub = [a for a in safe_assignments if not isinstance(a.lhs, Field.Access)]
-    result = AssignmentCollection(main, sub)
-    if with_cse:
-        result = sympy_cse(result)
-    return result
+    guarded = [Assignment(a.lhs, guard(a.rhs)) for a in collection.all_assignments]
+    result = AssignmentCollection([a for a in guarded if isinstance(a.lhs, Field.Access)],
+                                  [a for a in guarded if not isinstance(a.lhs, Field.Access)])
+    return sympy_cse(result) if with_cse else result
