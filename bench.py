@@ -227,8 +227,10 @@ def main_ours(args):
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(evs[i])
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time spent issuing one step (not a GPU time)
     end.record()
     barrier()
     launches = runtime.launch_count() - n0
@@ -284,6 +286,7 @@ def main_ours(args):
                         'chunks, H2D / forward+adjoint kernels / D2H overlapped on three streams') if world == 1 else
                        'SlabStencilOp: H2D of the slab, halo exchange + kernels, D2H of outputs and input gradients'},
         'gpu_launches': launches,
+        'host_issue_ms_per_step': host_ms,
     }
     if not args.no_cpu_baseline:
         base, _ = cpu_reference_run(wl, steps=5, warmup=2)

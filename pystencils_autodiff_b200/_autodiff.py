@@ -327,7 +327,7 @@ class AutoDiffOp:
 
     # -- lowered kernels (what the emitter specialises) ---------------------------------------------------------
     def _lower(self, assignments, suffix):
-        kw = {k: v for k, v in self._kwargs.items() if k in ('ghost_layers', 'data_type')}
+        kw = {k: v for k, v in self._kwargs.items() if k in ('ghost_layers', 'data_type', 'fast_math')}
         return lower_assignments(assignments, self._boundary_handling, self.op_name + suffix, **kw)
 
     @property

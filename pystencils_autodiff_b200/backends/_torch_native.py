@@ -140,8 +140,10 @@ class CompiledKernel:
         if variant == 'march':
             # the mask-free instance is valid whenever every written cell is also an evaluated cell
             if _range is not None:
-                same = all(list(_range['iter_lo'][d:d + 1]) == list(_range['write_lo'][d:d + 1]) and
-                           list(_range['iter_hi'][d:d + 1]) == list(_range['write_hi'][d:d + 1]) for d in range(nd))
+                same = _range.get('_same')
+                if same is None:
+                    same = _range['_same'] = (list(_range['iter_lo'][:nd]) == list(_range['write_lo'][:nd]) and
+                                              list(_range['iter_hi'][:nd]) == list(_range['write_hi'][:nd]))
             else:
                 same = self.ir.boundary == 'zeros' or self.ir.ghost_layers == 0
             if same:

@@ -181,6 +181,7 @@ class SlabDataHandling:
         self.gpu_arrays = OrderedDict()
         self.fields = OrderedDict()
         self.call_queue = []
+        self._range_cache = {}
         self._comm_stream = None
         self._ev_ready = None
         self._ev_halo = None
@@ -303,7 +304,10 @@ class SlabDataHandling:
         self.call_queue.append(('KernelCall', kernel.function_name))
         arrays = {f.name: self.gpu_arrays[f.name] for f in kernel.fields}
         ir = kernel.ir
-        interior, lo, hi = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
+        key = id(kernel)
+        if key not in self._range_cache:
+            self._range_cache[key] = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
+        interior, lo, hi = self._range_cache[key]
         for n in halo_fields:
             self.call_queue.append(('Communication', n, None, True))
             self.start_exchange(n)

@@ -31,6 +31,9 @@ KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'k
 EMITTER_VERSION = '10'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
+# AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
+# chains stay as they are
+FAST_MATH_OPTIONS = ['-ftz=true', '-prec-div=false', '-prec-sqrt=false']
 
 
 @dataclass
@@ -254,7 +257,10 @@ def emit_generic(ir: StencilKernelIR, threads=256) -> EmittedKernel:
                              is_output=int(f in ir.output_fields),
                              index_size=int(f.index_shape[0]) if f.index_dimensions else 1, tma=0, box=(0, 0, 0))
                         for f in fields])
-    return EmittedKernel(name, 'generic', '\n'.join(L), ir, fields, scalars, plan)
+    ek = EmittedKernel(name, 'generic', '\n'.join(L), ir, fields, scalars, plan)
+    if ir.fast_math:
+        ek.options = ek.options + FAST_MATH_OPTIONS
+    return ek
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -752,6 +758,8 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
                 ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
     ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
     ek.masked = masked
+    if ir.fast_math:
+        ek.options = ek.options + FAST_MATH_OPTIONS
     ek.geometry = dict(TX=TX, TY=TY, RY=RY, SX=SX, STAGES=STAGES, STAGE_BYTES=STAGE_BYTES, HZ=(HZL, HZH),
                        threads=THREADS, min_ctas=min_ctas)
     return ek

@@ -54,6 +54,7 @@ class StencilKernelIR:
     lhs_offset: Tuple[int, ...] = ()
     assignments: AssignmentCollection = None
     compute_dtype: np.dtype = None
+    fast_math: bool = False             # opt-in: flush-to-zero, approximate division / sqrt (like pystencils' fast approximations)
 
     # -- reference-compatible introspection (``_backport.py:20-29``: fields_read / fields_written) -----------
     @property
@@ -126,7 +127,7 @@ def _strip_conditional(expr):
 
 
 def lower_assignments(assignments, boundary_handling=None, function_name='kernel', ghost_layers=None,
-                      data_type=None) -> StencilKernelIR:
+                      data_type=None, fast_math=False) -> StencilKernelIR:
     ac = coerce_assignments(assignments)
     boundary = 'zeros' if (boundary_handling is not None and str(getattr(boundary_handling, 'value', boundary_handling)) == 'zeros') else 'none'
 
@@ -212,4 +213,4 @@ def lower_assignments(assignments, boundary_handling=None, function_name='kernel
     return StencilKernelIR(function_name=function_name, ndim=ndim, boundary=boundary, ghost_layers=gl,
                            input_fields=input_fields, output_fields=output_fields, scalars=scalars,
                            subexpressions=subexpressions, main=main, read_accesses=read_accesses,
-                           lhs_offset=lhs_offset, assignments=clean, compute_dtype=cdt)
+                           lhs_offset=lhs_offset, assignments=clean, compute_dtype=cdt, fast_math=bool(fast_math))

@@ -178,10 +178,13 @@ class NativeKernel:
             self._scal[i] = float(s)
         r = None
         if rng is not None:
-            r = Range()
-            for d in range(len(rng['iter_lo'])):
-                r.iter_lo[d], r.iter_hi[d] = rng['iter_lo'][d], rng['iter_hi'][d]
-                r.write_lo[d], r.write_hi[d] = rng['write_lo'][d], rng['write_hi'][d]
+            r = rng.get('_ctypes') if isinstance(rng, dict) else None
+            if r is None:
+                r = Range()
+                for d in range(len(rng['iter_lo'])):
+                    r.iter_lo[d], r.iter_hi[d] = rng['iter_lo'][d], rng['iter_hi'][d]
+                    r.write_lo[d], r.write_hi[d] = rng['write_lo'][d], rng['write_hi'][d]
+                rng['_ctypes'] = r          # launch ranges are reused every step: build the struct once
             r = ctypes.byref(r)
         check(lib().psad_kernel_launch(self._handle, fa, n, self._scal, len(scalars), r, ctypes.c_void_p(stream)),
               'psad_kernel_launch(%s)' % self.emitted.name)
