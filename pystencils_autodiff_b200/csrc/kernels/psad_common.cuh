@@ -76,8 +76,18 @@ template <typename T> PSAD_DEV void psad_lds_vec(const T* p, T* e) {
   PsadVec<T>::unpack(v, e);
 }
 // registers -> global, one aligned 16-byte streaming store (STG.128, evict-first: outputs are not re-read)
+#ifndef PSAD_STORE_MODE
+#define PSAD_STORE_MODE 1   // 0: default caching, 1: streaming / evict-first (.cs), 2: write-through (.wt)
+#endif
 template <typename T> PSAD_DEV void psad_stg_vec(T* p, const T* e) {
-  __stcs(reinterpret_cast<typename PsadVec<T>::type*>(p), PsadVec<T>::pack(e));
+  typedef typename PsadVec<T>::type V;
+#if PSAD_STORE_MODE == 0
+  *reinterpret_cast<V*>(p) = PsadVec<T>::pack(e);
+#elif PSAD_STORE_MODE == 2
+  __stwt(reinterpret_cast<V*>(p), PsadVec<T>::pack(e));
+#else
+  __stcs(reinterpret_cast<V*>(p), PsadVec<T>::pack(e));
+#endif
 }
 
 // ---- small integer powers by repeated multiplication (fixed association: ((x*x)*x)*...)

@@ -282,6 +282,7 @@ class MarchTuning:
     linopt: bool = True      # shared partial sums across the cells of a thread for linear plane sums (linopt.py)
     arrival: Optional[bool] = None  # evaluate EVERY per-plane group of the sum when its plane arrives and carry only
     #                                 scalars (no raw values); default: when the stencil has more than 9 accesses
+    store_mode: int = 1    # global store cache policy: 0 default, 1 streaming (.cs, default), 2 write-through
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes; scalar LDS halos only win for narrow fp64 strips)
 
@@ -525,6 +526,8 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     min_ctas = t.min_ctas or max(1, min(2048 // (THREADS + 32), (227 * 1024) // smem_bytes, 65536 // ((THREADS + 32) * est_regs)))
     out_fields = ir.output_fields
     L = _header(ir, 'march')
+    if t.store_mode != 1:
+        L.append('#define PSAD_STORE_MODE %d' % t.store_mode)
     L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT, 'namespace cfg {',
           'constexpr int NDIM = %d, TX = %d, TY = %d;' % (nd, TX, TY),
           'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d, JREL = %d, NP = %d;'

@@ -94,3 +94,57 @@ def test_iteration_space_rule():
     ir = lower_assignments(ps.add_fixed_constant_boundary_handling(ps.AssignmentCollection(asg)), None)
     assert ir.boundary == 'zeros' and ir.ghost_layers == 0
     assert ir.halo('u') == [(0, 2), (1, 0)]
+
+
+def test_show_code_and_kernel_options():
+    op = make_config('c5', shape=(2, 16, 128), fast_math=True)
+    k = CompiledKernel(op.forward_ast_gpu)
+    assert k.emitted('march').options == ['-fmad=false', '-ftz=true', '-prec-div=false', '-prec-sqrt=false']
+    assert 'rsqrtf' in k.emitted('march').source and 'powf' not in k.emitted('march').source
+    src = ps.show_code(op.forward_ast_gpu)
+    assert 'psad_tvgrad_forward_gpu' in src and 'PSAD_KERNEL_NAME' in src
+    # a mask-free instance exists for every march kernel and differs only in the selects
+    masked, plain = k.emitted('march').source, k.emitted('march_nomask').source
+    assert '? (float)(' in masked and '? (float)(' not in plain
+
+
+def test_tiles_fall_back_when_the_ring_does_not_fit():
+    import sympy as sp
+    a, b, o = ps.fields('a, b, o: float64[9,12,64]')
+    asg = ps.AssignmentCollection({o.center: a[2, 0, 0] - a[1, -1, 1] * b[0, 0, 0] + sp.exp(-b[0, 1, 0] ** 2) + a[0, 0, -2]})
+    op = ps.AutoDiffOp(asg, boundary_handling='zeros')
+    for ir in (op.forward_ast_gpu, op.backward_ast_gpu):
+        ek = emit_march(ir)
+        assert ek.plan['smem_bytes'] <= 227 * 1024
+        assert ek.plan['threads'] % 128 == 0        # 4k-1 consumer warps + the producer warp
+
+
+def test_linear_plan_shares_partial_sums():
+    from pystencils_autodiff_b200.linopt import plan_linear
+    import sympy as sp
+    U = {(r, c): sp.Symbol('u_%d_%d' % (r + 1, c + 1)) for r in range(-1, 3) for c in range(-1, 5)}
+
+    def plane(r, c, wc, wf, wk):
+        return (wc * U[r, c] + wf * (U[r - 1, c] + U[r + 1, c] + U[r, c - 1] + U[r, c + 1])
+                + wk * (U[r - 1, c - 1] + U[r - 1, c + 1] + U[r + 1, c - 1] + U[r + 1, c + 1]))
+    targets = []
+    for r in range(2):
+        for c in range(4):
+            targets += [(('q', r, c), plane(r, c, 0.05, 0.02, 0.0075)), (('p', r, c), plane(r, c, 0.4, 0.05, 0.02))]
+    plan = plan_linear(targets, set(U.values()))
+    assert plan.op_count() <= 15 * 8 < 34 * 8          # 34 flops per cell evaluated naively
+    # the plan is an exact re-association: evaluate it numerically
+    import random
+    random.seed(0)
+    vals = {str(s): random.random() for s in U.values()}
+    env = dict(vals)
+    for nm, x, y in plan.temps:
+        env[nm] = env[x] + env[y]
+    for nm, adds in plan.sums:
+        env[nm] = sum(env[x] for x in adds)
+    for (key, expr), (key2, lst) in zip(targets, plan.targets):
+        assert key == key2
+        got = sum(float(cw) * env[nm] for cw, nm in lst)
+        ref = float(expr.subs({s: vals[str(s)] for s in U.values()}))
+        assert abs(got - ref) < 1e-12
+    assert plan_linear([(0, U[0, 0] * U[0, 1])], set(U.values())) is None      # not linear -> no plan
