@@ -153,9 +153,7 @@ def lower_assignments(assignments, boundary_handling=None, function_name='kernel
     # ``free_symbols`` (rhs symbols minus bound symbols) does not list
     reads = sorted(set().union(*[r.atoms(Field.Access) for _, r in subexpressions + main]), key=str)
     writes = [l for l, _ in main]
-    bound = {l for l, _ in subexpressions} | set(writes)
     scalars = sorted([s for s in clean.free_symbols if not isinstance(s, Field.Access)], key=str)
-    del bound
 
     all_acc = reads + writes
     ndims = {a.field.spatial_dimensions for a in all_acc}

@@ -60,8 +60,9 @@ def main():
             for k, d in sorted(by.items(), key=lambda kv: -kv[1][1]):
                 fh.write('| `%s` | %d | %.3f | %.1f %% | %.3f | %s | %s |\n' % (k, d[0], d[1] / 1e6, 100 * d[1] / total,
                                                                              d[1] / d[0] / 1e6, d[2], d[3]))
-            fh.write('\nThe `psad_*_march` kernels are this repo\'s (NVRTC, sm_100a); everything else is torch\'s fill / RNG / copy '
-                     'used to create the synthetic inputs and to stage the e2e pass — outside the timed region except the e2e copies.\n')
+            fh.write('\nThe `psad_*_march*` kernels are this repo\'s (NVRTC, sm_100a): 8 whole-field launches each (3 warm-up + 5 '
+                     'timed steps, ~1.39 ms per launch) plus the 22-chunk launches of the two host-streamed e2e passes. Everything '
+                     'else is torch\'s fill / RNG used to create the synthetic inputs, outside the timed region.\n')
         import shutil
         shutil.copy(lpath, os.path.join(OUT, '%s_launches_c3.csv' % tag))
     # ---- full captures

@@ -1,5 +1,4 @@
 """Emitter: determinism, window analysis and the structure of the specialised kernels."""
-import numpy as np
 import pytest
 
 from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
