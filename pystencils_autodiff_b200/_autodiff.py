@@ -202,6 +202,7 @@ class AutoDiffOp:
         self._backward_field_map = None
         self._forward_ir = None
         self._backward_ir = None
+        self._fused_ir = None
 
         if backward_assignments:
             self._backward_assignments = coerce_assignments(backward_assignments)
@@ -344,6 +345,36 @@ class AutoDiffOp:
         if self._backward_ir is None:
             self._backward_ir = self._lower(self._backward_assignments, '_backward_gpu')
         return self._backward_ir
+
+    @property
+    def fused_assignments(self):
+        """Forward and adjoint assignments as ONE collection (forward subexpressions inlined).
+
+        Valid whenever the upstream gradients ``diff<out>`` are known together with the forward inputs — a linear loss,
+        a prescribed adjoint source, or evaluating operator and adjoint operator side by side.  One kernel then reads
+        every field once: for a nonlinear stencil the forward inputs that the adjoint's coefficients need are not
+        fetched a second time (README example: 32 -> 24 bytes per cell)."""
+        fwd = self._forward_assignments.new_without_subexpressions()
+        bwd = self._backward_assignments
+        written = {a.lhs.field.name for a in fwd.main_assignments}
+        if written & {f.name for f in bwd.free_fields}:
+            raise NotImplementedError('the adjoint reads a forward output: forward and adjoint cannot be fused')
+        return AssignmentCollection(list(fwd.main_assignments) + list(bwd.main_assignments), list(bwd.subexpressions))
+
+    @property
+    def fused_ast_gpu(self):
+        """Lowered forward+adjoint kernel (no counterpart in the reference, which always launches two kernels)."""
+        if getattr(self, '_fused_ir', None) is None:
+            fw, bw = self.forward_ast_gpu, self.backward_ast_gpu
+            if fw.boundary == 'none' and fw.ghost_layers != bw.ghost_layers:
+                raise NotImplementedError('forward and adjoint iterate over different interiors: use two kernels')
+            self._fused_ir = self._lower(self.fused_assignments, '_fused_gpu')
+        return self._fused_ir
+
+    @property
+    def fused_kernel_gpu(self):
+        from .backends._torch_native import compile_kernel
+        return compile_kernel(self.fused_ast_gpu)
 
     def _no_cpu(self, *_, **__):
         raise NotImplementedError(

@@ -316,8 +316,8 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked
     if not t.lookahead and not t.stages:
         candidates += [dataclasses.replace(t, lookahead=la) for la in (3, 2)]
     if not t.ty and not t.ry:
-        for ry, ty in ((2, 14), (1, 15), (1, 7)):
-            candidates += [dataclasses.replace(t, ry=ry, ty=ty, lookahead=t.lookahead or 2)]
+        for ry, ty in ((2, 30), (2, 14), (1, 15), (1, 7)):
+            candidates += [dataclasses.replace(t, ry=ry, ty=ty, lookahead=t.lookahead or (2 if ty < 30 else 0))]
     last = None
     for cand in candidates:
         try:
@@ -497,6 +497,10 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     words += sum(SX * (lhs.field.dtype.itemsize // 4) for lhs, _ in ir.main)
     words += sum((qc['hi'] - qc['lo'] + 1) * RY * SX * (np.dtype(ir.compute_dtype).itemsize // 4) for qc in q_classes)
     est_regs = min(255, words + 48)
+    # ptxas budgets registers for the CTA size rounded up to 4 warps; a tile whose window cannot fit would spill
+    reg_cap = min(255, 65536 // (-(-(THREADS + 32) // 128) * 128))
+    if words + 24 > reg_cap and not (t.ty or t.ry):
+        raise ValueError('register window of ~%d words does not fit %d threads (cap %d registers)' % (words, THREADS + 32, reg_cap))
 
     # The window is addressed by *physical* plane slot k = (plane index) mod NP.  In phase PH = step mod NP the
     # plane at stencil position j lives in slot (PH + j + 1) mod NP, so nothing has to be moved between steps: the

@@ -269,3 +269,34 @@ def test_tensor_field_front_door():
     assert coerce_to_field('w', c).name == 'w' and create_field_from_array_like('q', b).strides == (7, 1)
     t = torch_tensor_from_field(z, init_val=2.0, cuda=True)
     assert t.is_cuda and t.shape == (20, 10) and float(t[0, 0]) == 2.0
+
+
+@pytest.mark.parametrize('name,shape,lo', [('c1', (24, 32), 0.5), ('c2', (48, 128), -1), ('c5', (2, 32, 128), 0.0),
+                                           ('c3', (10, 30, 128), -1), ('c1', (20, 30), 0.5)])
+@pytest.mark.parametrize('bh', [None, 'zeros'])
+def test_fused_forward_adjoint_equals_two_kernels(name, shape, lo, bh):
+    """One launch over the union of forward and adjoint assignments == the two separate kernels."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    op = make_config(name, shape=shape, boundary_handling=bh)
+    fused = op.fused_kernel_gpu
+    assert fused.ir.bytes_per_cell() <= op.forward_ast_gpu.bytes_per_cell() + op.backward_ast_gpu.bytes_per_cell()
+    g = torch.Generator(device='cuda')
+    g.manual_seed(3)
+    tens = {}
+    for f in fused.ir.input_fields:
+        tens[f.name] = torch.rand(shape, dtype=getattr(torch, f.dtype.numpy_dtype.name), device='cuda', generator=g) + lo + 0.01
+    a = dict(tens)
+    for f in fused.ir.output_fields:
+        a[f.name] = torch.full(shape, float('nan'), dtype=tens[fused.ir.input_fields[0].name].dtype, device='cuda')
+    fused(**{f.name: a[f.name] for f in fused.fields})
+    b = dict(tens)
+    for k in (CompiledKernel(op.forward_ast_gpu), CompiledKernel(op.backward_ast_gpu)):
+        for f in k.ir.output_fields:
+            b[f.name] = torch.full(shape, float('nan'), dtype=a[f.name].dtype, device='cuda')
+        k(**{f.name: b[f.name] for f in k.fields})
+    for f in fused.ir.output_fields:
+        # same per-cell expressions; the summation order may differ (the fused kernel has more accesses and may
+        # switch to arrival-time plane sums), so allow rounding-level differences
+        scale = b[f.name].abs().max().item()
+        assert (a[f.name] - b[f.name]).abs().max().item() <= 2e-6 * max(scale, 1e-30), f.name

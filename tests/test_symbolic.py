@@ -171,3 +171,16 @@ def test_matches_reference_symbolic_output(name):
     assert sorted(f.name for f in op.backward_input_fields) == g['backward_input_fields']
     assert sorted(f.name for f in op.backward_output_fields) == g['backward_output_fields']
     assert str(ps.add_fixed_constant_boundary_handling(op.backward_assignments)) == g['backward_zeros']
+
+
+def test_fused_forward_adjoint_collection():
+    from pystencils_autodiff_b200.configs import make_config
+    op = make_config('c1', shape=(6, 7))
+    fused = op.fused_assignments
+    assert [a.lhs.field.name for a in fused.main_assignments] == ['z', 'diffx', 'diffy']
+    ir = op.fused_ast_gpu
+    assert [f.name for f in ir.input_fields] == ['diffz', 'x', 'y']
+    assert ir.bytes_per_cell() == 24 and op.forward_ast_gpu.bytes_per_cell() + op.backward_ast_gpu.bytes_per_cell() == 32
+    u, out = ps.fields('u, out: float32[8,8]')
+    op2 = ps.AutoDiffOp([ps.Assignment(out.center, u[1, 0] + u[0, 0] ** 2)])     # forward gl=1, adjoint gl=1
+    assert op2.fused_ast_gpu.ghost_layers == 1
