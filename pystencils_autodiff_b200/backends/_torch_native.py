@@ -22,7 +22,7 @@ from collections import OrderedDict
 import numpy as np
 
 from ..emit import emit_generic, emit_march, march_ineligible_reason
-from ..ir import StencilKernelIR
+from ..ir import StencilKernelIR, split_index_components
 from .. import runtime
 
 __all__ = ['create_autograd_function', 'compile_kernel', 'CompiledKernel', 'numpy_dtype_to_torch']
@@ -44,11 +44,13 @@ class CompiledKernel:
         self.tuning = tuning
         self._emitted = {}
         self._native = {}
-        self._march_reason = march_ineligible_reason(ir)
+        # fields with an index dimension reach the fast path as one scalar field per component (SoA layouts only)
+        self._scalar_ir, self._components = split_index_components(ir)
+        self._march_reason = march_ineligible_reason(self._scalar_ir)
         if self._march_reason is None:
             try:
-                self._emitted['march'] = emit_march(ir, tuning, masked=True)
-                self._emitted['march_nomask'] = emit_march(ir, tuning, masked=False)
+                self._emitted['march'] = emit_march(self._scalar_ir, tuning, masked=True)
+                self._emitted['march_nomask'] = emit_march(self._scalar_ir, tuning, masked=False)
             except ValueError as e:
                 self._march_reason = str(e)
         self._emitted['generic'] = emit_generic(ir)
@@ -94,12 +96,15 @@ class CompiledKernel:
     def _select_variant(self, tensors):
         if 'march' not in self._emitted:
             return 'generic'
+        nd = self.ir.ndim
         for f, t in zip(self.fields, tensors):
             es = t.element_size()
-            if t.stride(-1) != 1 or t.data_ptr() % 16 or (t.shape[-1] * es) % 16:
+            # x (the last SPATIAL dim) must be contiguous; every other pitch — including the index dimension's for
+            # structure-of-arrays vector fields — a multiple of 16 bytes
+            if t.stride(nd - 1) != 1 or t.data_ptr() % 16 or (t.shape[nd - 1] * es) % 16:
                 return 'generic'
-            for d in range(t.dim() - 1):
-                if (t.stride(d) * es) % 16:
+            for d in range(t.dim()):
+                if d != nd - 1 and (t.stride(d) * es) % 16:
                     return 'generic'
         return 'march'
 
@@ -149,10 +154,20 @@ class CompiledKernel:
             if same:
                 variant = 'march_nomask'
         field_args = []
-        for f, t in zip(self.fields, tensors):
-            st = list(t.stride()[:nd]) + [0] * (3 - nd)
-            st.append(t.stride(nd) if f.index_dimensions else 0)
-            field_args.append((t.data_ptr(), tuple(t.shape[:nd]), st))
+        if variant.startswith('march') and self._components:
+            by_name = {f.name: t for f, t in zip(self.fields, tensors)}
+            for cf in self._emitted['march'].fields:          # component fields, plan order of the scalar kernel
+                name, i = self._components.get(cf.name, (cf.name, None))
+                t = by_name[name]
+                off = 0 if i is None else i * t.stride(nd) * t.element_size()
+                if i is not None and i >= t.shape[nd]:
+                    raise ValueError('%s: index %d out of range for field %r' % (self.function_name, i, name))
+                field_args.append((t.data_ptr() + off, tuple(t.shape[:nd]), list(t.stride()[:nd]) + [0] * (4 - nd)))
+        else:
+            for f, t in zip(self.fields, tensors):
+                st = list(t.stride()[:nd]) + [0] * (3 - nd)
+                st.append(t.stride(nd) if f.index_dimensions else 0)
+                field_args.append((t.data_ptr(), tuple(t.shape[:nd]), st))
         with torch.cuda.device(dev):
             stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
             self.native(variant, dev.index if dev.index is not None else torch.cuda.current_device()).launch(
@@ -210,12 +225,38 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
         shape = tuple(int(s) for s in field.shape) if field.has_fixed_shape else \
             tuple(like.shape[:field.spatial_dimensions]) + tuple(int(s) for s in field.index_shape)
         maker = torch.zeros if read_too else torch.empty
-        return maker(shape, dtype=numpy_dtype_to_torch(field.dtype.numpy_dtype), device=device)
+        dtype = numpy_dtype_to_torch(field.dtype.numpy_dtype)
+        if field.index_dimensions:
+            # vector outputs are allocated structure-of-arrays (x contiguous) so that they qualify for the fast path;
+            # the returned tensor still has the field's logical shape [spatial..., index]
+            nsp = field.spatial_dimensions
+            t = maker(tuple(shape[nsp:]) + tuple(shape[:nsp]), dtype=dtype, device=device)
+            return t.permute(*range(len(shape) - nsp, len(shape)), *range(len(shape) - nsp))
+        return maker(shape, dtype=dtype, device=device)
+
+    fields_by_name = {f.name: f for f in list(fwd_inputs) + list(fwd_outputs) + list(bwd_inputs) + list(bwd_outputs)}
+
+    def _device_layout(t, field=None):
+        # the reference forces ``.cuda().contiguous()`` (:47-49).  Same here, except for vector fields that are stored
+        # structure-of-arrays (x contiguous, dense): those keep their layout, it is the one the fast kernels want
+        t = t.cuda()
+        if field is not None and field.index_dimensions and t.dim() == field.spatial_dimensions + 1:
+            nsp = field.spatial_dimensions
+            if t.stride(nsp - 1) == 1:
+                order = sorted(range(t.dim()), key=lambda d: -t.stride(d))
+                if t.permute(*order).is_contiguous():
+                    return t
+            # array-of-structs (or strided) vector field: one transposing copy, then the fast kernels apply
+            soa = t.permute(nsp, *range(nsp)).contiguous()
+            return soa.permute(*range(1, nsp + 1), 0)
+        return t if t.is_contiguous() else t.contiguous()
 
     def forward(ctx, *args, **kwargs):
         kwargs.update(class_kwargs)
-        args = [a.cuda().contiguous() if isinstance(a, torch.Tensor) else a for a in args]
-        kwargs = {k: v.cuda().contiguous() if isinstance(v, torch.Tensor) else v for k, v in kwargs.items()}
+        args = [_device_layout(a, fwd_inputs[i] if i < len(fwd_inputs) else None) if isinstance(a, torch.Tensor) else a
+                for i, a in enumerate(args)]
+        kwargs = {k: _device_layout(v, fields_by_name.get(k)) if isinstance(v, torch.Tensor) else v
+                  for k, v in kwargs.items()}
         if len(args) > len(fwd_inputs):
             raise TypeError('%s takes %d input tensors (%s), got %d'
                             % (op_name, len(fwd_inputs), [f.name for f in fwd_inputs], len(args)))
@@ -246,7 +287,7 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
             if g is None:
                 g = torch.zeros(tuple(int(s) for s in f.shape) if f.has_fixed_shape else shape,
                                 dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=device)
-            g = g.contiguous()
+            g = _device_layout(g, f) if g.is_cuda else g.contiguous()
             if not g.is_cuda:
                 raise AssertionError('Some of the tensors where on the wrong device. Op was compiled for CUDA: True')
             if f.has_fixed_shape and tuple(int(s) for s in f.shape) != tuple(g.shape):

@@ -22,7 +22,7 @@ from .assignment import AssignmentCollection, coerce_assignments
 from .field import Field
 from .transformations import ConditionalFieldAccess
 
-__all__ = ['StencilKernelIR', 'KernelParameter', 'lower_assignments']
+__all__ = ['StencilKernelIR', 'KernelParameter', 'lower_assignments', 'split_index_components']
 
 
 @dataclass
@@ -212,3 +212,43 @@ def lower_assignments(assignments, boundary_handling=None, function_name='kernel
                            input_fields=input_fields, output_fields=output_fields, scalars=scalars,
                            subexpressions=subexpressions, main=main, read_accesses=read_accesses,
                            lhs_offset=lhs_offset, assignments=clean, compute_dtype=cdt, fast_math=bool(fast_math))
+
+
+def split_index_components(ir: StencilKernelIR):
+    """Rewrite a kernel over fields with one index dimension as a kernel over scalar *component fields*.
+
+    ``v[offsets](i)`` becomes ``v__i[offsets]``: with a structure-of-arrays layout (x contiguous — the ``fzyx`` layout
+    the reference's lattice-Boltzmann code uses on GPUs, lbm/_autodiff_lbstep.py:69-86) component ``i`` of ``v`` is an
+    ordinary scalar field starting ``i * stride_index`` elements after ``v``, so the fast kernels apply unchanged.
+    Returns ``(scalar_ir, components)`` with ``components[name__i] = (original field name, i)``, or ``(ir, {})`` when no
+    field has an index dimension."""
+    if not any(f.index_dimensions for f in ir.all_fields):
+        return ir, {}
+    components, repl, cache = {}, {}, {}
+
+    def comp_field(f, i):
+        key = (f.name, i)
+        if key not in cache:
+            nf = Field.create_fixed_size('%s__%d' % (f.name, i), tuple(f.spatial_shape), 0, f.dtype.numpy_dtype) \
+                if f.has_fixed_shape else Field.create_generic('%s__%d' % (f.name, i), f.spatial_dimensions,
+                                                               f.dtype.numpy_dtype)
+            cache[key] = nf
+            components[nf.name] = (f.name, i)
+        return cache[key]
+
+    def conv(a):
+        if not a.field.index_dimensions:
+            return a
+        return Field.Access(comp_field(a.field, int(a.index[0])), a.offsets)
+
+    accesses = set()
+    for _, r in ir.subexpressions + ir.main:
+        accesses |= r.atoms(Field.Access)
+    for a in accesses:
+        repl[a] = conv(a)
+    sub = {l: r.xreplace(repl) for l, r in ir.subexpressions}
+    main = {conv(l): r.xreplace(repl) for l, r in ir.main}
+    scalar_ir = lower_assignments(AssignmentCollection(main, sub), 'zeros' if ir.boundary == 'zeros' else None,
+                                  ir.function_name, ghost_layers=ir.ghost_layers if ir.boundary != 'zeros' else None,
+                                  data_type=ir.compute_dtype, fast_math=ir.fast_math)
+    return scalar_ir, components

@@ -300,3 +300,27 @@ def test_fused_forward_adjoint_equals_two_kernels(name, shape, lo, bh):
         # switch to arrival-time plane sums), so allow rounding-level differences
         scale = b[f.name].abs().max().item()
         assert (a[f.name] - b[f.name]).abs().max().item() <= 2e-6 * max(scale, 1e-30), f.name
+
+
+def test_vector_output_through_the_function_uses_soa_and_fast_path():
+    """Curl (vector output): the Function allocates the output structure-of-arrays, both kernels take the march path,
+    gradcheck-style comparison against the oracle."""
+    import torch
+    shape = (24, 128)
+    u = ps.Field.create_fixed_size('curl_input', shape, index_dimensions=0, dtype=np.float64)
+    c = ps.Field.create_fixed_size('curl', shape + (2,), index_dimensions=1, dtype=np.float64)
+    disc = ps.fd.Discretization2ndOrder(dx=1)
+    fa = ps.AssignmentCollection([ps.Assignment(c.center(0), disc(ps.fd.Diff(u, 0))),
+                                  ps.Assignment(c.center(1), disc(ps.fd.Diff(u, 1)) + u.center ** 2)], [])
+    op = ps.AutoDiffOp(fa, boundary_handling='zeros')
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    rng = np.random.default_rng(6)
+    U, G = rng.normal(size=shape), rng.normal(size=shape + (2,))
+    ut = _t(U).requires_grad_(True)
+    (curl,) = fn.apply(ut)
+    assert tuple(curl.shape) == shape + (2,) and curl.stride(1) == 1
+    curl.backward(_t(G))
+    assert fn.forward_kernel.last_variant == 'march' and fn.backward_kernel.last_variant == 'march'
+    ref_o, ref_d = forward_backward(op, dict(curl_input=U), dict(curl=G))
+    np.testing.assert_allclose(curl.detach().cpu().numpy(), ref_o['curl'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ut.grad.cpu().numpy(), ref_d['diffcurl_input'], rtol=1e-12, atol=1e-12)
