@@ -90,6 +90,16 @@ template <typename T> PSAD_DEV void psad_stg_vec(T* p, const T* e) {
 #endif
 }
 
+// ---- reciprocal square root.  float: the hardware approximation (rsqrt.approx.ftz.f32, max relative error 2^-22.4 —
+// the accuracy class of CUDA's rsqrtf(), without its subnormal pre-scaling branches; subnormal arguments are treated
+// as zero).  double: CUDA's rsqrt() (1 ulp).
+PSAD_DEV float psad_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+PSAD_DEV double psad_rsqrt(double x) { return rsqrt(x); }
+
 // ---- small integer powers by repeated multiplication (fixed association: ((x*x)*x)*...)
 template <int N, typename T> PSAD_DEV T psad_ipow(T x) {
   T r = x;

@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '10'
+EMITTER_VERSION = '12'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
@@ -124,6 +124,30 @@ class _CudaPrinter(C99CodePrinter):
                 acc = '%s(%s, %s, %s)' % (fma, self._print(a), self._print(b), acc)
         return acc
 
+    def _print_Mul(self, expr):
+        # keep half-integer negative powers as *factors* (they print as psad_rsqrt(...), see _print_Pow) instead of
+        # letting the stock printer turn a*b**(-1/2) into a/sqrt(b): an IEEE division plus an IEEE square root
+        c, factors = expr.as_coeff_mul()
+        num, den = [], []
+        for f in factors:
+            if f.is_Pow and f.exp.is_Rational and f.exp.is_negative and f.exp.q != 2:
+                den.append(sp.Pow(f.base, -f.exp))
+            else:
+                num.append(f)
+        if not any(f.is_Pow and f.exp.is_Rational and f.exp.q == 2 and f.exp.is_negative for f in num):
+            return super()._print_Mul(expr)
+
+        def fac(f):
+            s_ = self._print(f)
+            return '(%s)' % s_ if f.is_Add else s_
+        parts = [fac(f) for f in num]
+        if c != 1 and c != -1:
+            parts.insert(0, self._print(c))
+        text = '*'.join(parts)
+        if den:
+            text = '%s/(%s)' % (text, '*'.join(fac(f) for f in den))
+        return '-(%s)' % text if c == -1 else text
+
     def _paren(self, e):
         s_ = self._print(e)
         return '(%s)' % s_ if (e.is_Add or e.is_Mul) else s_
@@ -139,13 +163,13 @@ class _CudaPrinter(C99CodePrinter):
         if e == -1:
             return '(%s/(%s))' % (self._one, self._print(b))
         if e.is_Rational and e.q == 2 and abs(int(e.p)) <= 9:
-            # half-integer powers through sqrt / rsqrt (CUDA math API, <= 2 ulp) instead of pow(): x**(3/2) = x*sqrt(x),
+            # half-integer powers through sqrt / psad_rsqrt (<= 2 ulp) instead of pow(): x**(3/2) = x*sqrt(x),
             # x**(-3/2) = rsqrt(x)**3.  The backward of anything containing 1/sqrt(...) is full of these.
             n = int(e.p)
             if n > 0:
                 root = '%s(%s)' % (self._sqrt, self._print(b))
                 return root if n == 1 else '(%s*%s)' % (root, self._print(sp.Pow(b, (n - 1) // 2)))
-            r = '%s(%s)' % ('rsqrtf' if self._sqrt == 'sqrtf' else 'rsqrt', self._print(b))
+            r = 'psad_rsqrt(%s)' % self._print(b)
             return r if n == -1 else 'psad_ipow<%d>(%s)' % (-n, r)
         return super()._print_Pow(expr)
 
