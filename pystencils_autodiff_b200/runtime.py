@@ -12,7 +12,25 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 KERNEL_DIR = os.path.join(CSRC_DIR, 'kernels')
 LIB_PATH = os.path.join(CSRC_DIR, 'libpsad.so')
-DEFAULT_CACHE_DIR = os.environ.get('PSAD_CACHE_DIR', os.path.join(_HERE, '_cubin_cache'))
+
+
+def _default_cache_dir():
+    """$PSAD_CACHE_DIR, else the in-tree cache (it travels with the repo snapshot), else ~/.cache when the package
+    directory is read-only (site-packages installs)."""
+    env = os.environ.get('PSAD_CACHE_DIR')
+    if env:
+        return env
+    in_tree = os.path.join(_HERE, '_cubin_cache')
+    try:
+        os.makedirs(in_tree, exist_ok=True)
+        if os.access(in_tree, os.W_OK):
+            return in_tree
+    except OSError:
+        pass
+    return os.path.join(os.path.expanduser('~'), '.cache', 'pystencils_autodiff_b200', 'cubin')
+
+
+DEFAULT_CACHE_DIR = _default_cache_dir()
 
 PSAD_MAX_FIELDS = 12
 PSAD_MAX_SCALARS = 16
