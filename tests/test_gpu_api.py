@@ -324,3 +324,52 @@ def test_vector_output_through_the_function_uses_soa_and_fast_path():
     ref_o, ref_d = forward_backward(op, dict(curl_input=U), dict(curl=G))
     np.testing.assert_allclose(curl.detach().cpu().numpy(), ref_o['curl'], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(ut.grad.cpu().numpy(), ref_d['diffcurl_input'], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('with_offsets', (False, True))
+def test_tfmad_gradient_check_torch_native_reference_case(with_offsets):
+    """/root/reference/tests/test_tfmad.py:186-231 verbatim (float64[5,7], 'zeros', gradcheck atol=1e-4), plus the
+    same check on random non-zero inputs (the reference only ever checks all-zero tensors)."""
+    import torch
+    a, b, out = ps.fields("a, b, out: float64[5,7]")
+    if with_offsets:
+        cont = 2 * ps.fd.Diff(a, 0) - 1.5 * ps.fd.Diff(a, 1) - ps.fd.Diff(b, 0) + 3 * ps.fd.Diff(b, 1)
+        assignment = ps.Assignment(out.center(), ps.fd.Discretization2ndOrder(dx=1)(cont) + 1.2 * a.center())
+    else:
+        assignment = ps.Assignment(out.center(), 1.2 * a.center + 0.1 * b.center)
+    auto_diff = ps.AutoDiffOp(ps.AssignmentCollection([assignment], []), boundary_handling='zeros',
+                              diff_mode='transposed-forward')
+    function = auto_diff.create_tensorflow_op(use_cuda=True, backend='torch_native')
+    for maker in (torch.zeros, torch.randn):
+        a_tensor = maker(*a.shape, dtype=torch.float64, device='cuda').requires_grad_(True)
+        b_tensor = maker(*b.shape, dtype=torch.float64, device='cuda').requires_grad_(True)
+        d = {a: a_tensor, b: b_tensor}
+        assert torch.autograd.gradcheck(function.apply, tuple(d[f] for f in auto_diff.forward_input_fields),
+                                        atol=1e-4, raise_exception=True)
+
+
+def test_tfmad_gradient_check_two_outputs_reference_case():
+    """/root/reference/tests/test_tfmad.py:234-285: three outputs incl. exp(b[-1,0]), float64[21,13], 'zeros'.
+    With the reference's all-zero inputs gradcheck passes; on random inputs the adjoint is the reference's
+    (un-shifted coefficient) and is compared with the oracle instead."""
+    import torch
+    a, b, out1, out2, out3 = ps.fields("a, b, out1, out2, out3: float64[21,13]")
+    ac = ps.AssignmentCollection({out1.center: a.center + b.center, out2.center: a.center - b.center,
+                                  out3.center: sp.exp(b[-1, 0])})
+    auto_diff = ps.AutoDiffOp(ac, boundary_handling='zeros', diff_mode='transposed-forward')
+    function = auto_diff.create_tensorflow_op(use_cuda=True, backend='torch_native')
+    a_tensor = torch.zeros(*a.shape, dtype=torch.float64, device='cuda', requires_grad=True)
+    b_tensor = torch.zeros(*b.shape, dtype=torch.float64, device='cuda', requires_grad=True)
+    assert torch.autograd.gradcheck(function.apply, (a_tensor, b_tensor), atol=1e-4, raise_exception=True)
+    rng = np.random.default_rng(12)
+    A, B = rng.normal(size=(21, 13)), rng.normal(size=(21, 13))
+    G = {n: rng.normal(size=(21, 13)) for n in ('out1', 'out2', 'out3')}
+    at, bt = _t(A).requires_grad_(True), _t(B).requires_grad_(True)
+    outs = function.apply(at, bt)
+    assert len(outs) == 3
+    torch.autograd.backward(outs, [_t(G[f.name]) for f in auto_diff.forward_output_fields])
+    ref_o, ref_d = forward_backward(auto_diff, dict(a=A, b=B), G)
+    for f, o in zip(auto_diff.forward_output_fields, outs):
+        np.testing.assert_allclose(o.detach().cpu().numpy(), ref_o[f.name], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(at.grad.cpu().numpy(), ref_d['diffa'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(bt.grad.cpu().numpy(), ref_d['diffb'], rtol=1e-12, atol=1e-12)
