@@ -419,12 +419,22 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   // tensor maps live here for the duration of cuLaunchKernel (parameters are copied at launch)
   struct alignas(64) { CUtensorMap m[PSAD_MAX_FIELDS]; } TM;
 
+  unsigned grid_y = 1, grid_z = 1;
   if (P.kind == PSAD_KIND_GENERIC) {
-    long long cells = 1;
-    for (int d = 0; d < 3; ++d) cells *= (A.wr_hi[d] - A.wr_lo[d]);
-    long long blocks = cdiv(cells, P.threads);
-    long long cap = (long long)k->sm_count * (P.ctas_per_sm > 0 ? P.ctas_per_sm : 8);
-    grid = (unsigned)(blocks < cap ? blocks : cap);
+    // x over threads (coalesced), y / z over blockIdx.y / blockIdx.z with grid-stride loops in the kernel
+    const long long nx = A.wr_hi[2] - A.wr_lo[2], ny = A.wr_hi[1] - A.wr_lo[1], nz = A.wr_hi[0] - A.wr_lo[0];
+    long long gx = cdiv(nx, P.threads);
+    if (gx > 65535) gx = 65535;
+    grid = (unsigned)gx;
+    // enough blocks to fill the machine a few times over, few enough that every block walks many rows
+    const long long want = (long long)k->sm_count * 32;
+    long long gy = ny < 65535 ? ny : 65535, gz = nz < 65535 ? nz : 65535;
+    if (gx * gy * gz > want) {
+      gz = want / (gx * gy);
+      if (gz < 1) { gz = 1; gy = want / gx; if (gy < 1) gy = 1; }
+    }
+    grid_y = (unsigned)gy;
+    grid_z = (unsigned)gz;
   } else if (P.kind == PSAD_KIND_MARCH) {
     if (nd < 2) return fail(PSAD_ERR_INVALID, "march kernels need 2 or 3 spatial dims");
     if (A.wr_lo[2] != 0 || A.wr_hi[2] != A.shape[2] || A.wr_lo[1] < 0)
@@ -492,7 +502,7 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   if (getenv("PSAD_DEBUG"))
     fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d\n", k->name.c_str(), grid,
             P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy);
-  CUresult r = g_drv.cuLaunchKernel(k->fn, grid, 1, 1, (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
+  CUresult r = g_drv.cuLaunchKernel(k->fn, grid, grid_y, grid_z, (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
   if (r != 0) return cu_fail(r, "cuLaunchKernel");
   g_launches.fetch_add(1);
   return 0;

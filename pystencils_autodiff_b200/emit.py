@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '12'
+EMITTER_VERSION = '14'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
@@ -219,16 +219,17 @@ def emit_generic(ir: StencilKernelIR, threads=256) -> EmittedKernel:
     L += ['',
           'extern "C" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ PsadArgs A)' % (threads, name),
           '{',
-          '  const long long nx = A.wr_hi[2] - A.wr_lo[2], ny = A.wr_hi[1] - A.wr_lo[1], nz = A.wr_hi[0] - A.wr_lo[0];',
-          '  const long long total = nx * ny * nz;']
+          '  // x from the thread index (coalesced), y and z from the block indices with grid-stride loops: no 64-bit',
+          '  // division per cell; pointer arithmetic is the only 64-bit work',
+          '  const int nx = (int)(A.wr_hi[2] - A.wr_lo[2]), ny = (int)(A.wr_hi[1] - A.wr_lo[1]), nz = (int)(A.wr_hi[0] - A.wr_lo[0]);']
     for i, s in enumerate(scalars):
         L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s), i))
-    L += ['  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;',
-          '       i += (long long)gridDim.x * blockDim.x) {',
-          '    const long long x = A.wr_lo[2] + i % nx;',
-          '    const long long t = i / nx;',
-          '    const long long y = A.wr_lo[1] + t % ny;',
-          '    const long long z = A.wr_lo[0] + t / ny;',
+    L += ['  for (int iz = blockIdx.z; iz < nz; iz += gridDim.z)',
+          '  for (int iy = blockIdx.y; iy < ny; iy += gridDim.y)',
+          '  for (int ix = blockIdx.x * blockDim.x + threadIdx.x; ix < nx; ix += gridDim.x * blockDim.x) {',
+          '    const long long x = A.wr_lo[2] + ix;',
+          '    const long long y = A.wr_lo[1] + iy;',
+          '    const long long z = A.wr_lo[0] + iz;',
           '    const long long cz = z - (%d), cy = y - (%d), cx = x - (%d);  // cell the expression is evaluated at' % (lz, ly, lx),
           '    const bool inside = cz >= A.it_lo[0] && cz < A.it_hi[0] && cy >= A.it_lo[1] && cy < A.it_hi[1] &&',
           '                        cx >= A.it_lo[2] && cx < A.it_hi[2];']
@@ -239,15 +240,17 @@ def emit_generic(ir: StencilKernelIR, threads=256) -> EmittedKernel:
     L.append('    if (inside) {')
     local = {}
     n = 0
+    pre = []   # loop-invariant element offsets of every access, hoisted in front of the loops
     for fname in sorted(ir.read_accesses):
         fi = fidx[fname]
         for a in ir.read_accesses[fname]:
             dz, dy, dx = _off3(a.offsets)
             idx = int(a.index[0]) if a.index else 0
             var = 'r_%d' % n
+            pre.append('  const long long off_%d = (%d) * A.stride[%d][0] + (%d) * A.stride[%d][1] + (%d) * A.stride[%d][2] + %d * A.stride[%d][3];'
+                       % (n, dz, fi, dy, fi, dx, fi, idx, fi))
+            addr = '((const T_%d*)A.ptr[%d])[base_%d + off_%d]' % (fi, fi, fi, n)
             n += 1
-            addr = ('((const T_%d*)A.ptr[%d])[(cz + (%d)) * A.stride[%d][0] + (cy + (%d)) * A.stride[%d][1] + '
-                    '(cx + (%d)) * A.stride[%d][2] + %d * A.stride[%d][3]]' % (fi, fi, dz, fi, dy, fi, dx, fi, idx, fi))
             if ir.boundary == 'zeros' and (dz or dy or dx):
                 conds = []
                 for o, c, d in ((dz, 'cz', 0), (dy, 'cy', 1), (dx, 'cx', 2)):
@@ -259,6 +262,13 @@ def emit_generic(ir: StencilKernelIR, threads=256) -> EmittedKernel:
             else:
                 L.append('      const CT %s = (CT)%s;' % (var, addr))
             local[a] = var
+    # base offset of the evaluated cell per read field (one 64-bit multiply-add chain per field, not per access)
+    base_lines = ['    const long long base_%d = cz * A.stride[%d][0] + cy * A.stride[%d][1] + cx * A.stride[%d][2];'
+                  % (fidx[fname], fidx[fname], fidx[fname], fidx[fname]) for fname in sorted(ir.read_accesses)]
+    at = L.index('    if (inside) {')
+    L[at:at] = base_lines
+    first_loop = next(i_ for i_, ln in enumerate(L) if ln.startswith('  for (int iz'))
+    L[first_loop:first_loop] = pre
     for s in ir.scalars:
         local[s] = _c_ident(s.name)
     for lhs, rhs in ir.subexpressions:
