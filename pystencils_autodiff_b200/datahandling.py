@@ -414,11 +414,12 @@ class SlabStencilOp:
     ``local_shape`` is the owned (ghost-free) shape per rank; the global field is ``world_size`` such slabs stacked
     along dim 0."""
 
-    def __init__(self, op, local_shape, rank=0, world_size=1, device=None, backend='nccl', tuning=None):
+    def __init__(self, op, local_shape, rank=0, world_size=1, device=None, backend='nccl', tuning=None, scalars=None):
         import torch
         self.torch = torch
         self.op = op
         self.rank, self.world = rank, world_size
+        scalars = dict(scalars or {})
         self.device = device
         self.fwd = CompiledKernel(op.forward_ast_gpu, tuning)
         self.bwd = CompiledKernel(op.backward_ast_gpu, tuning)
@@ -439,8 +440,13 @@ class SlabStencilOp:
         fwd_ir, bwd_ir = op.forward_ast_gpu, op.backward_ast_gpu
         self.fwd_halo = [f.name for f in fwd_ir.input_fields if max(fwd_ir.halo(f.name)[0]) > 0] if g else []
         self.bwd_halo = [f.name for f in bwd_ir.input_fields if max(bwd_ir.halo(f.name)[0]) > 0] if g else []
-        self.fwd_scalars = {s: 1.0 for s in self.fwd.scalars}
-        self.bwd_scalars = {s: 1.0 for s in self.bwd.scalars}
+        for kern in (self.fwd, self.bwd):
+            missing = [s_ for s_ in kern.scalars if s_ not in scalars]
+            if missing:
+                raise TypeError('%s: missing scalar argument(s) %s (pass scalars={...})' % (kern.function_name, missing))
+        self.scalars = scalars
+        self.fwd_scalars = {s_: scalars[s_] for s_ in self.fwd.scalars}
+        self.bwd_scalars = {s_: scalars[s_] for s_ in self.bwd.scalars}
         self._fn = None
         self._pinned = None
 
@@ -504,7 +510,7 @@ class SlabStencilOp:
             h_out = {n: self._host[n] for n in streamed.output_names}
 
             def step():
-                streamed(h_in, h_out)
+                streamed(h_in, h_out, **self.scalars)
         else:
             grad_names = [f.name for f in op.backward_input_fields if f not in op.forward_input_fields]
             dnames = [f.name for f in op.backward_output_fields]
@@ -581,10 +587,15 @@ class HostStreamedOp:
         ir = kernel.ir   # the chunk's ghost planes are filled from the host array, so one launch covers it
         return slab_ranges(self.shape, k * self.chunk, n_k, self.g, False, False, ir.boundary, ir.ghost_layers, ir.ndim)[0]
 
-    def __call__(self, host_in, host_out):
+    def __call__(self, host_in, host_out, **scalars):
         """``host_in``: name -> pinned CPU tensor for every input field (forward inputs and ``diff<out>`` gradients);
-        ``host_out``: name -> pinned CPU tensor receiving every output (forward outputs and ``diff<in>``)."""
+        ``host_out``: name -> pinned CPU tensor receiving every output (forward outputs and ``diff<in>``);
+        ``scalars``: values of the free scalar symbols of the kernels."""
         torch = self.torch
+        for kern in (self.fwd, self.bwd):
+            missing = [s_ for s_ in kern.scalars if s_ not in scalars]
+            if missing:
+                raise TypeError('%s: missing scalar argument(s) %s' % (kern.function_name, missing))
         g, C, N0 = self.g, self.chunk, self.shape[0]
         cur = torch.cuda.current_stream(self.device)
         start = torch.cuda.Event()
@@ -617,8 +628,11 @@ class HostStreamedOp:
                 if k >= self.stages:
                     self.s_cmp.wait_event(self.ev_out[st])
                 for kern in (self.fwd, self.bwd):
+                    for f in kern.ir.output_fields:
+                        if f in kern.ir.input_fields:       # ``+=`` form: accumulates onto a zero-initialised output
+                            buf[f.name].zero_()
                     views = {f.name: buf[f.name][:n_k + 2 * g] for f in kern.fields}
-                    kern(**views, **{s: 1.0 for s in kern.scalars}, _range=self._ranges(kern, k, n_k))
+                    kern(**views, **{s_: scalars[s_] for s_ in kern.scalars}, _range=self._ranges(kern, k, n_k))
                 self.ev_cmp[st].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_cmp[st])

@@ -373,3 +373,28 @@ def test_tfmad_gradient_check_two_outputs_reference_case():
         np.testing.assert_allclose(o.detach().cpu().numpy(), ref_o[f.name], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(at.grad.cpu().numpy(), ref_d['diffa'], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(bt.grad.cpu().numpy(), ref_d['diffb'], rtol=1e-12, atol=1e-12)
+
+
+def test_host_streamed_op_with_scalar_and_accumulate_form():
+    """HostStreamedOp passes scalar parameters through and zero-initialises ``+=``-form outputs per chunk."""
+    import torch
+    from pystencils_autodiff_b200.datahandling import HostStreamedOp
+    shape = (21, 16, 64)
+    u, out = ps.fields('u, out: float64[%d,%d,%d]' % shape)
+    al = sp.Symbol('alpha')
+    fa = [ps.Assignment(out.center, u[0, 0, 0] + al * (u[1, 0, 0] + u[-1, 0, 0] + u[0, 0, 1] - 3 * u[0, 0, 0]))]
+    op = ps.AutoDiffOp(fa, boundary_handling='zeros', time_constant_fields=[u])
+    st = HostStreamedOp(op, shape, 'cuda:0', chunk_planes=4)
+    rng = np.random.default_rng(21)
+    U, G = rng.normal(size=shape), rng.normal(size=shape)
+    host = {'u': torch.from_numpy(U).pin_memory(), 'diffout': torch.from_numpy(G).pin_memory(),
+            'out': torch.empty(shape, dtype=torch.float64).pin_memory(),
+            'diffu': torch.empty(shape, dtype=torch.float64).pin_memory()}
+    assert sorted(st.input_names) == ['diffout', 'u'] and sorted(st.output_names) == ['diffu', 'out']
+    with pytest.raises(TypeError):
+        st({n: host[n] for n in st.input_names}, {n: host[n] for n in st.output_names})
+    st({n: host[n] for n in st.input_names}, {n: host[n] for n in st.output_names}, alpha=0.3)
+    torch.cuda.synchronize()
+    ref_o, ref_d = forward_backward(op, dict(u=U), dict(out=G), scalars=dict(alpha=0.3))
+    np.testing.assert_allclose(host['out'].numpy(), ref_o['out'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host['diffu'].numpy(), ref_d['diffu'], rtol=1e-12, atol=1e-12)
