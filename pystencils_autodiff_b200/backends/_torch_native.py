@@ -214,6 +214,14 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
     bwd_accessed = {f.name for f in backward_ir.fields_accessed} if backward_ir is not None else set()
     bwd_read = {f.name for f in backward_ir.fields_read} if backward_ir is not None else set()
     grad_fields = [f for f in bwd_inputs if f not in fwd_inputs and f not in fwd_outputs and f not in bwd_outputs]
+    # which forward output each upstream-gradient field belongs to.  The reference binds ``grad_outputs[i]`` to the
+    # i-th such field (:99-100), which is only right when the adjoint reads the gradient of EVERY output; here the
+    # position comes from the forward output the adjoint field was derived from.
+    grad_index = {}
+    for i_, f in enumerate(grad_fields):
+        fwd_f = getattr(f, 'corresponding_forward_field', None)
+        names = [o.name for o in fwd_outputs]
+        grad_index[f.name] = names.index(fwd_f.name) if fwd_f is not None and fwd_f.name in names else i_
     # adjoint of forward input i (None for constant fields)
     prefix_map = {}
     for f in bwd_outputs:
@@ -282,7 +290,8 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
         saved = dict(zip(ctx.saved_names, ctx.saved_tensors))
         shape, device = ctx.like
         gradients = {}
-        for i, f in enumerate(grad_fields):
+        for f in grad_fields:
+            i = grad_index[f.name]
             g = grad_outputs[i] if i < len(grad_outputs) else None
             if g is None:
                 g = torch.zeros(tuple(int(s) for s in f.shape) if f.has_fixed_shape else shape,

@@ -398,3 +398,21 @@ def test_host_streamed_op_with_scalar_and_accumulate_form():
     ref_o, ref_d = forward_backward(op, dict(u=U), dict(out=G), scalars=dict(alpha=0.3))
     np.testing.assert_allclose(host['out'].numpy(), ref_o['out'], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(host['diffu'].numpy(), ref_d['diffu'], rtol=1e-12, atol=1e-12)
+
+
+def test_gradients_are_matched_to_outputs_by_name_not_position():
+    """An output whose value does not depend on any input has no ``diff<out>`` field in the adjoint kernel; the
+    gradients of the remaining outputs must still reach the right fields (the reference binds them by position)."""
+    import torch
+    x, a_out, b_out = ps.fields('x, a_out, b_out: float64[8,16]')
+    ac = ps.AssignmentCollection({a_out.center: sp.Float(2.5) + 0 * x.center, b_out.center: 3 * x[0, 1] + x.center})
+    op = ps.AutoDiffOp(ac, boundary_handling='zeros')
+    assert [f.name for f in op.backward_input_fields] == ['diffb_out']
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    rng = np.random.default_rng(2)
+    X, GA, GB = rng.normal(size=(8, 16)), rng.normal(size=(8, 16)), rng.normal(size=(8, 16))
+    xt = _t(X).requires_grad_(True)
+    oa, ob = fn.apply(xt)
+    torch.autograd.backward((oa, ob), (_t(GA), _t(GB)))
+    _, ref = forward_backward(op, dict(x=X), dict(a_out=GA, b_out=GB))
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), ref['diffx'], rtol=1e-13, atol=1e-13)
