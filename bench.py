@@ -218,29 +218,43 @@ def main_ours(args):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    n0 = runtime.launch_count()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.3)
     # per-kernel durations: CUDA events around the forward and the adjoint launch on every `stride`-th timed step (an
     # event between two 90 us kernels costs a few us of GPU idle time, so not on every step)
     stride = 1 if args.steps < 40 else 8
-    evs = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, args.steps, stride)}
-    barrier()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    t_host0 = time.perf_counter()
-    for i in range(args.steps):
-        step(evs.get(i))
-    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time spent issuing one step (not a GPU time)
-    end.record()
-    barrier()
-    launches = runtime.launch_count() - n0
-    clk = clocks.stop() if rank == 0 else None
-    ms_total = start.elapsed_time(end)
-    t_fwd = sum(e[0].elapsed_time(e[1]) for e in evs.values()) / len(evs)
-    t_bwd = sum(e[1].elapsed_time(e[2]) for e in evs.values()) / len(evs)
+
+    def timed_region():
+        n0 = runtime.launch_count()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+            time.sleep(0.3)
+        evs = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, args.steps, stride)}
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        t_host0 = time.perf_counter()
+        for i in range(args.steps):
+            step(evs.get(i))
+        host_ms_ = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time spent issuing one step
+        end.record()
+        barrier()
+        clk_ = clocks.stop() if rank == 0 else None
+        return (start.elapsed_time(end), sum(e[0].elapsed_time(e[1]) for e in evs.values()) / len(evs),
+                sum(e[1].elapsed_time(e[2]) for e in evs.values()) / len(evs), host_ms_, clk_,
+                runtime.launch_count() - n0, len(evs))
+
+    ms_total, t_fwd, t_bwd, host_ms, clk, launches, n_samples = timed_region()
+    # a run that saw a hardware / thermal slowdown is rejected and measured again, once (sw_power_cap is kept and noted)
+    bad = {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    retry = torch.tensor([1 if (rank == 0 and clk and bad & set(clk.get('reasons', []))) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(retry, op=dist.ReduceOp.MAX)
+    if int(retry.item()):
+        first_reasons = clk.get('reasons') if clk else None
+        time.sleep(2.0)
+        ms_total, t_fwd, t_bwd, host_ms, clk, launches, n_samples = timed_region()
+        if clk is not None:
+            clk['remeasured_after'] = first_reasons
     if world > 1:
         t = torch.tensor([ms_total, t_fwd, t_bwd], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,12 +284,17 @@ def main_ours(args):
             fused_ms = None
 
     # ---- end to end through the public API with HOST buffers (copies inside the timed region) -------------------
-    e2e = slab.end_to_end(args.e2e_steps, barrier)
+    e2e_error = None
+    try:
+        e2e = slab.end_to_end(args.e2e_steps, barrier)
+    except Exception as exc:   # e.g. not enough pinnable host memory: keep the line, say what happened
+        e2e_error = '%s: %s' % (type(exc).__name__, exc)
+        e2e = {'ms_per_step': float('inf'), 'h2d': 0, 'd2h': 0}
     if world > 1:
         t = torch.tensor([e2e['ms_per_step']], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e['ms_per_step'] = float(t.item())
-    e2e_value = cells * world / (e2e['ms_per_step'] * 1e-3) / 1e6
+    e2e_value = cells * world / (e2e['ms_per_step'] * 1e-3) / 1e6 if e2e_error is None else None
 
     if rank != 0:
         if world > 1:
@@ -301,12 +320,12 @@ def main_ours(args):
                    'kernel_variants': slab.variants(), 'halo_exchange': slab.exchange_kind if world > 1 else 'none (1 GPU)'},
         'roofline': {'bound': 'hbm', 'kernel': op.forward_ast_gpu.function_name, 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                     'forward_ms': t_fwd, 'adjoint_ms': t_bwd, 'kernel_timing_samples': len(evs),
+                     'forward_ms': t_fwd, 'adjoint_ms': t_bwd, 'kernel_timing_samples': n_samples,
                      'pair_achieved': pair, 'pair_frac': pair / peak,
                      'pair_frac_of_8000_nominal': pair / 8000.0},
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
-                'ms_per_step': e2e['ms_per_step'], 'steps': args.e2e_steps,
+                'ms_per_step': e2e['ms_per_step'] if e2e_error is None else None, 'steps': args.e2e_steps, 'error': e2e_error,
                 'api': ('HostStreamedOp(AutoDiffOp)(host_in, host_out): pinned host fields streamed through the GPU in plane '
                         'chunks, H2D / forward+adjoint kernels / D2H overlapped on three streams') if world == 1 else
                        'SlabStencilOp: H2D of the slab, halo exchange + kernels, D2H of outputs and input gradients'},
@@ -318,7 +337,11 @@ def main_ours(args):
             'note': 'one launch over the union of forward and adjoint assignments (outside the headline timed region)'},
     }
     if not args.no_cpu_baseline:
-        base, _ = cpu_reference_run(wl, steps=5, warmup=2)
+        try:
+            base, _ = cpu_reference_run(wl, steps=5, warmup=2)
+        except Exception as exc:
+            base = {'value': None, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': 'failed',
+                    'error': '%s: %s' % (type(exc).__name__, exc)}
         line['cpu_baseline'] = base
     print(json.dumps(line), flush=True)
     if world > 1:
