@@ -179,6 +179,7 @@ class SlabDataHandling:
         self.device = torch.device(device)
         self.exchanger = HaloExchanger(self.dec, backend, group)
         self.gpu_arrays = OrderedDict()
+        self.cpu_arrays = OrderedDict()
         self.fields = OrderedDict()
         self.call_queue = []
         self._range_cache = {}
@@ -219,6 +220,26 @@ class SlabDataHandling:
 
     def owned(self, name):
         return self.gpu_arrays[name][self.dec.owned]
+
+    # -- host mirrors (reference: GraphDataHandling.to_cpu / to_gpu record a DataTransfer, graph_datahandling.py:255-282)
+    def to_cpu(self, name):
+        self.call_queue.append(('DataTransfer', name, 'DEVICE_TO_HOST'))
+        self.cpu_arrays[name] = self.gpu_arrays[name].detach().to('cpu', copy=True)
+        return self.cpu_arrays[name]
+
+    def to_gpu(self, name):
+        self.call_queue.append(('DataTransfer', name, 'HOST_TO_DEVICE'))
+        if name not in self.cpu_arrays:
+            raise KeyError('no host copy of %r: call to_cpu(%r) first or fill cpu_arrays[%r]' % (name, name, name))
+        self.gpu_arrays[name].copy_(self.cpu_arrays[name])
+
+    def all_to_cpu(self):
+        for n in self.gpu_arrays:
+            self.to_cpu(n)
+
+    def all_to_gpu(self):
+        for n in self.cpu_arrays:
+            self.to_gpu(n)
 
     def swap(self, name1, name2, gpu=True):
         self.call_queue.append(('Swap', name1, name2))

@@ -31,7 +31,10 @@ def main():
             k, v = kv.split('=')
             tun[k] = bool(int(v)) if k in ("carry", "shuffle", "plane_sums", "arrival", "linopt") else int(v)
     tuning = MarchTuning(**tun) if tun else None
-    op = make_config(name, shape=shape, **({'fast_math': True} if os.environ.get('PSAD_FAST_MATH') else {}))
+    extra = {'fast_math': True} if os.environ.get('PSAD_FAST_MATH') else {}
+    if os.environ.get('PSAD_BH'):
+        extra['boundary_handling'] = None if os.environ['PSAD_BH'] == 'none' else os.environ['PSAD_BH']
+    op = make_config(name, shape=shape, **extra)
     dev = torch.device('cuda:0')
     cells = 1
     for s in shape:

@@ -101,3 +101,26 @@ def test_decomposition_ranges():
     assert interior['iter_lo'] == [2, 1, 1] and interior['write_lo'] == [1, 0, 0]   # global plane 0 is border: zero
     with pytest.raises(ValueError):
         SlabDecomposition((4, 8, 8), rank=0, world_size=4, ghost_layers=1)
+
+
+def test_data_handling_registry_and_call_queue_single_rank():
+    """SlabDataHandling's registry vocabulary on one rank (CPU tensors): arrays, fill, swap, host mirrors, queue."""
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    dh = SlabDataHandling((6, 8), 0, 1, 1, device='cpu', backend='torch')
+    u, v = dh.add_arrays('u, v', dtype=np.float64)
+    assert u.name == 'u' and dh.fields['v'].shape == (8, 8) and dh.gpu_arrays['u'].shape == (8, 8)   # 6 + 2 ghost rows
+    w = dh.add_array_like('w', 'u')
+    assert w.dtype.numpy_dtype == np.float64
+    dh.fill('u', 3.0)
+    assert float(dh.owned('u').sum()) == 3.0 * 6 * 8 and float(dh.gpu_arrays['u'].sum()) == 3.0 * 6 * 8
+    dh.swap('u', 'v')
+    assert float(dh.owned('v').sum()) == 3.0 * 48 and float(dh.owned('u').sum()) == 0
+    host = dh.to_cpu('v')
+    host += 1
+    dh.to_gpu('v')
+    assert float(dh.owned('v')[0, 0]) == 4.0
+    dh.synchronization_function(['u'])()          # single rank: records the marker, moves nothing
+    assert [c[0] for c in dh.call_queue] == ['Swap', 'DataTransfer', 'DataTransfer', 'Communication']
+    assert np.array_equal(dh.gather_array('v'), dh.owned('v').numpy())
+    with pytest.raises(ValueError):
+        dh.add_array('u')
