@@ -283,6 +283,42 @@ def main_ours(args):
         except NotImplementedError:
             fused_ms = None
 
+    # ---- two unrolled steps of the forward stencil as ONE launch (emit_chain.py) beside two
+    # single-step launches; reported next to the headline, not part of it
+    steps_info = None
+    if world == 1:
+        try:
+            fk = slab.fwd
+            if fk.fused_steps_reason() is None:
+                fin, fout = op.forward_ast_gpu.input_fields[0].name, op.forward_ast_gpu.output_fields[0].name
+                g = slab.dh.gpu_arrays
+                src, dst, tmp = g[fin], g[fout], g[[n for n in g if n not in (fin, fout)][-1]]
+
+                def _time(fn, n=5):
+                    for _ in range(3):
+                        fn()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    a.record()
+                    for _ in range(n):
+                        fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    return a.elapsed_time(b) / n
+
+                def _two():
+                    fk(**{fin: src, fout: tmp})
+                    fk(**{fin: tmp, fout: dst})
+                t_two = _time(_two)
+                t_x2 = _time(lambda: fk(**{fin: src, fout: dst}, _variant='march_x2'))
+                steps_info = {'two_launches_ms': t_two, 'one_fused_launch_ms': t_x2, 'speedup': t_two / t_x2,
+                              'gcell_steps_per_s': 2 * src.numel() / (t_x2 * 1e-3) / 1e9,
+                              'used_by_default': bool(src.element_size() == 4),
+                              'note': 'out = S(S(u)) with one read and one write of the field; run_steps() / '
+                                      'create_unrolled_torch_op() fuse pairs only where this is a win (4-byte fields)'}
+        except Exception as exc:   # a diagnostic beside the headline must never take the line down
+            steps_info = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     # ---- end to end through the public API with HOST buffers (copies inside the timed region) -------------------
     e2e_error = None
     try:
@@ -331,6 +367,7 @@ def main_ours(args):
                        'SlabStencilOp: H2D of the slab, halo exchange + kernels, D2H of outputs and input gradients'},
         'gpu_launches': launches,
         'host_issue_ms_per_step': host_ms,
+        'fused_steps': steps_info,
         'fused_forward_adjoint': None if fused_ms is None else {
             'ms_per_step': fused_ms, 'value': cells / (fused_ms * 1e-3) / 1e6, 'unit': UNIT,
             'bytes_per_cell': op.fused_ast_gpu.bytes_per_cell(),

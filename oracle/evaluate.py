@@ -9,7 +9,7 @@ neither vendored in /root/reference nor installable here, and the reference's te
 vectors for this path.  This file restates pystencils' kernel semantics as used by the
 reference and is pinned by (i) the reference's symbolic known answers (tests/test_autodiff.py:21,46;
 README.rst:66-68,85-86) via ``tests/test_symbolic.py``, (ii) the reference's own ``_autodiff.py`` executed on
-top of our front end (``tests/golden/make_reference_symbolic.py``), and (iii) gradient checks in the style of
+top of our front end (``tests/golden/make_reference_golden.py``), and (iii) gradient checks in the style of
 tests/test_tfmad.py:186-231.
 
 Semantics restated:

@@ -413,6 +413,13 @@ class AutoDiffOp:
     def create_torch_op(self, *args, **kwargs):
         return self.create_tensorflow_op(*args, backend='torch_native', **kwargs)
 
+    def create_unrolled_torch_op(self, steps, op_name=None, tuning=None):
+        """``Function`` applying this one-field stencil ``steps`` times (pairs of steps fused into one launch); see
+        ``backends/_torch_native.create_unrolled_function``.  Not part of the reference API: its users chain
+        ``op.apply`` calls, which still works here."""
+        from .backends._torch_native import create_unrolled_function
+        return create_unrolled_function(self, steps, op_name=op_name, tuning=tuning)
+
     def create_tensorflow_op(self, inputfield_tensor_dict={}, forward_loop=None, backward_loop=None,
                              use_cuda=True, backend='tensorflow'):
         """Same dispatch signature as the reference (:611-616); only ``backend='torch_native', use_cuda=True`` exists."""

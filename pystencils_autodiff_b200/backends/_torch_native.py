@@ -22,10 +22,12 @@ from collections import OrderedDict
 import numpy as np
 
 from ..emit import emit_generic, emit_march, march_ineligible_reason
+from ..emit_chain import chain_ineligible_reason, emit_march_chain
 from ..ir import StencilKernelIR, split_index_components
 from .. import runtime
 
-__all__ = ['create_autograd_function', 'compile_kernel', 'CompiledKernel', 'numpy_dtype_to_torch']
+__all__ = ['create_autograd_function', 'create_unrolled_function', 'compile_kernel', 'CompiledKernel',
+           'numpy_dtype_to_torch']
 
 
 def numpy_dtype_to_torch(dtype):
@@ -69,7 +71,47 @@ class CompiledKernel:
         return sorted(v for v in self._emitted if v != 'march_nomask')
 
     def emitted(self, variant):
+        if variant == 'march_x2' and variant not in self._emitted:
+            reason = self.fused_steps_reason()
+            if reason:
+                raise ValueError('%s: two fused steps per launch are not available: %s' % (self.function_name, reason))
+            self._emitted[variant] = emit_march_chain(self.ir, self.tuning_x2)
         return self._emitted[variant]
+
+    tuning_x2 = None   # MarchTuning of the fused-step kernel (None = emit_chain defaults)
+
+    def fused_steps_reason(self):
+        """None when ``out = S(S(u))`` can run as one launch (emit_chain.py), else why not."""
+        if self._components:
+            return 'index dimensions'
+        return self._march_reason or chain_ineligible_reason(self.ir)
+
+    def run_steps(self, src, steps, out=None, fuse=None, **scalars):
+        """``S^steps(src)``: the stencil applied ``steps`` times, ping-ponging between ``out`` and one scratch tensor;
+        ``src`` is not modified.  ``fuse``: run pairs of steps as one launch (one read and one write of the field per
+        pair instead of two).  Default: where that is a measured win — 4-byte fields (7-point fp32 at 1024^3: 1.39x);
+        for fp64 the rows recomputed by the fused kernel cost as much FP64 issue as the saved traffic (27-point fp64 at
+        768^3: 1.00x), so those stay on single-step launches unless asked."""
+        import torch
+        if len(self.ir.input_fields) != 1 or len(self.ir.output_fields) != 1:
+            raise ValueError('%s: run_steps needs a kernel with one input and one output field' % self.function_name)
+        if steps < 1:
+            raise ValueError('steps must be >= 1')
+        fin, fout = self.ir.input_fields[0].name, self.ir.output_fields[0].name
+        can_pair = self.fused_steps_reason() is None and self._select_variant([src, src]) == 'march'
+        if fuse and not can_pair:
+            raise ValueError('%s: steps cannot be fused: %s' % (self.function_name, self.fused_steps_reason() or
+                                                                'tensor layout needs the generic kernel'))
+        pair = can_pair and (src.element_size() == 4 if fuse is None else bool(fuse))
+        launches = [2] * (steps // 2) + [1] * (steps % 2) if pair else [1] * steps
+        out = torch.empty_like(src) if out is None else out
+        scratch = torch.empty_like(src) if len(launches) > 1 else None
+        cur = src
+        for i, n in enumerate(launches):
+            dst = out if (len(launches) - 1 - i) % 2 == 0 else scratch
+            self(**{fin: cur, fout: dst}, _variant='march_x2' if n == 2 else None, **scalars)
+            cur = dst
+        return out
 
     def get_parameters(self):
         return self.ir.get_parameters()
@@ -142,6 +184,14 @@ class CompiledKernel:
                 raise TypeError('%s: missing scalar argument %r' % (self.function_name, s))
             scal.append(float(kwargs[s]))
         variant = _variant or self._select_variant(tensors)
+        if variant == 'march_x2':
+            self.emitted(variant)
+            if _range is not None:
+                raise ValueError('%s: fused steps run on whole arrays only' % self.function_name)
+            if self._select_variant(tensors) != 'march':
+                raise ValueError('%s: fused steps need dense, 16-byte aligned rows' % self.function_name)
+            if tensors[0].data_ptr() == tensors[1].data_ptr():
+                raise ValueError('%s: input and output must be different tensors' % self.function_name)
         if variant == 'march':
             # the mask-free instance is valid whenever every written cell is also an evaluated cell
             if _range is not None:
@@ -172,7 +222,7 @@ class CompiledKernel:
             stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
             self.native(variant, dev.index if dev.index is not None else torch.cuda.current_device()).launch(
                 field_args, scal, stream, _range)
-        self.last_variant = 'march' if variant == 'march_nomask' else variant
+        self.last_variant = 'march' if variant.startswith('march') else variant
         self.last_instance = variant
         return None
 
@@ -336,4 +386,52 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
     cls.num_regs = None
     cls.call = classmethod(call)
     cls.code = fwd_kernel.code + ('\n' + bwd_kernel.code if bwd_kernel is not None else '')
+    return cls
+
+
+def create_unrolled_function(autodiff_obj, steps, op_name=None, tuning=None):
+    """``torch.autograd.Function`` for ``steps`` unrolled applications of a one-field stencil, ``u_T = S^T(u_0)``.
+
+    The reference unrolls time steps by chaining ``op.apply`` calls (tests/test_tfmad.py style) — T forward and T
+    adjoint launches, each a full read + write of the field, with T - 1 intermediate tensors kept alive by autograd.
+    Here pairs of steps run as one launch (``CompiledKernel.run_steps``, emit_chain.py) and nothing is saved: the
+    adjoint of a stencil whose adjoint kernel reads only the upstream gradient is ``(S^T)`` applied ``steps`` times to
+    that gradient.  Stencils whose adjoint needs forward values are rejected (chain ``op.apply`` for those)."""
+    import torch
+    fwd_ir = autodiff_obj.forward_ast_gpu
+    bwd_ir = autodiff_obj.backward_ast_gpu
+    if len(fwd_ir.input_fields) != 1 or len(fwd_ir.output_fields) != 1:
+        raise ValueError('unrolled steps need a stencil with one input and one output field')
+    if len(bwd_ir.input_fields) != 1 or len(bwd_ir.output_fields) != 1:
+        raise ValueError('unrolled steps need an adjoint that reads only the upstream gradient (a linear stencil)')
+    if any(f.index_dimensions for f in fwd_ir.all_fields):
+        raise ValueError('unrolled steps need scalar fields')
+    steps = int(steps)
+    fwd_kernel = CompiledKernel(fwd_ir, tuning)
+    bwd_kernel = CompiledKernel(bwd_ir, tuning)
+    dtype = numpy_dtype_to_torch(fwd_ir.input_fields[0].dtype.numpy_dtype)
+
+    def _prep(t):
+        t = t.cuda()
+        if t.dtype != dtype:
+            raise TypeError('expected a %s tensor, got %s' % (dtype, t.dtype))
+        return t if t.is_contiguous() else t.contiguous()
+
+    class_kwargs = dict()      # scalar parameters, like the single-step Function's class_kwargs
+
+    def forward(ctx, u):
+        ctx.scalars = dict(class_kwargs)
+        return (fwd_kernel.run_steps(_prep(u), steps, **{k: v for k, v in ctx.scalars.items() if k in fwd_kernel.scalars}),)
+
+    def backward(ctx, grad):
+        return bwd_kernel.run_steps(_prep(grad), steps, **{k: v for k, v in ctx.scalars.items() if k in bwd_kernel.scalars})
+
+    cls = type(op_name or '%s_x%d' % (autodiff_obj.op_name, steps), (torch.autograd.Function,),
+               {'forward': staticmethod(forward), 'backward': staticmethod(backward)})
+    cls.steps = steps
+    cls.class_kwargs = class_kwargs
+    cls.forward_kernel = fwd_kernel
+    cls.backward_kernel = bwd_kernel
+    cls.forward_ast = fwd_ir
+    cls.backward_ast = bwd_ir
     return cls

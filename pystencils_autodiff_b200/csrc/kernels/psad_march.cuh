@@ -15,7 +15,7 @@
 // and the queue of outstanding HBM requests never drains.
 //
 // The including translation unit defines, before this header:
-//   namespace cfg { NDIM, TX, TY, THREADS (consumer threads), MIN_CTAS, STAGES, HZL, HZH, JREL, NP, NTMA,
+//   namespace cfg { NDIM, TX, TY, TXS, XORG, THREADS (consumer threads), MIN_CTAS, STAGES, HZL, HZH, JREL, NP, NTMA,
 //                   STAGE_BYTES, TX_BYTES, F_OFF[], F_ORGX[], F_ORGY[] }
 //   struct PsadCarry;  psad_item_begin(...);  psad_step(...);  PSAD_KERNEL_NAME
 #ifndef PSAD_MARCH_CUH
@@ -25,37 +25,7 @@ struct PsadTmaps {
   PsadTensorMap m[cfg::NTMA];
 };
 
-struct PsadItem {
-  int x0, y0;            // tile origin (y0 only meaningful for NDIM == 3)
-  int p_first, p_last;   // first / last plane (3-D) or row-tile (2-D) to stage
-  int z0;                // first output plane of the item
-};
-
-PSAD_DEV PsadItem psad_decode_item(const PsadArgs& A, long long item) {
-  PsadItem it;
-  const int tx = (int)(item % A.tiles_x);
-  const long long rest = item / A.tiles_x;
-  it.x0 = tx * cfg::TX;
-  if (cfg::NDIM == 3) {
-    const int ty = (int)(rest % A.tiles_y);
-    const int c = (int)(rest / A.tiles_y);
-    it.y0 = ty * cfg::TY;
-    it.z0 = (int)A.wr_lo[0] + c * A.chunk;
-    int z1 = it.z0 + A.chunk;
-    if (z1 > (int)A.wr_hi[0]) z1 = (int)A.wr_hi[0];
-    it.p_first = it.z0 - cfg::HZL;
-    it.p_last = z1 - 1 + cfg::HZH;
-  } else {
-    const int c = (int)rest;
-    it.y0 = 0;
-    it.z0 = c * A.chunk;
-    int k1 = it.z0 + A.chunk;
-    if (k1 > A.tiles_y) k1 = A.tiles_y;
-    it.p_first = it.z0;
-    it.p_last = k1 - 1;
-  }
-  return it;
-}
+#include "psad_item.cuh"
 
 extern "C" __global__ void __launch_bounds__(cfg::THREADS + 32, cfg::MIN_CTAS)
 PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ PsadTmaps TM) {

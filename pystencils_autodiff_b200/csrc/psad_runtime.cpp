@@ -363,27 +363,27 @@ extern "C" int psad_kernel_attributes(psad_kernel_t k, int* num_regs, int* stati
 // launch
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
-extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields,
-                                  const double* scalars, int n_scalars, const psad_range_t* range, void* stream) {
-  if (!k || !fields) return fail(PSAD_ERR_INVALID, "psad_kernel_launch: null argument");
-  const psad_plan_t& P = k->plan;
-  if (n_fields != P.n_fields) return fail(PSAD_ERR_INVALID, "%s: expected %d fields, got %d", k->name.c_str(), P.n_fields, n_fields);
-  if (n_scalars != P.n_scalars) return fail(PSAD_ERR_INVALID, "%s: expected %d scalars, got %d", k->name.c_str(), P.n_scalars, n_scalars);
+// Everything a launch needs that does not touch the device: the parameter block (shapes, strides, iteration / write
+// ranges), the work decomposition of march kernels and the grid.  *empty = 1 when there is nothing to write.
+static int build_args(const psad_plan_t& P, const char* kname, int sm_count, int occupancy, const psad_field_arg_t* fields,
+                      int n_fields, const double* scalars, int n_scalars, const psad_range_t* range, PsadArgs& A,
+                      unsigned grid[3], int* empty) {
+  if (n_fields != P.n_fields) return fail(PSAD_ERR_INVALID, "%s: expected %d fields, got %d", kname, P.n_fields, n_fields);
+  if (n_scalars != P.n_scalars) return fail(PSAD_ERR_INVALID, "%s: expected %d scalars, got %d", kname, P.n_scalars, n_scalars);
   if (n_scalars > 0 && !scalars) return fail(PSAD_ERR_INVALID, "null scalars");
-  if (int rc = ensure_context()) return rc;
-
   const int nd = P.ndim;
-  PsadArgs A;
+  *empty = 0;
+  grid[0] = grid[1] = grid[2] = 1;
   memset(&A, 0, sizeof(A));
   // normalise to (z, y, x): leading dims of extent 1
   for (int d = 0; d < 3; ++d) A.shape[d] = 1;
   for (int d = 0; d < nd; ++d) A.shape[3 - nd + d] = fields[0].shape[d];
   for (int f = 0; f < n_fields; ++f) {
-    if (!fields[f].ptr) return fail(PSAD_ERR_INVALID, "%s: field %d has a null pointer", k->name.c_str(), f);
+    if (!fields[f].ptr) return fail(PSAD_ERR_INVALID, "%s: field %d has a null pointer", kname, f);
     for (int d = 0; d < nd; ++d) {
       if (fields[f].shape[d] != fields[0].shape[d])
         return fail(PSAD_ERR_INVALID, "%s: all fields of a kernel must share one spatial shape (field %d, dim %d: %lld vs %lld)",
-                    k->name.c_str(), f, d, (long long)fields[f].shape[d], (long long)fields[0].shape[d]);
+                    kname, f, d, (long long)fields[f].shape[d], (long long)fields[0].shape[d]);
       A.stride[f][3 - nd + d] = fields[f].stride[d];
     }
     A.stride[f][3] = fields[f].stride[3];
@@ -397,7 +397,7 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
       A.it_lo[e] = range->iter_lo[d]; A.it_hi[e] = range->iter_hi[d];
       A.wr_lo[e] = range->write_lo[d]; A.wr_hi[e] = range->write_hi[d];
       if (A.wr_lo[e] < 0 || A.wr_hi[e] > A.shape[e])
-        return fail(PSAD_ERR_INVALID, "%s: write range [%lld, %lld) outside the array extent %lld in dim %d", k->name.c_str(),
+        return fail(PSAD_ERR_INVALID, "%s: write range [%lld, %lld) outside the array extent %lld in dim %d", kname,
                     A.wr_lo[e], A.wr_hi[e], A.shape[e], d);
     }
   } else if (P.boundary == 0 && P.ghost_layers > 0) {
@@ -409,41 +409,35 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   }
   for (int d = 0; d < 3; ++d) {
     if (A.it_hi[d] < A.it_lo[d]) A.it_hi[d] = A.it_lo[d];
-    if (A.wr_hi[d] <= A.wr_lo[d]) return 0;  // nothing to write
+    if (A.wr_hi[d] <= A.wr_lo[d]) { *empty = 1; return 0; }  // nothing to write
   }
 
-  unsigned grid = 1;
-  void* params[2];
-  int n_params = 1;
-  params[0] = &A;
-  // tensor maps live here for the duration of cuLaunchKernel (parameters are copied at launch)
-  struct alignas(64) { CUtensorMap m[PSAD_MAX_FIELDS]; } TM;
-
-  unsigned grid_y = 1, grid_z = 1;
   if (P.kind == PSAD_KIND_GENERIC) {
     // x over threads (coalesced), y / z over blockIdx.y / blockIdx.z with grid-stride loops in the kernel
     const long long nx = A.wr_hi[2] - A.wr_lo[2], ny = A.wr_hi[1] - A.wr_lo[1], nz = A.wr_hi[0] - A.wr_lo[0];
     long long gx = cdiv(nx, P.threads);
     if (gx > 65535) gx = 65535;
-    grid = (unsigned)gx;
+    grid[0] = (unsigned)gx;
     // enough blocks to fill the machine a few times over, few enough that every block walks many rows
-    const long long want = (long long)k->sm_count * 32;
+    const long long want = (long long)sm_count * 32;
     long long gy = ny < 65535 ? ny : 65535, gz = nz < 65535 ? nz : 65535;
     if (gx * gy * gz > want) {
       gz = want / (gx * gy);
       if (gz < 1) { gz = 1; gy = want / gx; if (gy < 1) gy = 1; }
     }
-    grid_y = (unsigned)gy;
-    grid_z = (unsigned)gz;
+    grid[1] = (unsigned)gy;
+    grid[2] = (unsigned)gz;
   } else if (P.kind == PSAD_KIND_MARCH) {
     if (nd < 2) return fail(PSAD_ERR_INVALID, "march kernels need 2 or 3 spatial dims");
     if (A.wr_lo[2] != 0 || A.wr_hi[2] != A.shape[2] || A.wr_lo[1] < 0)
       return fail(PSAD_ERR_INVALID, "march kernels write full rows: the x range must be the whole axis");
+    if (P.reserved[1] > 1 && range)
+      return fail(PSAD_ERR_INVALID, "%s: kernels fusing %d steps run on whole arrays only (no launch range)", kname, P.reserved[1]);
     A.tiles_x = (int)cdiv(A.shape[2], P.tile_x);
     A.tiles_y = (int)cdiv(A.shape[1], P.tile_y);
     long long span = (nd == 3) ? (A.wr_hi[0] - A.wr_lo[0]) : A.tiles_y;
     const long long tiles = (long long)A.tiles_x * (nd == 3 ? A.tiles_y : 1);
-    const long long cap = (long long)k->sm_count * k->occupancy;
+    const long long cap = (long long)sm_count * occupancy;
     long long n_chunks;
     if (P.chunk > 0) {
       n_chunks = cdiv(span, P.chunk);
@@ -468,18 +462,56 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
     A.chunk = (int)chunk;
     A.n_chunks = (int)n_chunks;
     A.n_items = tiles * n_chunks;
-    grid = (unsigned)(A.n_items < cap ? A.n_items : cap);
+    grid[0] = (unsigned)(A.n_items < cap ? A.n_items : cap);
+    for (int f = 0; f < n_fields; ++f) {
+      const psad_field_plan_t& fp = P.field[f];
+      if (A.stride[f][2] != 1) return fail(PSAD_ERR_INVALID, "%s: field %d is not contiguous along x", kname, f);
+      if (((uintptr_t)A.ptr[f]) % 16 != 0) return fail(PSAD_ERR_INVALID, "%s: field %d pointer is not 16-byte aligned", kname, f);
+      if ((A.stride[f][1] * fp.elem_size) % 16 != 0 || (nd == 3 && (A.stride[f][0] * fp.elem_size) % 16 != 0))
+        return fail(PSAD_ERR_INVALID, "%s: field %d row/plane pitch is not a multiple of 16 bytes", kname, f);
+      if (fp.tma && fp.elem_size != 4 && fp.elem_size != 8) return fail(PSAD_ERR_INVALID, "TMA fields must be float32/float64");
+    }
+  } else {
+    return fail(PSAD_ERR_INVALID, "unknown kernel kind %d", P.kind);
+  }
+  return 0;
+}
+
+extern "C" int psad_plan_launch(const psad_plan_t* plan, int sm_count, int ctas_per_sm, const psad_field_arg_t* fields,
+                                int n_fields, const double* scalars, int n_scalars, const psad_range_t* range,
+                                void* args_out, size_t args_bytes, unsigned grid_out[3]) {
+  if (!plan || !fields || !args_out || !grid_out) return fail(PSAD_ERR_INVALID, "psad_plan_launch: null argument");
+  if (args_bytes != sizeof(PsadArgs)) return fail(PSAD_ERR_INVALID, "psad_plan_launch: parameter block is %zu bytes", sizeof(PsadArgs));
+  int empty = 0;
+  PsadArgs A;
+  if (int rc = build_args(*plan, "plan", sm_count, ctas_per_sm, fields, n_fields, scalars, n_scalars, range, A, grid_out, &empty)) return rc;
+  if (empty) grid_out[0] = 0;
+  memcpy(args_out, &A, sizeof(A));
+  return 0;
+}
+
+extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields,
+                                  const double* scalars, int n_scalars, const psad_range_t* range, void* stream) {
+  if (!k || !fields) return fail(PSAD_ERR_INVALID, "psad_kernel_launch: null argument");
+  const psad_plan_t& P = k->plan;
+  PsadArgs A;
+  unsigned grid[3];
+  int empty = 0;
+  if (int rc = build_args(P, k->name.c_str(), k->sm_count, k->occupancy, fields, n_fields, scalars, n_scalars, range, A, grid, &empty)) return rc;
+  if (empty) return 0;
+  if (int rc = ensure_context()) return rc;
+  const int nd = P.ndim;
+  void* params[2];
+  params[0] = &A;
+  // tensor maps live here for the duration of cuLaunchKernel (parameters are copied at launch)
+  struct alignas(64) { CUtensorMap m[PSAD_MAX_FIELDS]; } TM;
+  if (P.kind == PSAD_KIND_MARCH) {
     int n_tma = 0;
     // L2 promotion of TMA requests: 0 none, 1 64B, 2 128B, 3 256B (PSAD_L2PROMO overrides for experiments)
     static const int l2promo = getenv("PSAD_L2PROMO") ? atoi(getenv("PSAD_L2PROMO")) : 3;
     for (int f = 0; f < n_fields; ++f) {
       const psad_field_plan_t& fp = P.field[f];
-      if (A.stride[f][2] != 1) return fail(PSAD_ERR_INVALID, "%s: field %d is not contiguous along x", k->name.c_str(), f);
-      if (((uintptr_t)A.ptr[f]) % 16 != 0) return fail(PSAD_ERR_INVALID, "%s: field %d pointer is not 16-byte aligned", k->name.c_str(), f);
-      if ((A.stride[f][1] * fp.elem_size) % 16 != 0 || (nd == 3 && (A.stride[f][0] * fp.elem_size) % 16 != 0))
-        return fail(PSAD_ERR_INVALID, "%s: field %d row/plane pitch is not a multiple of 16 bytes", k->name.c_str(), f);
       if (!fp.tma) continue;
-      if (fp.elem_size != 4 && fp.elem_size != 8) return fail(PSAD_ERR_INVALID, "TMA fields must be float32/float64");
       unsigned long long gdim[3] = {(unsigned long long)A.shape[2], (unsigned long long)A.shape[1], (unsigned long long)A.shape[0]};
       unsigned long long gstr[2] = {(unsigned long long)A.stride[f][1] * fp.elem_size, (unsigned long long)A.stride[f][0] * fp.elem_size};
       unsigned box[3] = {(unsigned)fp.box[0], (unsigned)fp.box[1], (unsigned)(nd == 3 ? fp.box[2] : 1)};
@@ -493,16 +525,12 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
       ++n_tma;
     }
     params[1] = &TM;
-    n_params = 2;
-  } else {
-    return fail(PSAD_ERR_INVALID, "unknown kernel kind %d", P.kind);
   }
-  (void)n_params;
-  if (grid == 0) return 0;
+  if (grid[0] == 0) return 0;
   if (getenv("PSAD_DEBUG"))
-    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d\n", k->name.c_str(), grid,
+    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d\n", k->name.c_str(), grid[0],
             P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy);
-  CUresult r = g_drv.cuLaunchKernel(k->fn, grid, grid_y, grid_z, (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
+  CUresult r = g_drv.cuLaunchKernel(k->fn, grid[0], grid[1], grid[2], (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
   if (r != 0) return cu_fail(r, "cuLaunchKernel");
   g_launches.fetch_add(1);
   return 0;

@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '14'
+EMITTER_VERSION = '16'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
@@ -567,7 +567,7 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     if t.store_mode != 1:
         L.append('#define PSAD_STORE_MODE %d' % t.store_mode)
     L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT, 'namespace cfg {',
-          'constexpr int NDIM = %d, TX = %d, TY = %d;' % (nd, TX, TY),
+          'constexpr int NDIM = %d, TX = %d, TY = %d, TXS = %d, XORG = 0;' % (nd, TX, TY, TX),
           'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d, JREL = %d, NP = %d;'
           % (THREADS, min_ctas, STAGES, HZL, HZH, jrel, NP),
           'constexpr int NTMA = %d, STAGE_BYTES = %d, TX_BYTES = %d;' % (len(tma_fields), STAGE_BYTES,

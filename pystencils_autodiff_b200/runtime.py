@@ -103,6 +103,9 @@ def lib():
         L.psad_kernel_launch.argtypes = [ctypes.c_void_p, ctypes.POINTER(FieldArg), ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(Range),
                                          ctypes.c_void_p]
+        L.psad_plan_launch.argtypes = [ctypes.POINTER(Plan), ctypes.c_int, ctypes.c_int, ctypes.POINTER(FieldArg),
+                                       ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(Range),
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint)]
         L.psad_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
         L.psad_nccl_unique_id.argtypes = [ctypes.c_void_p]
         L.psad_nccl_comm_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
@@ -129,6 +132,7 @@ def make_plan(p):
               'ctas_per_sm', 'boundary', 'ghost_layers'):
         setattr(plan, k, int(p[k]))
     plan.reserved[0] = int(p.get('warmup', 0))
+    plan.reserved[1] = int(p.get('fused_steps', 1))
     for i, f in enumerate(p['fields']):
         fp = plan.field[i]
         for k in ('elem_size', 'is_input', 'is_output', 'index_size', 'tma'):

@@ -1,0 +1,96 @@
+"""Two fused steps per launch (emit_chain.py) against two single-step launches: parity on a small grid (oracle applied
+twice), agreement at full size, and timing over a few tile geometries.
+    python scripts/steps_bench.py c4            # 27-point fp64, 768^3
+    python scripts/steps_bench.py c3 "2,30,4,0;2,22,4,0"   # candidates as ry,ty,sx,lookahead"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from pystencils_autodiff_b200.configs import make_config, CONFIG_SHAPES
+from pystencils_autodiff_b200.backends._torch_native import CompiledKernel, numpy_dtype_to_torch
+from pystencils_autodiff_b200.emit import MarchTuning
+
+DEFAULT_CANDIDATES = {'c3': '0,0,0,0;2,22,4,0;4,28,4,0;3,33,4,0', 'c4': '0,0,0,0;4,28,2,0;3,21,2,0;2,22,2,0'}
+
+
+def timed(fn, iters=8, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else 'c4'
+    cands = (sys.argv[2] if len(sys.argv) > 2 else DEFAULT_CANDIDATES[name]).split(';')
+    dev = torch.device('cuda:0')
+    # ---- parity on a small grid, both boundary modes, forward and adjoint kernels
+    from oracle.evaluate import evaluate
+    small = (19, 45, 252)
+    for bh in ('zeros', None):
+        op = make_config(name, shape=small, boundary_handling=bh)
+        for ir, assigns in ((op.forward_ast_gpu, op.forward_assignments), (op.backward_ast_gpu, op.backward_assignments)):
+            k = CompiledKernel(ir)
+            fin, fout = ir.input_fields[0], ir.output_fields[0]
+            u = np.random.default_rng(1).standard_normal(small).astype(fin.dtype.numpy_dtype)
+            r1 = evaluate(assigns, {fin.name: u}, boundary_handling=bh)[fout.name].astype(u.dtype)
+            r2 = evaluate(assigns, {fin.name: r1}, boundary_handling=bh)[fout.name]
+            ut = torch.from_numpy(u).to(dev)
+            out = torch.full_like(ut, float('nan'))
+            k(**{fin.name: ut, fout.name: out}, _variant='march_x2')
+            err = float(np.abs(out.cpu().numpy() - r2).max())
+            out5 = k.run_steps(ut, 5)
+            r = u
+            for _ in range(5):
+                r = evaluate(assigns, {fin.name: r}, boundary_handling=bh)[fout.name].astype(u.dtype)
+            err5 = float(np.abs(out5.cpu().numpy() - r).max())
+            print('parity %-28s bh=%-5s x2 err %.3g   5 steps err %.3g' % (ir.function_name, bh, err, err5), flush=True)
+    # ---- full size
+    shape = CONFIG_SHAPES[name]['shape']
+    op = make_config(name, shape=shape)
+    ir = op.forward_ast_gpu
+    fin, fout = ir.input_fields[0], ir.output_fields[0]
+    dt = numpy_dtype_to_torch(fin.dtype.numpy_dtype)
+    cells = int(np.prod(shape))
+    u = torch.randn(shape, dtype=dt, device=dev)
+    a = torch.empty_like(u)
+    b = torch.empty_like(u)
+    k1 = CompiledKernel(ir)
+
+    def two_single():
+        k1(**{fin.name: u, fout.name: a})
+        k1(**{fin.name: a, fout.name: b})
+    t1 = timed(two_single)
+    bpc = ir.bytes_per_cell()
+    print('%s %s: two single-step launches %.3f ms (%.0f GB/s algorithmic per launch)' % (name, shape, t1, 2 * cells * bpc / t1 / 1e6),
+          flush=True)
+    ref = b.clone()
+    for cand in cands:
+        ry, ty, sx, la = [int(v) for v in cand.split(',')]
+        k2 = CompiledKernel(ir)
+        k2.tuning_x2 = MarchTuning(ry=ry, ty=ty, sx=sx, lookahead=la)
+        try:
+            ek = k2.emitted('march_x2')
+        except ValueError as e:
+            print('  %-12s not emitted: %s' % (cand, e))
+            continue
+        out = torch.empty_like(u)
+        t2 = timed(lambda: k2(**{fin.name: u, fout.name: out}, _variant='march_x2'))
+        diff = float((out - ref).abs().max())
+        attrs = k2.native('march_x2').attributes()
+        print('  x2 %-10s tile %dx%d ry=%d sx=%d stages=%d regs=%d occ=%d: %.3f ms  = %.2fx two launches, %.1f Gcell-steps/s, '
+              '%.0f GB/s of field traffic, max|diff| vs two launches %.3g'
+              % (cand, ek.geometry['TY'], ek.geometry['TX'], ek.geometry['RY'], ek.geometry['SX'], ek.geometry['STAGES'],
+                 attrs['num_regs'], attrs['max_ctas_per_sm'], t2, t1 / t2, 2 * cells / t2 / 1e6, cells * bpc / t2 / 1e6, diff), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,101 @@
+"""Replay of an emitted march kernel on the CPU.  TEST INFRASTRUCTURE.
+
+The emitted CUDA source is compiled by g++ against ``tests/cpu_shim/`` (host stand-ins for ``psad_common.cuh`` and
+``psad_march.cuh``): the stencil's own ``psad_item_begin`` / ``psad_step`` code — register window, slot rotation,
+shuffled halos, masks, vector stores — runs unchanged, one OS thread per lane, over work items decoded by the
+product's ``psad_item.cuh`` from a parameter block built by the product's ``psad_plan_launch``.  What is *not*
+exercised: TMA, mbarriers and the producer/consumer overlap (GPU tests cover those)."""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+from pystencils_autodiff_b200 import runtime
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, 'cpu_shim')
+_BUILD = os.path.join(_HERE, '..', 'oracle', '_build')
+
+
+class _EmuField(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('stride', ctypes.c_longlong * 3), ('esize', ctypes.c_int),
+                ('boxw', ctypes.c_int), ('boxh', ctypes.c_int)]
+
+
+def _compile(emitted):
+    os.makedirs(_BUILD, exist_ok=True)
+    h = hashlib.md5(emitted.source.encode())
+    for fn in sorted(os.listdir(_SHIM)) + ['psad_item.cuh', 'psad_args.h']:
+        path = os.path.join(_SHIM, fn) if os.path.exists(os.path.join(_SHIM, fn)) else os.path.join(runtime.KERNEL_DIR, fn)
+        with open(path, 'rb') as fh:
+            h.update(fh.read())
+    base = os.path.join(_BUILD, 'emu_%s_%s' % (emitted.name[:32], h.hexdigest()[:12]))
+    if not os.path.exists(base + '.so'):
+        with open(base + '.cpp', 'w') as fh:
+            fh.write(emitted.source)
+        # -ffp-contract=off mirrors -fmad=false; fma()/fmaf() map to the hardware FMA like on the GPU
+        subprocess.check_call(['g++', '-std=c++20', '-O1', '-ffp-contract=off', '-mfma', '-fPIC', '-shared', '-pthread', '-w',
+                               '-I', _SHIM, '-I', runtime.KERNEL_DIR, '-o', base + '.so.tmp', base + '.cpp'])
+        os.replace(base + '.so.tmp', base + '.so')
+    return ctypes.CDLL(base + '.so')
+
+
+def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=None):
+    """``arrays``: numpy arrays in the plan's field order (outputs first; written in place)."""
+    L = runtime.lib()
+    plan = runtime.make_plan(emitted.plan)
+    n = len(arrays)
+    fa = (runtime.FieldArg * n)()
+    for i, a in enumerate(arrays):
+        assert a.flags['C_CONTIGUOUS'] and a.ctypes.data % 16 == 0
+        fa[i].ptr = a.ctypes.data
+        for d in range(3):
+            fa[i].shape[d] = a.shape[d] if d < a.ndim else 1
+            fa[i].stride[d] = a.strides[d] // a.itemsize if d < a.ndim else 0
+        fa[i].stride[3] = 0
+    sc = (ctypes.c_double * max(1, len(scalars)))(*scalars)
+    args = ctypes.create_string_buffer(4096)
+    grid = (ctypes.c_uint * 3)()
+    rng = None
+    if launch_range is not None:
+        rng = runtime.Range()
+        for d in range(arrays[0].ndim):
+            rng.iter_lo[d], rng.iter_hi[d] = launch_range['iter'][d]
+            rng.write_lo[d], rng.write_hi[d] = launch_range['write'][d]
+    size = _args_size()
+    runtime.check(L.psad_plan_launch(ctypes.byref(plan), sm_count, ctas_per_sm, fa, n, sc, len(scalars),
+                                     ctypes.byref(rng) if rng is not None else None, args, size, grid), 'psad_plan_launch')
+    if grid[0] == 0:
+        return 0
+    tma = [(i, f) for i, f in enumerate(emitted.plan['fields']) if f['tma']]
+    tf = (_EmuField * len(tma))()
+    nd = arrays[0].ndim
+    for k, (i, f) in enumerate(tma):
+        a = arrays[i]
+        st = [0] * (3 - nd) + [s // a.itemsize for s in a.strides]
+        tf[k].ptr = a.ctypes.data
+        tf[k].stride[:] = st
+        tf[k].esize = a.itemsize
+        tf[k].boxw, tf[k].boxh = f['box'][0], f['box'][1]
+    so = _compile(emitted)
+    so.psad_emulate.argtypes = [ctypes.c_void_p, ctypes.POINTER(_EmuField), ctypes.c_int, ctypes.c_int]
+    rc = so.psad_emulate(args, tf, len(tma), int(grid[0]))
+    assert rc == 0, 'psad_emulate failed'
+    return int(grid[0])
+
+
+def _args_size():
+    # sizeof(PsadArgs), from the header's layout: 12 ptrs + 12*4 strides + 5*3 int64 + 16 doubles + int64 + 4 ints
+    return 12 * 8 + 12 * 4 * 8 + 5 * 3 * 8 + 16 * 8 + 8 + 4 * 4
+
+
+def aligned_empty(shape, dtype, fill=None):
+    n = int(np.prod(shape))
+    raw = np.empty(n * np.dtype(dtype).itemsize + 64, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 64
+    a = raw[off:off + n * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+    if fill is not None:
+        a[...] = fill
+    return a

@@ -1,0 +1,98 @@
+"""Emitted march kernels replayed on the CPU (tests/march_emulator.py): the per-step bodies — register-window slot
+rotation, shuffled halos, plane sums, masks, vector stores, and the two-stage fused-step bodies of emit_chain.py —
+run unchanged under g++ and are compared with the oracle.  TMA / mbarrier behaviour is covered by the GPU tests."""
+import numpy as np
+import pytest
+
+import march_emulator as emu
+from oracle.evaluate import evaluate
+from pystencils_autodiff_b200 import configs
+from pystencils_autodiff_b200.emit import MarchTuning, emit_march
+from pystencils_autodiff_b200.emit_chain import chain_ineligible_reason, emit_march_chain
+
+
+def _fields(ek, ir, shape, seed=0):
+    rng = np.random.default_rng(seed)
+    arrays, named = [], {}
+    for f in ek.fields:
+        a = emu.aligned_empty(shape, f.dtype.numpy_dtype)
+        a[...] = rng.standard_normal(shape) if f in ir.input_fields else np.nan
+        arrays.append(a)
+        named[f.name] = a
+    return arrays, named
+
+
+@pytest.mark.parametrize('make, shape, bh, which, masked, tol', [
+    (configs.heat3d_op, (5, 34, 132), 'zeros', 'forward', True, 3e-7),
+    (configs.heat3d_op, (5, 34, 132), None, 'backward', True, 3e-7),
+    (configs.heat3d_op, (5, 64, 256), 'zeros', 'forward', False, 3e-7),
+    (configs.stencil27_op, (6, 30, 136), 'zeros', 'forward', True, 1e-14),
+    (configs.stencil27_op, (6, 30, 136), None, 'backward', True, 1e-14),
+    (configs.diffusion2d_op, (40, 260), 'zeros', 'forward', True, 3e-7),
+])
+def test_single_step_kernels_replay(make, shape, bh, which, masked, tol):
+    op = make(shape=shape, boundary_handling=bh)
+    ir = op.forward_ast_gpu if which == 'forward' else op.backward_ast_gpu
+    assigns = op.forward_assignments if which == 'forward' else op.backward_assignments
+    ek = emit_march(ir, None, masked=masked)
+    arrays, named = _fields(ek, ir, shape)
+    assert emu.run(ek, arrays) > 0
+    ref = evaluate(assigns, {f.name: named[f.name].copy() for f in ir.input_fields}, boundary_handling=bh)
+    for f in ir.output_fields:
+        assert not np.isnan(named[f.name]).any()
+        np.testing.assert_allclose(named[f.name], ref[f.name], rtol=0, atol=tol)
+
+
+def _twice(assigns, fin, fout, u, bh):
+    r1 = evaluate(assigns, {fin: u}, boundary_handling=bh)[fout].astype(u.dtype)
+    return evaluate(assigns, {fin: r1}, boundary_handling=bh)[fout]
+
+
+@pytest.mark.parametrize('make, shape, bh, which, tuning, tol', [
+    (configs.heat3d_op, (5, 31, 124), 'zeros', 'forward', None, 4e-7),
+    (configs.heat3d_op, (7, 23, 252), None, 'backward', MarchTuning(ry=2, ty=10, sx=4), 4e-7),
+    (configs.heat3d_op, (5, 20, 132), 'zeros', 'forward', MarchTuning(ry=3, ty=9, sx=4), 4e-7),
+    (configs.stencil27_op, (5, 23, 68), 'zeros', 'forward', None, 1e-14),
+    (configs.stencil27_op, (6, 17, 124), None, 'backward', MarchTuning(ry=2, ty=14, sx=4), 1e-14),
+])
+def test_fused_two_steps_replay(make, shape, bh, which, tuning, tol):
+    """out = S(S(u)) from one launch == the oracle applied twice, including the zero border of the intermediate
+    field (boundary None) and the zero reads outside the array ('zeros')."""
+    op = make(shape=shape, boundary_handling=bh)
+    ir = op.forward_ast_gpu if which == 'forward' else op.backward_ast_gpu
+    assigns = op.forward_assignments if which == 'forward' else op.backward_assignments
+    assert chain_ineligible_reason(ir) is None
+    ek = emit_march_chain(ir, tuning)
+    assert ek.plan['fused_steps'] == 2 and ek.plan['tile_x'] < ek.geometry['TX']
+    arrays, named = _fields(ek, ir, shape, seed=3)
+    assert emu.run(ek, arrays) > 0
+    fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
+    ref = _twice(assigns, fin, fout, named[fin].copy(), bh)
+    assert not np.isnan(named[fout]).any()
+    np.testing.assert_allclose(named[fout], ref, rtol=0, atol=tol)
+
+
+def test_fused_steps_asymmetric_stencil_replay():
+    """One-sided offsets in every direction (halo (1,0) / (0,1) / (1,0)): tile overlap and the accumulator rotation
+    must follow the actual halo, not a symmetric radius."""
+    import sympy as sp
+    import pystencils_autodiff_b200 as ps
+    shape = (6, 19, 124)
+    u, out = ps.fields('u, out: float64[%d,%d,%d]' % shape)
+    rhs = 0.5 * u[0, 0, 0] + 0.25 * u[-1, 0, 0] - 0.125 * u[0, 1, 0] + 0.0625 * u[0, 0, -1] + sp.Rational(1, 3) * u[0, 1, -1]
+    op = ps.AutoDiffOp(ps.AssignmentCollection([ps.Assignment(out.center, rhs)]), op_name='skew', boundary_handling='zeros')
+    for ir, assigns in ((op.forward_ast_gpu, op.forward_assignments), (op.backward_ast_gpu, op.backward_assignments)):
+        assert chain_ineligible_reason(ir) is None
+        ek = emit_march_chain(ir)
+        arrays, named = _fields(ek, ir, shape, seed=5)
+        emu.run(ek, arrays)
+        fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
+        ref = _twice(assigns, fin, fout, named[fin].copy(), 'zeros')
+        np.testing.assert_allclose(named[fout], ref, rtol=0, atol=1e-14)
+
+
+def test_fused_steps_eligibility():
+    assert 'one input' in chain_ineligible_reason(configs.tv_gradient_op(shape=(2, 16, 32)).forward_ast_gpu)
+    assert '3-D' in chain_ineligible_reason(configs.diffusion2d_op(shape=(16, 32)).forward_ast_gpu)
+    with pytest.raises(ValueError):
+        emit_march_chain(configs.diffusion2d_op(shape=(16, 32)).forward_ast_gpu)

@@ -1,9 +1,7 @@
 """The CUDA expression printer, checked on the CPU: printed expressions are compiled with g++ (tiny prelude for the
 device helpers) and compared with sympy's numeric evaluation."""
-import os
 import random
 import subprocess
-import sys
 
 import numpy as np
 import pytest
