@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '16'
+EMITTER_VERSION = '17'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
@@ -181,6 +181,31 @@ def _c_ident(name):
     return out
 
 
+def _is_nonlinear(ir):
+    """Does any right-hand side combine field values other than by a weighted sum?  (Those kernels have expensive
+    per-position terms — norms, roots, fluxes — that neighbouring cells share.)"""
+    if ir.subexpressions:
+        return True
+    for _, rhs in ir.main:
+        for node in sp.preorder_traversal(rhs):
+            if isinstance(node, (sp.Pow, sp.Function)) and node.has(Field.Access):
+                return True
+            if isinstance(node, sp.Mul) and sum(1 for a in node.args if a.has(Field.Access)) > 1:
+                return True
+    return False
+
+
+def _even_power_canonical(expr):
+    """``(b - a)**2 -> (a - b)**2``: one sign convention under even powers, so that the same squared difference reached
+    from two neighbouring cells is the same expression (bitwise the same value)."""
+    def fix(pw):
+        base, e = pw.args
+        if e.is_Integer and e % 2 == 0 and base.could_extract_minus_sign():
+            return sp.Pow(-base, e)
+        return pw
+    return expr.replace(lambda z: z.is_Pow, fix)
+
+
 def _off3(offsets):
     return (0,) * (3 - len(offsets)) + tuple(int(o) for o in offsets)
 
@@ -316,6 +341,8 @@ class MarchTuning:
     linopt: bool = True      # shared partial sums across the cells of a thread for linear plane sums (linopt.py)
     arrival: Optional[bool] = None  # evaluate EVERY per-plane group of the sum when its plane arrives and carry only
     #                                 scalars (no raw values); default: when the stencil has more than 9 accesses
+    cross_cse: Optional[bool] = None   # common subexpressions across ALL cells of a thread (default: non-linear
+    #                                    stencils, whose neighbouring cells share fluxes / norms / reciprocal roots)
     store_mode: int = 1    # global store cache policy: 0 default, 1 streaming (.cs, default), 2 write-through
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes; scalar LDS halos only win for narrow fp64 strips)
@@ -393,9 +420,12 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     D = HZL + HZH
     # measured on B200 (scripts/sweep.py, profiles/): fp32 3-D 32x128 tiles / 2 rows per thread, fp32 2-D 16x128 / 1 row,
     # fp64 21x128 tiles / 3 rows, x-halos by warp shuffle (27-pt: 6.44 TB/s)
+    cross_cse = _is_nonlinear(ir) if t.cross_cse is None else bool(t.cross_cse)
     if max_esize == 4:
         RY = t.ry or (2 if nd == 3 else 1)
-        TY = t.ty or (32 if nd == 3 else 16)
+        # cross-cell CSE keeps the shared temporaries of all the thread's cells live: 15+1 warps (128 registers) instead
+        # of 16+1 (96) — TV-gradient adjoint 0.758 -> 0.722 ms, and 1.00 ms when it has to spill
+        TY = t.ty or ((30 if cross_cse else 32) if nd == 3 else 16)
     else:
         # 7 consumer warps + the producer warp = 8 warps: ptxas budgets registers for the CTA size rounded up to 4
         # warps, so 8+1 warps would be capped at 168 registers and spill (the 27-point window needs ~240)
@@ -739,6 +769,30 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
             L.append('    const unsigned zm = (z >= R.zlo && z < R.zhi) ? R.ymask_it : 0u;')
         elif masked:
             L.append('    const unsigned zm = R.ymask_it;')
+        shared = None
+        if cross_cse:
+            # One CSE over the inlined right-hand sides of every cell of the thread, in absolute element symbols: what
+            # two neighbouring cells have in common (a gradient norm, its reciprocal root, a flux) is evaluated once.
+            defs = {}
+            for lhs, rhs in ir.subexpressions:
+                defs[lhs] = rhs.xreplace(defs)
+            all_local, exprs, keys = {}, [], []
+            for r in range(RY):
+                for c in range(SX):
+                    subs, local = cell_map(r, c)
+                    # element symbols are absolute (one name per staged value); plane-sum symbols are per cell
+                    percell = {k: sp.Symbol('%s_%d_%d' % (k.name, r, c)) for k in local if k.name.startswith('psadQ_')}
+                    subs = dict(subs)
+                    subs.update(percell)
+                    all_local.update({percell.get(k, k): v for k, v in local.items()})
+                    for lhs, rhs in main_exprs:
+                        exprs.append(_even_power_canonical(rhs.xreplace(defs).xreplace(subs)))
+                        keys.append((fidx[lhs.field.name], r, c))
+            repl, reduced = sp.cse(exprs, symbols=sp.numbered_symbols('cs'), order='canonical')
+            for sym, e in repl:
+                L.append('    const CT %s = %s;' % (sym.name, pr.print_with(e, all_local)))
+                all_local[sym] = sym.name
+            shared = {k: pr.print_with(e, all_local) for k, e in zip(keys, reduced)}
         for r in range(RY):
             L.append('    if ((R.ymask_wr >> %d) & 1u) {' % r)
             if masked:
@@ -746,6 +800,15 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
             for lhs, _ in ir.main:
                 L.append('      %s o%d[%d];' % (_CT[lhs.field.dtype.numpy_dtype], fidx[lhs.field.name], SX))
             for c in range(SX):
+                if shared is not None:
+                    for lhs, _ in main_exprs:
+                        To = _CT[lhs.field.dtype.numpy_dtype]
+                        fi = fidx[lhs.field.name]
+                        if masked:
+                            L.append('      o%d[%d] = ((m >> %d) & 1u) ? (%s)(%s) : (%s)0;' % (fi, c, c, To, shared[(fi, r, c)], To))
+                        else:
+                            L.append('      o%d[%d] = (%s)(%s);' % (fi, c, To, shared[(fi, r, c)]))
+                    continue
                 subs, local = cell_map(r, c)
                 L.append('      {')
                 for lhs, rhs in ir.subexpressions:

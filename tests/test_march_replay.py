@@ -96,3 +96,65 @@ def test_fused_steps_eligibility():
     assert '3-D' in chain_ineligible_reason(configs.diffusion2d_op(shape=(16, 32)).forward_ast_gpu)
     with pytest.raises(ValueError):
         emit_march_chain(configs.diffusion2d_op(shape=(16, 32)).forward_ast_gpu)
+
+
+@pytest.mark.parametrize('which', ['forward', 'backward'])
+def test_tv_gradient_cross_cell_cse_replay(which):
+    """Non-linear stencil with subexpressions: by default one CSE runs over all cells of a thread (shared gradient
+    norms / reciprocal roots); must agree with the per-cell evaluation and with the oracle."""
+    shape = (2, 33, 132)
+    op = configs.tv_gradient_op(shape=shape)
+    ir = op.forward_ast_gpu if which == 'forward' else op.backward_ast_gpu
+    assigns = op.forward_assignments if which == 'forward' else op.backward_assignments
+    results = []
+    for cc in (None, False):
+        ek = emit_march(ir, MarchTuning(cross_cse=cc), masked=True)
+        assert ('const CT cs0' in ek.source) == (cc is None)
+        rng = np.random.default_rng(0)
+        arrays, named = [], {}
+        for f in ek.fields:
+            a = emu.aligned_empty(shape, f.dtype.numpy_dtype)
+            a[...] = rng.random(shape) if f in ir.input_fields else np.nan
+            arrays.append(a)
+            named[f.name] = a
+        emu.run(ek, arrays)
+        results.append({f.name: named[f.name].copy() for f in ir.output_fields})
+    ref = evaluate(assigns, {f.name: named[f.name].copy() for f in ir.input_fields}, boundary_handling='zeros')
+    for f in ir.output_fields:
+        scale = max(1.0, np.abs(ref[f.name]).max())
+        for res in results:
+            assert np.abs(res[f.name] - ref[f.name]).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3, 5, 6])
+def test_random_stencils_replay(seed):
+    """The random stencils of the GPU fuzz test (asymmetric halos, several fields and outputs, non-linear terms, both
+    boundary modes, 2-D / 3-D, fp32 / fp64), march variant, on the CPU."""
+    import pystencils_autodiff_b200 as ps
+    from stencil_fuzz import random_stencil
+    from pystencils_autodiff_b200.emit import march_ineligible_reason
+    asg, bh, shape, dtype = random_stencil(seed)
+    if shape[-1] * np.dtype(dtype).itemsize % 16:
+        pytest.skip('rows not 16-byte aligned: generic kernel only')
+    op = ps.AutoDiffOp(asg, boundary_handling=bh, op_name='fuzz%d' % seed)
+    rng = np.random.default_rng(seed)
+    tol = 2e-5 if dtype == 'float32' else 1e-11
+    for collection, ir in ((op.forward_assignments, op.forward_ast_gpu), (op.backward_assignments, op.backward_ast_gpu)):
+        if march_ineligible_reason(ir):
+            continue
+        try:
+            ek = emit_march(ir, None, masked=True)
+        except ValueError:
+            continue
+        arrays, named = [], {}
+        for f in ek.fields:
+            a = emu.aligned_empty(shape, f.dtype.numpy_dtype)
+            a[...] = rng.uniform(-1, 1, size=shape) if f in ir.input_fields else np.nan
+            arrays.append(a)
+            named[f.name] = a
+        emu.run(ek, arrays)
+        ref = evaluate(collection, {f.name: named[f.name].copy() for f in ir.input_fields}, bh)
+        for f in ir.output_fields:
+            scale = max(1.0, np.abs(ref[f.name]).max())
+            assert np.isfinite(named[f.name]).all(), (seed, f.name)
+            assert np.abs(named[f.name] - ref[f.name]).max() <= tol * scale, (seed, f.name)
