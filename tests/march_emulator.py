@@ -61,9 +61,9 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
     rng = None
     if launch_range is not None:
         rng = runtime.Range()
-        for d in range(arrays[0].ndim):
-            rng.iter_lo[d], rng.iter_hi[d] = launch_range['iter'][d]
-            rng.write_lo[d], rng.write_hi[d] = launch_range['write'][d]
+        for d in range(arrays[0].ndim):      # the product's range dicts (datahandling.slab_ranges)
+            rng.iter_lo[d], rng.iter_hi[d] = launch_range['iter_lo'][d], launch_range['iter_hi'][d]
+            rng.write_lo[d], rng.write_hi[d] = launch_range['write_lo'][d], launch_range['write_hi'][d]
     size = _args_size()
     runtime.check(L.psad_plan_launch(ctypes.byref(plan), sm_count, ctas_per_sm, fa, n, sc, len(scalars),
                                      ctypes.byref(rng) if rng is not None else None, args, size, grid), 'psad_plan_launch')

@@ -85,3 +85,50 @@ def test_product_does_not_import_the_oracle():
                 with open(os.path.join(dirpath, f)) as fh:
                     text = fh.read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+
+
+def test_plan_launch_work_decomposition():
+    """psad_plan_launch (the device-free half of psad_kernel_launch): parameter block and persistent-grid work list of
+    march kernels — tiles cover the array, chunks cover the written planes, grid = min(items, SMs x resident CTAs)."""
+    import ctypes
+    import struct
+    import numpy as np
+    from pystencils_autodiff_b200 import configs
+    from pystencils_autodiff_b200.emit import emit_march
+    from pystencils_autodiff_b200.emit_chain import emit_march_chain
+    L = runtime.lib()
+    shape = (300, 70, 1000)
+    op = configs.heat3d_op(shape=shape)
+    for ek, halo in ((emit_march(op.forward_ast_gpu), 1), (emit_march_chain(op.forward_ast_gpu), 2)):
+        plan = runtime.make_plan(ek.plan)
+        fa = (runtime.FieldArg * 2)()
+        buf = np.zeros(64, dtype=np.uint8)
+        base = buf.ctypes.data + (-buf.ctypes.data) % 16
+        for i in range(2):
+            fa[i].ptr = base                       # never dereferenced: planning only
+            fa[i].shape[:] = shape
+            fa[i].stride[:] = [shape[1] * shape[2], shape[2], 1, 0]
+        args = ctypes.create_string_buffer(752)
+        grid = (ctypes.c_uint * 3)()
+        for sms, ctas in ((148, 1), (4, 2)):
+            rc = L.psad_plan_launch(ctypes.byref(plan), sms, ctas, fa, 2, None, 0, None, args, 752, grid)
+            assert rc == 0, L.psad_last_error()
+            n_items, = struct.unpack_from('q', args.raw, 728)
+            tiles_x, tiles_y, n_chunks, chunk = struct.unpack_from('4i', args.raw, 736)
+            assert tiles_x == -(-shape[2] // ek.plan['tile_x']) and tiles_y == -(-shape[1] // ek.plan['tile_y'])
+            assert n_items == tiles_x * tiles_y * n_chunks
+            assert chunk * n_chunks >= shape[0] > chunk * (n_chunks - 1)
+            assert grid[0] == min(n_items, sms * ctas) and grid[1] == grid[2] == 1
+            # the busiest CTA's steps stay within 15 % of a perfectly balanced split (chunks amortise warm-up planes)
+            steps = -(-n_items // (sms * ctas)) * (chunk + 2 * halo)
+            assert steps <= 1.15 * (tiles_x * tiles_y * shape[0] / (sms * ctas)) + chunk + 2 * halo
+        # wrong field count, wrong block size and a launch range on a fused-step kernel are rejected with a message
+        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 1, None, 0, None, args, 752, grid) != 0
+        assert b'expected 2 fields' in L.psad_last_error()
+        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, None, args, 100, grid) != 0
+        if ek.plan.get('fused_steps', 1) > 1:
+            rng = runtime.Range()
+            for d in range(3):
+                rng.iter_hi[d] = rng.write_hi[d] = shape[d]
+            assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, 752, grid) != 0
+            assert b'whole arrays only' in L.psad_last_error()

@@ -158,3 +158,38 @@ def test_random_stencils_replay(seed):
             scale = max(1.0, np.abs(ref[f.name]).max())
             assert np.isfinite(named[f.name]).all(), (seed, f.name)
             assert np.abs(named[f.name] - ref[f.name]).max() <= tol * scale, (seed, f.name)
+
+
+@pytest.mark.parametrize('bh, world', [('zeros', 2), (None, 3)])
+def test_slab_launch_ranges_replay(bh, world):
+    """The slab decomposition on the CPU: every rank's interior / boundary-plane launches (datahandling.slab_ranges)
+    over its slab with ghost planes reproduce the unsharded launch bit for bit."""
+    from pystencils_autodiff_b200.datahandling import slab_ranges
+    shape = (6 if world == 2 else 9, 10, 132)
+    op = configs.heat3d_op(shape=shape, boundary_handling=bh)
+    ir = op.forward_ast_gpu
+    g = 1
+    rng = np.random.default_rng(11)
+    u = emu.aligned_empty(shape, np.float32)
+    u[...] = rng.standard_normal(shape)
+    whole = emu.aligned_empty(shape, np.float32, np.nan)
+    masked_kernel = emit_march(ir, None, masked=True)
+    plain_kernel = emit_march(ir, None, masked=False)
+    emu.run(plain_kernel if bh == 'zeros' else masked_kernel, [whole, u])
+    ref = evaluate(op.forward_assignments, {'u': u.copy()}, boundary_handling=bh)['out']
+    np.testing.assert_allclose(whole, ref, rtol=0, atol=3e-7)
+    n = shape[0] // world
+    for rank in range(world):
+        start = rank * n
+        local_u = emu.aligned_empty((n + 2 * g,) + shape[1:], np.float32, 0.0)
+        lo, hi = max(0, start - g), min(shape[0], start + n + g)
+        local_u[lo - (start - g):hi - (start - g)] = u[lo:hi]        # owned planes + received ghost planes
+        local_out = emu.aligned_empty(local_u.shape, np.float32, np.nan)
+        parts = slab_ranges(shape, start, n, g, rank > 0, rank < world - 1, 'zeros' if bh == 'zeros' else 'none',
+                            ir.ghost_layers, 3)
+        for part in parts:
+            if part is None:
+                continue
+            same = part['iter_lo'] == part['write_lo'] and part['iter_hi'] == part['write_hi']
+            emu.run(plain_kernel if same else masked_kernel, [local_out, local_u], launch_range=part)
+        assert np.array_equal(local_out[g:g + n], whole[start:start + n]), rank
