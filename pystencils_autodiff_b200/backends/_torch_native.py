@@ -105,6 +105,8 @@ class CompiledKernel:
         pair = can_pair and (src.element_size() == 4 if fuse is None else bool(fuse))
         launches = [2] * (steps // 2) + [1] * (steps % 2) if pair else [1] * steps
         out = torch.empty_like(src) if out is None else out
+        if out.data_ptr() == src.data_ptr():
+            raise ValueError('%s: run_steps cannot work in place (out is src)' % self.function_name)
         scratch = torch.empty_like(src) if len(launches) > 1 else None
         cur = src
         for i, n in enumerate(launches):

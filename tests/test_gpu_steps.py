@@ -3,7 +3,6 @@ AutoDiffOp.create_unrolled_torch_op) against the oracle applied step by step."""
 import numpy as np
 import pytest
 
-import pystencils_autodiff_b200 as ps
 from oracle import evaluate
 from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
 from pystencils_autodiff_b200.configs import heat3d_op, stencil27_op, tv_gradient_op
