@@ -75,6 +75,13 @@ template <typename T> PSAD_DEV void psad_lds_vec(const T* p, T* e) {
   typename PsadVec<T>::type v = *reinterpret_cast<const typename PsadVec<T>::type*>(p);
   PsadVec<T>::unpack(v, e);
 }
+// registers -> shared, one aligned 16-byte vector (STS.128)
+template <typename T> PSAD_DEV void psad_sts_vec(T* p, const T* e) {
+  *reinterpret_cast<typename PsadVec<T>::type*>(p) = PsadVec<T>::pack(e);
+}
+// Barrier over the consumer warps only (named barrier 1; the producer warp never joins it).  Orders the shared-memory
+// writes of the participating threads before the reads that follow it.
+PSAD_DEV void psad_consumer_barrier(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 // registers -> global, one aligned 16-byte streaming store (STG.128, evict-first: outputs are not re-read)
 #ifndef PSAD_STORE_MODE
 #define PSAD_STORE_MODE 1   // 0: default caching, 1: streaming / evict-first (.cs), 2: write-through (.wt)

@@ -1,10 +1,12 @@
 // psad_item.cuh — decoding of march work items (shared by the device template psad_march.cuh and by the host replay
-// of the per-step bodies in tests/cpu_shim/).  Needs namespace cfg { NDIM, TX, TY, TXS, XORG, HZL, HZH } and PsadArgs.
+// of the per-step bodies in tests/cpu_shim/).  Needs namespace cfg { NDIM, TX, TY, TXS, XORG, TYS, YORG, HZL, HZH } and
+// PsadArgs.
 //
 // Items are numbered x-tile fastest, then y-tile, then z-chunk, so CTAs that run concurrently (static round robin
 // over consecutive items) work on neighbouring tiles and share their halo columns / rows in L2.  Tiles are TX cells
 // wide and start every TXS cells at XORG + k * TXS: single-step kernels have TXS = TX, XORG = 0; kernels that fuse
-// several steps recompute the columns they cannot complete, so their tiles overlap (TXS < TX, XORG < 0).
+// several steps recompute the columns they cannot complete, so their tiles overlap (TXS < TX, XORG < 0; likewise TYS,
+// YORG along y for the kernels that exchange intermediate rows between warps instead of recomputing them).
 #ifndef PSAD_ITEM_CUH
 #define PSAD_ITEM_CUH
 
@@ -22,7 +24,7 @@ PSAD_DEV PsadItem psad_decode_item(const PsadArgs& A, long long item) {
   if (cfg::NDIM == 3) {
     const int ty = (int)(rest % A.tiles_y);
     const int c = (int)(rest / A.tiles_y);
-    it.y0 = ty * cfg::TY;
+    it.y0 = ty * cfg::TYS + cfg::YORG;
     it.z0 = (int)A.wr_lo[0] + c * A.chunk;
     int z1 = it.z0 + A.chunk;
     if (z1 > (int)A.wr_hi[0]) z1 = (int)A.wr_hi[0];

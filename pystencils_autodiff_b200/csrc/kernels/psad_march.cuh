@@ -15,7 +15,7 @@
 // and the queue of outstanding HBM requests never drains.
 //
 // The including translation unit defines, before this header:
-//   namespace cfg { NDIM, TX, TY, TXS, XORG, THREADS (consumer threads), MIN_CTAS, STAGES, HZL, HZH, JREL, NP, NTMA,
+//   namespace cfg { NDIM, TX, TY, TXS, XORG, TYS, YORG, THREADS (consumer threads), MIN_CTAS, STAGES, HZL, HZH, JREL, NP, NTMA,
 //                   STAGE_BYTES, TX_BYTES, F_OFF[], F_ORGX[], F_ORGY[] }
 //   struct PsadCarry;  psad_item_begin(...);  psad_step(...);  PSAD_KERNEL_NAME
 #ifndef PSAD_MARCH_CUH

@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '17'
+EMITTER_VERSION = '18'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
@@ -343,6 +343,8 @@ class MarchTuning:
     #                                 scalars (no raw values); default: when the stencil has more than 9 accesses
     cross_cse: Optional[bool] = None   # common subexpressions across ALL cells of a thread (default: non-linear
     #                                    stencils, whose neighbouring cells share fluxes / norms / reciprocal roots)
+    exchange: Optional[bool] = None    # fused-step kernels (emit_chain.py): pass intermediate rows between warps through
+    #                                    shared memory (one consumer barrier per plane) instead of recomputing them
     store_mode: int = 1    # global store cache policy: 0 default, 1 streaming (.cs, default), 2 write-through
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes; scalar LDS halos only win for narrow fp64 strips)
@@ -597,7 +599,7 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     if t.store_mode != 1:
         L.append('#define PSAD_STORE_MODE %d' % t.store_mode)
     L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT, 'namespace cfg {',
-          'constexpr int NDIM = %d, TX = %d, TY = %d, TXS = %d, XORG = 0;' % (nd, TX, TY, TX),
+          'constexpr int NDIM = %d, TX = %d, TY = %d, TXS = %d, XORG = 0, TYS = %d, YORG = 0;' % (nd, TX, TY, TX, TY),
           'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d, JREL = %d, NP = %d;'
           % (THREADS, min_ctas, STAGES, HZL, HZH, jrel, NP),
           'constexpr int NTMA = %d, STAGE_BYTES = %d, TX_BYTES = %d;' % (len(tma_fields), STAGE_BYTES,

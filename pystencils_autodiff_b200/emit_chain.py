@@ -70,7 +70,8 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     if reason:
         raise ValueError('fused-step march variant not applicable: ' + reason)
     t = tuning or MarchTuning()
-    name = _kernel_name(ir, 'march_x2')
+    _e = (ir.input_fields[0].dtype.itemsize == 4) if t.exchange is None else bool(t.exchange)
+    name = _kernel_name(ir, 'march_x2e' if (_e and sum(ir.halo(ir.input_fields[0].name)[0]) > 0) else 'march_x2')
     CT = _CT[ir.compute_dtype]
     pr = _CudaPrinter(ir.compute_dtype)
     fin, fout = ir.input_fields[0], ir.output_fields[0]
@@ -84,16 +85,21 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     # ---- geometry ------------------------------------------------------------------------------------------------
     (HZL, HZH), (HYL, HYH), (HXL, HXR) = [tuple(h) for h in ir.halo(fin.name)]
     D1 = HZL + HZH
-    # measured on B200 (scripts/steps_bench.py): fp32 7-point 30x128 tiles, 2 rows x 4 columns per thread, 15+1 warps at
-    # 128 registers: 2.00 ms per pair of steps at 1024^3 against 2.78 ms for two launches.  fp64: narrow strips keep
-    # the accumulators of both stages in registers (22x64 tiles, 2 x 2 cells per thread, 11+1 warps).
+    # measured on B200 (scripts/steps_bench.py), 7-point fp32 at 1024^3, two launches = 2.77 ms:
+    #   rows exchanged through shared memory, 44x128 tiles, 4 x 4 cells per thread, 11+1 warps, 168 registers: 1.73 ms
+    #   same with 30x128 tiles, 2 x 4 cells, 15+1 warps, 109 registers: 1.79 ms
+    #   rows recomputed, 30x128 tiles, 2 x 4 cells, 15+1 warps, 128 registers: 1.99 ms
+    # 27-point fp64 at 768^3, two launches = 2.26 ms: recomputed rows 22x64 / 2 x 2 cells / 11+1 warps 2.29 ms,
+    # exchanged rows 28x64 / 4 x 2 cells 2.37 ms — no gain either way, fp64 pairs are not fused by default (run_steps).
+    want_exchange = (es == 4) if t.exchange is None else bool(t.exchange)
     SX = t.sx or (4 if es == 4 else 2)
     if (SX * es) % 16:
         raise ValueError('sx*itemsize must be a multiple of 16 bytes')
     if HXL > SX or HXR > SX:
         raise ValueError('x halo wider than the per-thread strip')
-    RY = t.ry or 2
-    TY = t.ty or (RY * (15 if es == 4 else 11))    # 15+1 / 11+1 warps: the register budget is per CTA size rounded to 4 warps
+    RY = t.ry or (4 if (es == 4 and want_exchange) else 2)
+    # warps: the register budget is per CTA size rounded up to 4 warps (11+1 warps: 170 registers, 15+1: 128)
+    TY = t.ty or (RY * (11 if (es == 8 or want_exchange) else 15))
     if TY % RY:
         raise ValueError('ty must be a multiple of ry')
     THREADS = 32 * (TY // RY)
@@ -110,7 +116,16 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     padl = -(-HXL // vec) * vec if fixup else 0
     padr = -(-HXR // vec) * vec if fixup else 0
     boxw = TX + padl + padr
-    boxh = TY + 2 * (HYL + HYH)
+    # Intermediate rows owned by the neighbouring warps: recomputed by every thread (input box with two y radii), or —
+    # `exchange` — written to a shared buffer by their owners and read back after one consumer barrier (input box with
+    # one y radius; the tile's outermost rows have no owner, so tiles then overlap along y as well)
+    exchange = want_exchange and D1 > 0
+    U_L, U_H = (HYL, HYH) if exchange else (2 * HYL, 2 * HYH)      # input rows above / below the thread's own rows
+    TYS = TY - HYL - HYH if exchange else TY
+    YORG = -HYL if exchange else 0
+    if TYS < 1:
+        raise ValueError('tile too short for the y halo')
+    boxh = TY + U_L + U_H
     if boxw > 256 or boxh > 256:
         raise ValueError('TMA box too large')
     STAGE_BYTES = -(-(boxw * boxh * es) // 128) * 128
@@ -118,12 +133,17 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     STAGES = t.stages or (1 + max(1, lookahead))
     if STAGES < 2:
         raise ValueError('ring too small')
-    smem_bytes = STAGES * STAGE_BYTES + 16 * STAGES
+    NP = D1 + 1
+    cwb = np.dtype(ir.compute_dtype).itemsize
+    XB_ROWS = TY + HYL + HYH                        # exchange buffer: one intermediate plane of the tile + unowned pad rows
+    XBUF_OFF = -(-(STAGES * STAGE_BYTES + 16 * STAGES) // 128) * 128
+    smem_bytes = XBUF_OFF + NP * XB_ROWS * TX * cwb if exchange else STAGES * STAGE_BYTES + 16 * STAGES
     if smem_bytes > 227 * 1024:
         raise ValueError('ring does not fit in shared memory (%d bytes)' % smem_bytes)
-    NP = D1 + 1
-    rows1 = list(range(-HYL, RY + HYH))            # rows of T a thread evaluates (relative to its first output row)
-    rows0 = list(range(-2 * HYL, RY + 2 * HYH))    # rows of u it reads
+    rows1 = list(range(0, RY)) if exchange else list(range(-HYL, RY + HYH))   # rows of T a thread evaluates
+    trows = list(range(-HYL, RY + HYH))             # rows of T its second stage reads
+    rows0 = list(range(-U_L, RY + U_H))             # rows of u it reads
+    A1 = -rows1[0]                                  # row offset of the stage-1 accumulator / mask arrays
     cw = np.dtype(ir.compute_dtype).itemsize // 4
     words = (len(rows1) + RY) * SX * cw * D1 + len(rows0) * (SX + HXL + HXR) * (es // 4)
     reg_cap = min(255, 65536 // (-(-(THREADS + 32) // 128) * 128))
@@ -162,18 +182,20 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     if t.store_mode != 1:
         L.append('#define PSAD_STORE_MODE %d' % t.store_mode)
     L += ['#include "psad_common.cuh"', '', 'typedef %s CT;' % CT, 'namespace cfg {',
-          'constexpr int NDIM = 3, TX = %d, TY = %d, TXS = %d, XORG = %d;' % (TX, TY, TXS, XORG),
+          'constexpr int NDIM = 3, TX = %d, TY = %d, TXS = %d, XORG = %d, TYS = %d, YORG = %d;' % (TX, TY, TXS, XORG, TYS, YORG),
           'constexpr int THREADS = %d, MIN_CTAS = %d, STAGES = %d, HZL = %d, HZH = %d, JREL = %d, NP = %d;'
           % (THREADS, min_ctas, STAGES, 2 * HZL, 2 * HZH, 2 * D1, NP),
           'constexpr int NTMA = 1, STAGE_BYTES = %d, TX_BYTES = %d;' % (STAGE_BYTES, boxw * boxh * es),
           '__device__ constexpr int F_OFF[NTMA] = {0};',
           '__device__ constexpr int F_ORGX[NTMA] = {%d};' % -padl,
-          '__device__ constexpr int F_ORGY[NTMA] = {%d};' % (-2 * HYL),
-          '}  // namespace cfg', '']
+          '__device__ constexpr int F_ORGY[NTMA] = {%d};' % -U_L] + \
+         (['constexpr int SMEM_BYTES = %d, XBUF_OFF = %d, XB_PLANE = %d;  // exchange buffers: NP planes of %d x TX values'
+           % (smem_bytes, XBUF_OFF, XB_ROWS * TX, XB_ROWS)] if exchange else []) + \
+         ['}  // namespace cfg', ''] + (['#define PSAD_CTA_EXCHANGE 1', ''] if exchange else [])
     L.append('struct PsadCarry {')
     for k in range(NP):
         for r in rows1:
-            L.append('  CT a1_k%d_r%d[%d];  // intermediate plane accumulator, slot %d, row %+d' % (k, r + HYL, SX, k, r))
+            L.append('  CT a1_k%d_r%d[%d];  // intermediate plane accumulator, slot %d, row %+d' % (k, r + A1, SX, k, r))
     for k in range(NP):
         for r in range(RY):
             L.append('  CT a2_k%d_r%d[%d];  // output plane accumulator, slot %d, row %d' % (k, r, SX, k, r))
@@ -200,9 +222,12 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
           '  }',
           '#pragma unroll',
           '  for (int r = 0; r < %d; ++r)' % len(rows1),
-          '    ymt |= (ys + r - %d >= (int)A.it_lo[1] && ys + r - %d < (int)A.it_hi[1]) ? (1u << r) : 0u;' % (HYL, HYL),
+          '    ymt |= (ys + r - %d >= (int)A.it_lo[1] && ys + r - %d < (int)A.it_hi[1]) ? (1u << r) : 0u;' % (A1, A1),
           # lanes whose columns are recomputed by the neighbouring tile, or lie beyond the row, never store
-          '  if (lane < %d || lane >= %d%s) ymw = 0;' % (EL, 32 - ER, ' || xs + %d > (int)A.shape[2]' % SX if SX == vec else ''),
+          '  if (lane < %d || lane >= %d%s) ymw = 0;' % (EL, 32 - ER, ' || xs + %d > (int)A.shape[2]' % SX if SX == vec else '')] + \
+         (['#pragma unroll',     # exchange: the tile's outermost rows get no intermediate rows from a neighbour
+           '  for (int r = 0; r < %d; ++r)' % RY,
+           '    if (wy * %d + r < %d || wy * %d + r >= %d) ymw &= ~(1u << r);' % (RY, HYL, RY, TY - HYH)] if exchange else []) + [
           '  R.xmask = xm; R.ymask_wr = ymw; R.ymask_it = ymi; R.ymask_t = ymt;',
           '  R.o0 = reinterpret_cast<%s*>(A.ptr[%d]) + (long long)ys * A.stride[%d][1] + xs;' % (T, fo, fo),
           '}', '']
@@ -269,7 +294,7 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     def accumulate(stage, ph, cells, contribs, done):
         """Fold the groups of the arriving plane into the accumulators; ``done(r, c, text)`` receives the completed value."""
         def acc(k, r, c):
-            return 'R.a%d_k%d_r%d[%d]' % (stage, (ph + k) % NP, r + (HYL if stage == 1 else 0), c)
+            return 'R.a%d_k%d_r%d[%d]' % (stage, (ph + k) % NP, r + (A1 if stage == 1 else 0), c)
 
         for (r, c) in cells:
             for k in range(D1, -1, -1):          # k = D1: first contribution ... k = 0: last one, plane complete
@@ -295,14 +320,14 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
         L.append('  const unsigned char* st = ring + slot * cfg::STAGE_BYTES;')
         # ---- stage 1: the arriving input plane
         for r in rows0:
-            ri = r + 2 * HYL
+            ri = r + U_L
             L.append('  %s u%d[%d];' % (T, ri, W0))
             L.append('  const %s* p%d = reinterpret_cast<const %s*>(st) + (wy * %d + %d) * %d + %d + lane * %d;'
                      % (T, ri, T, RY, ri, boxw, padl, SX))
             for v in range(SX // vec):
                 L.append('  psad_lds_vec<%s>(p%d + %d, &u%d[%d]);' % (T, ri, v * vec, ri, HXL + v * vec))
         for r in rows0:
-            ri = r + 2 * HYL
+            ri = r + U_L
             for c in range(-HXL, 0):
                 L.append('  u%d[%d] = psad_from_left(u%d[%d]);' % (ri, c + HXL, ri, SX + c + HXL))
                 if fixup:
@@ -314,10 +339,10 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
         L.append('  __syncwarp();')
         L.append('  if (lane == 0 && rel_bar) psad_mbar_arrive(rel_bar);')
         cells1 = [(r, c) for r in rows1 for c in range(SX)]
-        g1 = emit_groups(1, cells1, lambda r, c: '((CT)u%d[%d])' % (r + 2 * HYL, c + HXL))
+        g1 = emit_groups(1, cells1, lambda r, c: '((CT)u%d[%d])' % (r + U_L, c + HXL))
         L.append('  // intermediate plane z + %d is complete; outside the iteration range the next step would read 0' % HZH)
         L.append('  const unsigned tm = (z + %d >= R.zlo && z + %d < R.zhi) ? R.ymask_t : 0u;' % (HZH, HZH))
-        for r in rows1:
+        for r in trows:
             L.append('  CT t%d[%d];' % (r + HYL, W0))
 
         def done1(r, c, text):
@@ -327,10 +352,26 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
         L.append('  if (tm != %du || R.xmask != %du) {' % ((1 << len(rows1)) - 1, (1 << SX) - 1))
         for (r, c) in cells1:
             L.append('    t%d[%d] = (((tm >> %d) & 1u) && ((R.xmask >> %d) & 1u)) ? t%d[%d] : (CT)0;'
-                     % (r + HYL, c + HXL, r + HYL, c, r + HYL, c + HXL))
+                     % (r + HYL, c + HXL, r + A1, c, r + HYL, c + HXL))
         L.append('  }')
+        if exchange:
+            # own rows -> shared buffer of this phase; barrier over the consumer warps; neighbours' rows <- buffer.  NP >= 2
+            # buffers: a warp that is one step ahead writes another buffer than the one a slower warp still reads, and
+            # cannot get two steps ahead without that warp passing the next barrier.
+            L.append('  CT* xb = reinterpret_cast<CT*>(const_cast<unsigned char*>(ring) + cfg::XBUF_OFF) + %d * cfg::XB_PLANE'
+                     ' + (wy * %d + %d) * %d + lane * %d;' % (ph, RY, HYL, TX, SX))
+            cvec = 16 // cwb
+            for r in rows1:
+                for v in range(SX // cvec):
+                    L.append('  psad_sts_vec<CT>(xb + %d + %d, &t%d[%d]);' % (r * TX, v * cvec, r + HYL, HXL + v * cvec))
+            L.append('  psad_consumer_barrier(cfg::THREADS);')
+            for r in trows:
+                if r in rows1:
+                    continue
+                for v in range(SX // cvec):
+                    L.append('  psad_lds_vec<CT>(xb + (%d) + %d, &t%d[%d]);' % (r * TX, v * cvec, r + HYL, HXL + v * cvec))
         # ---- stage 2: the completed intermediate plane arrives
-        for r in rows1:
+        for r in trows:
             ri = r + HYL
             for c in range(-HXL, 0):
                 L.append('  t%d[%d] = psad_from_left(t%d[%d]);' % (ri, c + HXL, ri, SX + c + HXL))
@@ -386,12 +427,12 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
                     tma=int(is_in), box=(boxw, boxh, 1) if is_in else (0, 0, 0))
 
     plan = dict(kind=1, ndim=3, n_fields=len(fields), n_scalars=len(scalars), threads=THREADS + 32, smem_bytes=smem_bytes,
-                tile_x=TXS, tile_y=TY, chunk=t.chunk, ctas_per_sm=t.ctas_per_sm, warmup=2 * D1, fused_steps=2,
+                tile_x=TXS, tile_y=TYS, chunk=t.chunk, ctas_per_sm=t.ctas_per_sm, warmup=2 * D1, fused_steps=2,
                 boundary=1 if ir.boundary == 'zeros' else 0, ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
     ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
     ek.masked = True
     if ir.fast_math:
         ek.options = ek.options + FAST_MATH_OPTIONS
-    ek.geometry = dict(TX=TX, TY=TY, RY=RY, SX=SX, TXS=TXS, STAGES=STAGES, STAGE_BYTES=STAGE_BYTES, HZ=(2 * HZL, 2 * HZH),
+    ek.geometry = dict(TX=TX, TY=TY, RY=RY, SX=SX, TXS=TXS, TYS=TYS, exchange=exchange, STAGES=STAGES, STAGE_BYTES=STAGE_BYTES, HZ=(2 * HZL, 2 * HZH),
                        threads=THREADS, min_ctas=min_ctas, reg_cap=reg_cap, est_words=words)
     return ek

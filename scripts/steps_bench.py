@@ -1,7 +1,8 @@
 """Two fused steps per launch (emit_chain.py) against two single-step launches: parity on a small grid (oracle applied
 twice), agreement at full size, and timing over a few tile geometries.
     python scripts/steps_bench.py c4            # 27-point fp64, 768^3
-    python scripts/steps_bench.py c3 "2,30,4,0;2,22,4,0"   # candidates as ry,ty,sx,lookahead"""
+    python scripts/steps_bench.py c3 "2,30,4,0;2,22,4,0"   # candidates as ry,ty,sx,lookahead[,exchange]
+    python scripts/steps_bench.py c4 "3,21,4,0,1" c3 "2,30,4,0,1"      # several workloads in one process"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,9 +29,25 @@ def timed(fn, iters=8, warm=3):
     return ts[len(ts) // 2]
 
 
+def _tuning(cand):
+    v = [int(x) for x in cand.split(',')]
+    return MarchTuning(ry=v[0], ty=v[1], sx=v[2], lookahead=v[3], exchange=bool(v[4]) if len(v) > 4 else None)
+
+
 def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else 'c4'
-    cands = (sys.argv[2] if len(sys.argv) > 2 else DEFAULT_CANDIDATES[name]).split(';')
+    args = sys.argv[1:] or ['c4']
+    i = 0
+    while i < len(args):
+        name = args[i]
+        cands = DEFAULT_CANDIDATES[name]
+        if i + 1 < len(args) and args[i + 1][0].isdigit():
+            cands = args[i + 1]
+            i += 1
+        i += 1
+        run(name, cands.split(';'))
+
+
+def run(name, cands):
     dev = torch.device('cuda:0')
     # ---- parity on a small grid, both boundary modes, forward and adjoint kernels
     from oracle.evaluate import evaluate
@@ -39,6 +56,7 @@ def main():
         op = make_config(name, shape=small, boundary_handling=bh)
         for ir, assigns in ((op.forward_ast_gpu, op.forward_assignments), (op.backward_ast_gpu, op.backward_assignments)):
             k = CompiledKernel(ir)
+            k.tuning_x2 = _tuning(cands[0])          # parity runs with the first candidate's geometry
             fin, fout = ir.input_fields[0], ir.output_fields[0]
             u = np.random.default_rng(1).standard_normal(small).astype(fin.dtype.numpy_dtype)
             r1 = evaluate(assigns, {fin.name: u}, boundary_handling=bh)[fout.name].astype(u.dtype)
@@ -47,7 +65,7 @@ def main():
             out = torch.full_like(ut, float('nan'))
             k(**{fin.name: ut, fout.name: out}, _variant='march_x2')
             err = float(np.abs(out.cpu().numpy() - r2).max())
-            out5 = k.run_steps(ut, 5)
+            out5 = k.run_steps(ut, 5, fuse=True)
             r = u
             for _ in range(5):
                 r = evaluate(assigns, {fin.name: r}, boundary_handling=bh)[fout.name].astype(u.dtype)
@@ -74,9 +92,8 @@ def main():
           flush=True)
     ref = b.clone()
     for cand in cands:
-        ry, ty, sx, la = [int(v) for v in cand.split(',')]
         k2 = CompiledKernel(ir)
-        k2.tuning_x2 = MarchTuning(ry=ry, ty=ty, sx=sx, lookahead=la)
+        k2.tuning_x2 = _tuning(cand)
         try:
             ek = k2.emitted('march_x2')
         except ValueError as e:
@@ -86,9 +103,9 @@ def main():
         t2 = timed(lambda: k2(**{fin.name: u, fout.name: out}, _variant='march_x2'))
         diff = float((out - ref).abs().max())
         attrs = k2.native('march_x2').attributes()
-        print('  x2 %-10s tile %dx%d ry=%d sx=%d stages=%d regs=%d occ=%d: %.3f ms  = %.2fx two launches, %.1f Gcell-steps/s, '
+        print('  %s %-12s tile %dx%d ry=%d sx=%d stages=%d regs=%d occ=%d: %.3f ms  = %.2fx two launches, %.1f Gcell-steps/s, '
               '%.0f GB/s of field traffic, max|diff| vs two launches %.3g'
-              % (cand, ek.geometry['TY'], ek.geometry['TX'], ek.geometry['RY'], ek.geometry['SX'], ek.geometry['STAGES'],
+              % ('x2e' if ek.geometry['exchange'] else 'x2 ', cand, ek.geometry['TY'], ek.geometry['TX'], ek.geometry['RY'], ek.geometry['SX'], ek.geometry['STAGES'],
                  attrs['num_regs'], attrs['max_ctas_per_sm'], t2, t1 / t2, 2 * cells / t2 / 1e6, cells * bpc / t2 / 1e6, diff), flush=True)
 
 

@@ -24,7 +24,10 @@ struct PsadEmuWarp {
 extern thread_local PsadEmuWarp* psad_emu_warp;
 extern thread_local int psad_emu_lane;
 
+extern thread_local std::barrier<>* psad_emu_cta;     // all consumer threads of the replayed CTA (exchange kernels)
+
 static inline void __syncwarp() { psad_emu_warp->bar.arrive_and_wait(); }
+static inline void psad_consumer_barrier(int) { psad_emu_cta->arrive_and_wait(); }
 static inline void psad_mbar_arrive(psad_u32) {}
 
 template <typename T> static inline T psad_emu_shift(T v, int delta) {
@@ -42,6 +45,7 @@ template <typename T> static inline T psad_from_right(T v) { return psad_emu_shi
 
 template <typename T> static inline void psad_lds_vec(const T* p, T* e) { std::memcpy(e, p, 16); }
 template <typename T> static inline void psad_stg_vec(T* p, const T* e) { std::memcpy(p, e, 16); }
+template <typename T> static inline void psad_sts_vec(T* p, const T* e) { std::memcpy(p, e, 16); }
 
 static inline float psad_rsqrt(float x) { return 1.0f / std::sqrt(x); }
 static inline double psad_rsqrt(double x) { return 1.0 / std::sqrt(x); }

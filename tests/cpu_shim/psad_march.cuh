@@ -12,6 +12,7 @@
 
 thread_local PsadEmuWarp* psad_emu_warp = nullptr;
 thread_local int psad_emu_lane = 0;
+thread_local std::barrier<>* psad_emu_cta = nullptr;
 
 struct PsadEmuField {      // one staged (TMA) input field, plan order
   const void* ptr;
@@ -31,6 +32,8 @@ static void psad_emu_stage(unsigned char* dst, const PsadArgs& A, const PsadEmuF
     }
 }
 
+#ifndef PSAD_CTA_EXCHANGE
+// ---- warps are independent: replay them one after the other, each with a private copy of the ring ----------------
 extern "C" int psad_emulate(const PsadArgs* Ap, const PsadEmuField* tf, int n_tf, int n_ctas) {
   const PsadArgs& A = *Ap;
   if (n_tf != cfg::NTMA) return 1;
@@ -86,5 +89,52 @@ extern "C" int psad_emulate(const PsadArgs* Ap, const PsadEmuField* tf, int n_tf
     }
   return 0;
 }
+#else
+// ---- kernels whose consumer warps talk to each other through shared memory (psad_consumer_barrier): all warps of the
+// CTA run concurrently on one shared-memory image [ring | barriers | exchange buffers] of cfg::SMEM_BYTES; the plane is
+// staged once per step by thread 0 between two CTA-wide barriers.  Inside a step the warps are ordered only by the
+// kernel's own barrier, so a missing or misplaced one shows up as a race.
+extern "C" int psad_emulate(const PsadArgs* Ap, const PsadEmuField* tf, int n_tf, int n_ctas) {
+  const PsadArgs& A = *Ap;
+  if (n_tf != cfg::NTMA) return 1;
+  constexpr int D = cfg::HZL + cfg::HZH;
+  constexpr int NWARPS = cfg::THREADS / 32;
+  static_assert(D - cfg::JREL == 0 && cfg::NDIM == 3, "exchange kernels read only the newest plane of a 3-D march");
+  for (int cta = 0; cta < n_ctas; ++cta) {
+    std::vector<unsigned char> smem((size_t)cfg::SMEM_BYTES, 0xff);
+    std::vector<PsadEmuWarp> W(NWARPS);
+    std::barrier<> cta_bar(NWARPS * 32);
+    auto thread_main = [&](int warp, int lane) {
+      psad_emu_warp = &W[warp];
+      psad_emu_lane = lane;
+      psad_emu_cta = &cta_bar;
+      int slot = 0, ph = 0;
+      PsadCarry R;
+      std::memset(&R, 0xff, sizeof(R));
+      for (long long item = cta; item < A.n_items; item += n_ctas) {
+        const PsadItem it = psad_decode_item(A, item);
+        psad_item_begin(A, R, lane, warp, it.y0, it.x0);
+        for (int p = it.p_first; p <= it.p_last; ++p) {
+          if (warp == 0 && lane == 0)
+            for (int f = 0; f < cfg::NTMA; ++f)
+              psad_emu_stage(smem.data() + (size_t)slot * cfg::STAGE_BYTES + cfg::F_OFF[f], A, tf[f], it.x0 + cfg::F_ORGX[f],
+                             it.y0 + cfg::F_ORGY[f], p);
+          cta_bar.arrive_and_wait();
+          const int zo = p - cfg::HZH;
+          psad_step(A, smem.data(), slot, R, lane, warp, zo >= it.z0, zo, it.y0, it.x0, 1u, ph);
+          cta_bar.arrive_and_wait();
+          if (++slot == cfg::STAGES) slot = 0;
+          if (++ph == cfg::NP) ph = 0;
+        }
+      }
+    };
+    std::vector<std::thread> threads;
+    for (int warp = 0; warp < NWARPS; ++warp)
+      for (int lane = 0; lane < 32; ++lane) threads.emplace_back(thread_main, warp, lane);
+    for (auto& t : threads) t.join();
+  }
+  return 0;
+}
+#endif
 
 #endif

@@ -49,9 +49,11 @@ def _twice(assigns, fin, fout, u, bh):
 
 
 @pytest.mark.parametrize('make, shape, bh, which, tuning, tol', [
-    (configs.heat3d_op, (5, 31, 124), 'zeros', 'forward', None, 4e-7),
+    (configs.heat3d_op, (5, 47, 124), 'zeros', 'forward', None, 4e-7),       # default fp32: rows exchanged between warps
     (configs.heat3d_op, (7, 23, 252), None, 'backward', MarchTuning(ry=2, ty=10, sx=4), 4e-7),
-    (configs.heat3d_op, (5, 20, 132), 'zeros', 'forward', MarchTuning(ry=3, ty=9, sx=4), 4e-7),
+    (configs.heat3d_op, (5, 31, 124), 'zeros', 'forward', MarchTuning(exchange=False, ry=2, ty=30), 4e-7),   # rows recomputed
+    (configs.heat3d_op, (5, 20, 132), None, 'forward', MarchTuning(exchange=False, ry=3, ty=9, sx=4), 4e-7),
+    (configs.stencil27_op, (5, 17, 124), 'zeros', 'backward', MarchTuning(exchange=True, ry=3, ty=9, sx=4), 1e-14),
     (configs.stencil27_op, (5, 23, 68), 'zeros', 'forward', None, 1e-14),
     (configs.stencil27_op, (6, 17, 124), None, 'backward', MarchTuning(ry=2, ty=14, sx=4), 1e-14),
 ])
@@ -64,6 +66,7 @@ def test_fused_two_steps_replay(make, shape, bh, which, tuning, tol):
     assert chain_ineligible_reason(ir) is None
     ek = emit_march_chain(ir, tuning)
     assert ek.plan['fused_steps'] == 2 and ek.plan['tile_x'] < ek.geometry['TX']
+    assert (ek.plan['tile_y'] < ek.geometry['TY']) == ek.geometry['exchange'] == ('psad_consumer_barrier' in ek.source)
     arrays, named = _fields(ek, ir, shape, seed=3)
     assert emu.run(ek, arrays) > 0
     fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
@@ -193,3 +196,17 @@ def test_slab_launch_ranges_replay(bh, world):
             same = part['iter_lo'] == part['write_lo'] and part['iter_hi'] == part['write_hi']
             emu.run(plain_kernel if same else masked_kernel, [local_out, local_u], launch_range=part)
         assert np.array_equal(local_out[g:g + n], whole[start:start + n]), rank
+
+
+def test_replay_detects_a_missing_consumer_barrier():
+    """The CTA-concurrent replay orders warps inside a step only through the kernel's own barrier: without it the
+    neighbours' intermediate rows are read before they are written and the result is wrong."""
+    shape = (5, 20, 124)
+    op = configs.heat3d_op(shape=shape)
+    ek = emit_march_chain(op.forward_ast_gpu, MarchTuning(exchange=True, ry=2, ty=8))
+    assert ek.source.count('psad_consumer_barrier(cfg::THREADS);') == 3        # one per window phase
+    ek.source = ek.source.replace('  psad_consumer_barrier(cfg::THREADS);\n', '')
+    arrays, named = _fields(ek, op.forward_ast_gpu, shape, seed=0)
+    emu.run(ek, arrays)
+    ref = _twice(op.forward_assignments, 'u', 'out', named['u'].copy(), 'zeros')
+    assert np.nanmax(np.abs(named['out'] - ref)) > 1e-3
