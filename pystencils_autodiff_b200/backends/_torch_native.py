@@ -89,7 +89,7 @@ class CompiledKernel:
     def run_steps(self, src, steps, out=None, fuse=None, **scalars):
         """``S^steps(src)``: the stencil applied ``steps`` times, ping-ponging between ``out`` and one scratch tensor;
         ``src`` is not modified.  ``fuse``: run pairs of steps as one launch (one read and one write of the field per
-        pair instead of two).  Default: where that is a measured win — 4-byte fields (7-point fp32 at 1024^3: 1.39x);
+        pair instead of two).  Default: where that is a measured win — 4-byte fields (7-point fp32 at 1024^3: 1.61x);
         for fp64 the rows recomputed by the fused kernel cost as much FP64 issue as the saved traffic (27-point fp64 at
         768^3: 1.00x), so those stay on single-step launches unless asked."""
         import torch

@@ -6,18 +6,22 @@ and writes the whole field in HBM.  SURVEY.md §8 f-1 names fusing steps as the 
 kernel is at the roofline.  This emitter produces, for ``out = S(u)``, a kernel that computes ``out = S(S(u))`` with
 the per-step boundary semantics of two separate launches, reading ``u`` once and writing ``out`` once.
 
-How (all inside the march template, `csrc/kernels/psad_march.cuh`, with no synchronisation beyond the TMA ring):
+How (all inside the march template, `csrc/kernels/psad_march.cuh`):
 
-* the march along z is unchanged; the staged box carries a halo of two stencil radii;
+* the march along z is unchanged; the staged box carries the extra halo the second application needs;
 * **stage 1** — when input plane P arrives, every thread evaluates the in-plane groups of the stencil sum for its own
-  SX columns and for the rows stage 2 will read (its RY rows plus the y halo: those extra rows are *recomputed* per
-  thread instead of exchanged between warps) and adds them into per-cell accumulators of the intermediate planes in
-  flight.  Plane ``P - HZH`` of the intermediate field T is then complete.  T is forced to 0 outside the iteration
-  range — that is what the second launch would have read there;
+  SX columns and adds them into per-cell accumulators of the intermediate planes in flight.  Plane ``P - HZH`` of the
+  intermediate field T is then complete.  T is forced to 0 outside the iteration range — that is what the second
+  launch would have read there;
+* the T rows stage 2 needs from the neighbouring warps (the y halo) are either **exchanged** — every warp stores its rows
+  of the completed plane to a shared buffer, the consumer warps meet at one named barrier, each thread loads the rows
+  above and below its own (``MarchTuning.exchange``, default for 4-byte fields; tiles then overlap along y because the
+  tile's outermost rows have no owner) — or **recomputed**: stage 1 also covers the halo rows of every thread, and the
+  warps never synchronise beyond the TMA ring;
 * **stage 2** — the completed T plane is treated exactly like an arriving input plane: x halos come from the
   neighbouring lanes by warp shuffle, the in-plane groups go into the accumulators of the output planes in flight, and
-  output plane ``P - 2 HZH`` is complete and stored.
-* Lanes at the edge of a tile row have no neighbour to take the T halo from, so their columns are not stored: tiles
+  output plane ``P - 2 HZH`` is complete and stored;
+* lanes at the edge of a tile row have no neighbour to take the T halo from, so their columns are not stored: tiles
   overlap by one strip per side (tile pitch ``TXS = 30 * SX`` for a 32-lane row, origin ``XORG = -SX``).
 
 Accumulators are addressed by physical slot ``(phase + k) mod NP`` like the register window of the single-step
