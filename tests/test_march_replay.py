@@ -210,3 +210,57 @@ def test_replay_detects_a_missing_consumer_barrier():
     emu.run(ek, arrays)
     ref = _twice(op.forward_assignments, 'u', 'out', named['u'].copy(), 'zeros')
     assert np.nanmax(np.abs(named['out'] - ref)) > 1e-3
+
+
+def test_symbolic_scalar_and_fused_steps_replay():
+    """A free scalar (alpha) reaches the kernels through the parameter block; with a symbolic coefficient the
+    right-hand side only splits by z plane after expansion (emit_chain._planewise)."""
+    import sympy as sp
+    shape = (5, 12, 124)
+    alpha = sp.Symbol('alpha')
+    op = configs.heat3d_op(shape=shape, alpha=alpha)
+    ir = op.forward_ast_gpu
+    assert [s_.name for s_ in ir.scalars] == ['alpha']
+    for ek, steps in ((emit_march(ir, None, masked=False), 1), (emit_march_chain(ir), 2),
+                      (emit_march_chain(ir, MarchTuning(exchange=False)), 2)):
+        arrays, named = _fields(ek, ir, shape, seed=4)
+        emu.run(ek, arrays, scalars=[0.07])
+        ref = named['u'].copy()
+        for _ in range(steps):
+            ref = evaluate(op.forward_assignments, {'u': ref}, boundary_handling='zeros', scalars={'alpha': 0.07})['out'].astype(np.float32)
+        np.testing.assert_allclose(named['out'], ref, rtol=0, atol=5e-7)
+
+
+def test_two_dimensional_interior_iteration_replay():
+    """2-D march (row tiles instead of planes) with boundary None: zero border written by the kernel."""
+    shape = (37, 132)
+    op = configs.diffusion2d_op(shape=shape, boundary_handling=None)
+    for ir, assigns in ((op.forward_ast_gpu, op.forward_assignments), (op.backward_ast_gpu, op.backward_assignments)):
+        ek = emit_march(ir, None, masked=True)
+        arrays, named = _fields(ek, ir, shape, seed=8)
+        emu.run(ek, arrays)
+        ref = evaluate(assigns, {f.name: named[f.name].copy() for f in ir.input_fields}, boundary_handling=None)
+        for f in ir.output_fields:
+            np.testing.assert_allclose(named[f.name], ref[f.name], rtol=0, atol=3e-7)
+            assert (named[f.name][0] == 0).all() and (named[f.name][:, -1] == 0).all()
+
+
+def test_fused_forward_adjoint_kernel_replay():
+    """AutoDiffOp.fused_ast_gpu: forward and adjoint assignments of the README operator as one march kernel."""
+    shape = (24, 64)
+    op = configs.readme_op(shape=shape, boundary_handling='zeros')
+    ir = op.fused_ast_gpu
+    ek = emit_march(ir, None, masked=False)
+    rng = np.random.default_rng(9)
+    arrays, named = [], {}
+    for f in ek.fields:
+        a = emu.aligned_empty(shape, f.dtype.numpy_dtype)
+        a[...] = rng.uniform(0.5, 1.5, size=shape) if f in ir.input_fields else np.nan
+        arrays.append(a)
+        named[f.name] = a
+    emu.run(ek, arrays)
+    fwd = evaluate(op.forward_assignments, {n: named[n].copy() for n in ('x', 'y')}, boundary_handling='zeros')
+    bwd = evaluate(op.backward_assignments, {n: named[n].copy() for n in ('x', 'y', 'diffz')}, boundary_handling='zeros')
+    np.testing.assert_allclose(named['z'], fwd['z'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(named['diffx'], bwd['diffx'], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(named['diffy'], bwd['diffy'], rtol=2e-6, atol=2e-6)
