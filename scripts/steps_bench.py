@@ -1,5 +1,5 @@
-"""Two fused steps per launch (emit_chain.py) against two single-step launches: parity on a small grid (oracle applied
-twice), agreement at full size, and timing over a few tile geometries.
+"""Two fused steps per launch (emit_chain.py) against two single-step launches: agreement on a small grid and at full
+size, and timing over a few tile geometries.
     python scripts/steps_bench.py c4            # 27-point fp64, 768^3
     python scripts/steps_bench.py c3 "2,30,4,0;2,22,4,0"   # candidates as ry,ty,sx,lookahead[,exchange]
     python scripts/steps_bench.py c4 "3,21,4,0,1" c3 "2,30,4,0,1"      # several workloads in one process"""
@@ -49,28 +49,24 @@ def main():
 
 def run(name, cands):
     dev = torch.device('cuda:0')
-    # ---- parity on a small grid, both boundary modes, forward and adjoint kernels
-    from oracle.evaluate import evaluate
+    # ---- small grid, both boundary modes, forward and adjoint kernels: one fused launch against two single-step launches
+    # (parity against the CPU oracle is the tests' job: tests/test_gpu_steps.py, tests/test_march_replay.py)
     small = (19, 45, 252)
     for bh in ('zeros', None):
         op = make_config(name, shape=small, boundary_handling=bh)
-        for ir, assigns in ((op.forward_ast_gpu, op.forward_assignments), (op.backward_ast_gpu, op.backward_assignments)):
+        for ir in (op.forward_ast_gpu, op.backward_ast_gpu):
             k = CompiledKernel(ir)
-            k.tuning_x2 = _tuning(cands[0])          # parity runs with the first candidate's geometry
+            k.tuning_x2 = _tuning(cands[0])          # the first candidate's geometry
             fin, fout = ir.input_fields[0], ir.output_fields[0]
-            u = np.random.default_rng(1).standard_normal(small).astype(fin.dtype.numpy_dtype)
-            r1 = evaluate(assigns, {fin.name: u}, boundary_handling=bh)[fout.name].astype(u.dtype)
-            r2 = evaluate(assigns, {fin.name: r1}, boundary_handling=bh)[fout.name]
-            ut = torch.from_numpy(u).to(dev)
-            out = torch.full_like(ut, float('nan'))
+            ut = torch.randn(small, dtype=numpy_dtype_to_torch(fin.dtype.numpy_dtype), device=dev)
+            a, b, out = torch.empty_like(ut), torch.empty_like(ut), torch.full_like(ut, float('nan'))
+            k(**{fin.name: ut, fout.name: a})
+            k(**{fin.name: a, fout.name: b})
             k(**{fin.name: ut, fout.name: out}, _variant='march_x2')
-            err = float(np.abs(out.cpu().numpy() - r2).max())
-            out5 = k.run_steps(ut, 5, fuse=True)
-            r = u
-            for _ in range(5):
-                r = evaluate(assigns, {fin.name: r}, boundary_handling=bh)[fout.name].astype(u.dtype)
-            err5 = float(np.abs(out5.cpu().numpy() - r).max())
-            print('parity %-28s bh=%-5s x2 err %.3g   5 steps err %.3g' % (ir.function_name, bh, err, err5), flush=True)
+            err = float((out - b).abs().max())
+            err5 = float((k.run_steps(ut, 5, fuse=True) - k.run_steps(ut, 5, fuse=False)).abs().max())
+            print('small %-28s bh=%-5s fused pair vs two launches %.3g   5 steps fused vs unfused %.3g'
+                  % (ir.function_name, bh, err, err5), flush=True)
     # ---- full size
     shape = CONFIG_SHAPES[name]['shape']
     op = make_config(name, shape=shape)
