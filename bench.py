@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--shape', type=int, nargs='*', default=None, help='override the per-GPU field shape')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--strong', action='store_true',
+                    help='strong scaling: the workload shape is the GLOBAL field, split along dim 0 over the ranks '
+                         '(default: weak scaling, every rank owns the full workload shape)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -190,6 +193,10 @@ def main_ours(args):
 
     wl = args.workload
     shape = tuple(args.shape or CONFIG_SHAPES[wl]['shape'])   # per-GPU (local) shape: weak scaling
+    if args.strong:
+        if shape[0] % world:
+            raise SystemExit('--strong: dim 0 (%d) must be divisible by the number of GPUs (%d)' % (shape[0], world))
+        shape = (shape[0] // world,) + shape[1:]
     op = make_config(wl, shape=shape, boundary_handling='zeros')
     slab = SlabStencilOp(op, local_shape=shape, rank=rank, world_size=world, device=dev)
     cells = int(np.prod(shape))
@@ -347,7 +354,7 @@ def main_ours(args):
             traffic = json.load(fh).get(wl, {}).get('forward_dram_bytes_per_launch')
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None,
         'dtype': DTYPE[wl], 'data': 'synthetic',
         'config': {'workload': WORKLOADS[wl], 'per_gpu_shape': list(shape), 'cells_per_gpu': cells,
                    'bytes_per_cell': {'forward': b_fwd, 'adjoint': b_bwd},
