@@ -16,6 +16,7 @@ from pystencils_autodiff_b200 import runtime
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIM = os.path.join(_HERE, 'cpu_shim')
+_SHIM_FULL = os.path.join(_HERE, 'cpu_shim_full')
 _BUILD = os.path.join(_HERE, '..', 'oracle', '_build')
 
 
@@ -24,26 +25,40 @@ class _EmuField(ctypes.Structure):
                 ('boxw', ctypes.c_int), ('boxh', ctypes.c_int)]
 
 
-def _compile(emitted):
+class _EmuFieldFull(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('stride', ctypes.c_longlong * 3), ('shape', ctypes.c_longlong * 3),
+                ('esize', ctypes.c_int), ('boxw', ctypes.c_int), ('boxh', ctypes.c_int)]
+
+
+def _compile(emitted, full=False):
     os.makedirs(_BUILD, exist_ok=True)
+    shim = _SHIM_FULL if full else _SHIM
     h = hashlib.md5(emitted.source.encode())
-    for fn in sorted(os.listdir(_SHIM)) + ['psad_item.cuh', 'psad_args.h']:
-        path = os.path.join(_SHIM, fn) if os.path.exists(os.path.join(_SHIM, fn)) else os.path.join(runtime.KERNEL_DIR, fn)
+    for fn in sorted(os.listdir(shim)) + ['psad_item.cuh', 'psad_args.h'] + (['psad_march.cuh'] if full else []):
+        path = os.path.join(shim, fn) if os.path.exists(os.path.join(shim, fn)) else os.path.join(runtime.KERNEL_DIR, fn)
         with open(path, 'rb') as fh:
             h.update(fh.read())
-    base = os.path.join(_BUILD, 'emu_%s_%s' % (emitted.name[:32], h.hexdigest()[:12]))
+    base = os.path.join(_BUILD, 'emu%s_%s_%s' % ('full' if full else '', emitted.name[:32], h.hexdigest()[:12]))
     if not os.path.exists(base + '.so'):
         with open(base + '.cpp', 'w') as fh:
             fh.write(emitted.source)
+            if full:   # the real psad_march.cuh was included by the source; add the emulated machine + launch loop
+                with open(os.path.join(_SHIM_FULL, 'driver.inc')) as inc:
+                    fh.write('\n' + inc.read())
         # -ffp-contract=off mirrors -fmad=false; fma()/fmaf() map to the hardware FMA like on the GPU
-        subprocess.check_call(['g++', '-std=c++20', '-O1', '-ffp-contract=off', '-mfma', '-fPIC', '-shared', '-pthread', '-w',
-                               '-I', _SHIM, '-I', runtime.KERNEL_DIR, '-o', base + '.so.tmp', base + '.cpp'])
+        subprocess.check_call(['g++', '-std=c++20', '-O1', '-ffp-contract=off', '-mfma', '-fPIC', '-shared', '-pthread', '-w', '-Wno-psabi',
+                               '-I', shim, '-I', runtime.KERNEL_DIR, '-o', base + '.so.tmp', base + '.cpp'])
         os.replace(base + '.so.tmp', base + '.so')
     return ctypes.CDLL(base + '.so')
 
 
-def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=None):
-    """``arrays``: numpy arrays in the plan's field order (outputs first; written in place)."""
+def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=None, full=False):
+    """``arrays``: numpy arrays in the plan's field order (outputs first; written in place).
+
+    ``full=False``: the per-step bodies under a host copy of the consumer loop (``cpu_shim/``, warps one after the other
+    or — exchange kernels — concurrently).  ``full=True``: the REAL ``psad_march.cuh`` (producer warp, TMA ring, full /
+    empty mbarriers) with emulated mbarriers and TMA, every thread of the CTA an OS thread (``cpu_shim_full/``); returns
+    ``(ctas, mbarrier waits, TMA loads)``."""
     L = runtime.lib()
     plan = runtime.make_plan(emitted.plan)
     n = len(arrays)
@@ -70,7 +85,7 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
     if grid[0] == 0:
         return 0
     tma = [(i, f) for i, f in enumerate(emitted.plan['fields']) if f['tma']]
-    tf = (_EmuField * len(tma))()
+    tf = ((_EmuFieldFull if full else _EmuField) * len(tma))()
     nd = arrays[0].ndim
     for k, (i, f) in enumerate(tma):
         a = arrays[i]
@@ -79,6 +94,16 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
         tf[k].stride[:] = st
         tf[k].esize = a.itemsize
         tf[k].boxw, tf[k].boxh = f['box'][0], f['box'][1]
+        if full:
+            tf[k].shape[:] = [1] * (3 - nd) + list(a.shape)
+    if full:
+        so = _compile(emitted, full=True)
+        so.psad_emulate_full.argtypes = [ctypes.c_void_p, ctypes.POINTER(_EmuFieldFull), ctypes.c_int, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_longlong)]
+        stats = (ctypes.c_longlong * 2)()
+        rc = so.psad_emulate_full(args, tf, len(tma), int(grid[0]), stats)
+        assert rc == 0, 'psad_emulate_full failed'
+        return int(grid[0]), int(stats[0]), int(stats[1])
     so = _compile(emitted)
     so.psad_emulate.argtypes = [ctypes.c_void_p, ctypes.POINTER(_EmuField), ctypes.c_int, ctypes.c_int]
     rc = so.psad_emulate(args, tf, len(tma), int(grid[0]))

@@ -264,3 +264,35 @@ def test_fused_forward_adjoint_kernel_replay():
     np.testing.assert_allclose(named['z'], fwd['z'], rtol=2e-6, atol=1e-6)
     np.testing.assert_allclose(named['diffx'], bwd['diffx'], rtol=2e-6, atol=2e-6)
     np.testing.assert_allclose(named['diffy'], bwd['diffy'], rtol=2e-6, atol=2e-6)
+
+
+# ---- the real march template (producer warp, TMA ring, full / empty mbarriers) on the CPU --------------------------------
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('make, shape, bh, tuning, chain, tol', [
+    (configs.heat3d_op, (9, 12, 132), 'zeros', MarchTuning(ry=2, ty=6), False, 3e-7),            # register window, 5-slot ring
+    (configs.heat3d_op, (7, 10, 132), None, MarchTuning(ry=1, ty=3, lookahead=1), False, 3e-7),  # shortest ring, masks
+    (configs.stencil27_op, (6, 9, 68), 'zeros', MarchTuning(ry=3, ty=6, sx=4), False, 1e-14),     # arrival-time plane sums
+    (configs.diffusion2d_op, (23, 132), 'zeros', MarchTuning(ry=1, ty=4), False, 3e-7),          # 2-D: row tiles
+    (configs.heat3d_op, (6, 14, 124), 'zeros', MarchTuning(exchange=True, ry=2, ty=6), True, 4e-7),     # fused pair, rows exchanged
+    (configs.stencil27_op, (5, 9, 60), None, MarchTuning(exchange=False, ry=2, ty=4, sx=2), True, 1e-14),  # fused pair, recomputed
+    (configs.heat3d_op, (6, 40, 132), 'zeros', None, False, 3e-7),       # the shipped C3 geometry: 16+1 warps
+    (configs.heat3d_op, (6, 50, 124), 'zeros', None, True, 4e-7),        # the shipped fused-pair geometry: 11+1 warps
+    (configs.stencil27_op, (5, 25, 132), 'zeros', None, False, 1e-14),   # the shipped C4 geometry: 7+1 warps
+])
+def test_full_pipeline_replay(make, shape, bh, tuning, chain, tol):
+    """csrc/kernels/psad_march.cuh itself — item loop, producer lane, slot / parity bookkeeping, expect_tx / complete_tx,
+    slot release — with emulated mbarriers and TMA (tests/cpu_shim_full): several work items per CTA so that the ring
+    wraps and the barrier phases flip across item boundaries."""
+    op = make(shape=shape, boundary_handling=bh)
+    ir = op.forward_ast_gpu
+    ek = emit_march_chain(ir, tuning) if chain else emit_march(ir, tuning, masked=True)
+    arrays, named = _fields(ek, ir, shape, seed=12)
+    ctas, waits, loads = emu.run(ek, arrays, full=True, sm_count=2)
+    fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
+    ref = named[fin].copy()
+    for _ in range(2 if chain else 1):
+        ref = evaluate(op.forward_assignments, {fin: ref}, boundary_handling=bh)[fout].astype(ref.dtype)
+    assert not np.isnan(named[fout]).any()
+    np.testing.assert_allclose(named[fout], ref, rtol=0, atol=tol)
+    # every staged plane was requested exactly once: items x planes per item (3-D: chunk + warm-up planes)
+    assert ctas == 2 and loads > 2 * ek.geometry['STAGES'] and waits > loads
