@@ -74,8 +74,6 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     if reason:
         raise ValueError('fused-step march variant not applicable: ' + reason)
     t = tuning or MarchTuning()
-    _e = (ir.input_fields[0].dtype.itemsize == 4) if t.exchange is None else bool(t.exchange)
-    name = _kernel_name(ir, 'march_x2e' if (_e and sum(ir.halo(ir.input_fields[0].name)[0]) > 0) else 'march_x2')
     CT = _CT[ir.compute_dtype]
     pr = _CudaPrinter(ir.compute_dtype)
     fin, fout = ir.input_fields[0], ir.output_fields[0]
@@ -123,7 +121,8 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     # Intermediate rows owned by the neighbouring warps: recomputed by every thread (input box with two y radii), or —
     # `exchange` — written to a shared buffer by their owners and read back after one consumer barrier (input box with
     # one y radius; the tile's outermost rows have no owner, so tiles then overlap along y as well)
-    exchange = want_exchange and D1 > 0
+    exchange = want_exchange and D1 > 0 and HYL + HYH > 0      # needs >= 2 window phases; pointless without a y halo
+    name = _kernel_name(ir, 'march_x2e' if exchange else 'march_x2')
     U_L, U_H = (HYL, HYH) if exchange else (2 * HYL, 2 * HYH)      # input rows above / below the thread's own rows
     TYS = TY - HYL - HYH if exchange else TY
     YORG = -HYL if exchange else 0

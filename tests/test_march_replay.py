@@ -296,3 +296,25 @@ def test_full_pipeline_replay(make, shape, bh, tuning, chain, tol):
     np.testing.assert_allclose(named[fout], ref, rtol=0, atol=tol)
     # every staged plane was requested exactly once: items x planes per item (3-D: chunk + warm-up planes)
     assert ctas == 2 and loads > 2 * ek.geometry['STAGES'] and waits > loads
+
+
+@pytest.mark.parametrize('case', ['z-only', 'yx-only', 'radius-2-x', 'pointwise'])
+def test_fused_steps_degenerate_halos_replay(case):
+    """Stencils without a z, y or x halo (one window phase, no rows to exchange, no columns to overlap) and a radius-2
+    stencil (two radii exactly fill a strip) through the fused-pair emitter."""
+    import pystencils_autodiff_b200 as ps
+    shape = (5, 9, 60)
+    u, out = ps.fields('u, out: float32[5,9,60]')
+    rhs = {'z-only': 0.5 * u[0, 0, 0] + 0.25 * u[1, 0, 0] + 0.125 * u[-1, 0, 0],
+           'yx-only': 0.6 * u[0, 0, 0] + 0.1 * (u[0, 1, 0] + u[0, -1, 0] + u[0, 0, 1] + u[0, 0, -1]),
+           'radius-2-x': 0.5 * u[0, 0, 0] + 0.25 * u[0, 0, 2] + 0.25 * u[0, 0, -2],
+           'pointwise': 0.5 * u[0, 0, 0] * u[0, 0, 0] + 0.1}[case]
+    for bh in ('zeros', None):
+        op = ps.AutoDiffOp(ps.AssignmentCollection([ps.Assignment(out.center, rhs)]), op_name='deg', boundary_handling=bh)
+        ir = op.forward_ast_gpu
+        ek = emit_march_chain(ir)
+        assert ek.geometry['exchange'] == (case == 'never')       # no y halo or no z coupling: nothing to exchange
+        arrays, named = _fields(ek, ir, shape, seed=6)
+        emu.run(ek, arrays, full=(bh is None))
+        ref = _twice(op.forward_assignments, 'u', 'out', named['u'].copy(), bh)
+        np.testing.assert_allclose(named['out'], ref, rtol=1e-6, atol=1e-6)
