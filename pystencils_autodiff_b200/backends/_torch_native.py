@@ -23,7 +23,7 @@ import numpy as np
 
 from ..emit import emit_generic, emit_march, march_ineligible_reason
 from ..emit_chain import chain_ineligible_reason, emit_march_chain
-from ..ir import StencilKernelIR, split_index_components
+from ..ir import StencilKernelIR, lift_to_3d, split_index_components
 from .. import runtime
 
 __all__ = ['create_autograd_function', 'create_unrolled_function', 'compile_kernel', 'CompiledKernel',
@@ -75,8 +75,14 @@ class CompiledKernel:
             reason = self.fused_steps_reason()
             if reason:
                 raise ValueError('%s: two fused steps per launch are not available: %s' % (self.function_name, reason))
-            self._emitted[variant] = emit_march_chain(self.ir, self.tuning_x2)
+            self._emitted[variant] = emit_march_chain(self._chain_ir(), self.tuning_x2)
         return self._emitted[variant]
+
+    def _chain_ir(self):
+        """The kernel the fused-step emitter sees: 2-D 'zeros' kernels are lifted to 3-D fields of one plane."""
+        if self.ir.ndim == 2 and self.ir.boundary == 'zeros' and not self._components:
+            return lift_to_3d(self.ir)
+        return self.ir
 
     tuning_x2 = None   # MarchTuning of the fused-step kernel (None = emit_chain defaults)
 
@@ -84,7 +90,7 @@ class CompiledKernel:
         """None when ``out = S(S(u))`` can run as one launch (emit_chain.py), else why not."""
         if self._components:
             return 'index dimensions'
-        return self._march_reason or chain_ineligible_reason(self.ir)
+        return self._march_reason or chain_ineligible_reason(self._chain_ir())
 
     def run_steps(self, src, steps, out=None, fuse=None, **scalars):
         """``S^steps(src)``: the stencil applied ``steps`` times, ping-ponging between ``out`` and one scratch tensor;
@@ -102,7 +108,9 @@ class CompiledKernel:
         if fuse and not can_pair:
             raise ValueError('%s: steps cannot be fused: %s' % (self.function_name, self.fused_steps_reason() or
                                                                 'tensor layout needs the generic kernel'))
-        pair = can_pair and (src.element_size() == 4 if fuse is None else bool(fuse))
+        # measured wins only: 3-D fields of 4-byte elements (2-D pairs work — lifted to one-plane 3-D fields — but have
+        # not been timed yet, so they need an explicit fuse=True)
+        pair = can_pair and ((src.element_size() == 4 and self.ir.ndim == 3) if fuse is None else bool(fuse))
         launches = [2] * (steps // 2) + [1] * (steps % 2) if pair else [1] * steps
         out = torch.empty_like(src) if out is None else out
         if out.data_ptr() == src.data_ptr():
@@ -206,7 +214,11 @@ class CompiledKernel:
             if same:
                 variant = 'march_nomask'
         field_args = []
-        if variant.startswith('march') and self._components:
+        if variant == 'march_x2' and nd == 2:
+            # lifted kernel (lift_to_3d): the 2-D tensors are passed as one-plane 3-D fields
+            for t in tensors:
+                field_args.append((t.data_ptr(), (1,) + tuple(t.shape), [t.shape[0] * t.stride(0)] + list(t.stride()) + [0]))
+        elif variant.startswith('march') and self._components:
             by_name = {f.name: t for f, t in zip(self.fields, tensors)}
             for cf in self._emitted['march'].fields:          # component fields, plan order of the scalar kernel
                 name, i = self._components.get(cf.name, (cf.name, None))

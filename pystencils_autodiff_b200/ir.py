@@ -252,3 +252,35 @@ def split_index_components(ir: StencilKernelIR):
                                   ir.function_name, ghost_layers=ir.ghost_layers if ir.boundary != 'zeros' else None,
                                   data_type=ir.compute_dtype, fast_math=ir.fast_math)
     return scalar_ir, components
+
+
+def lift_to_3d(ir: StencilKernelIR):
+    """A 2-D kernel as a 3-D kernel over fields with a leading extent-1 dimension (offset 0 along it): the tensor
+    ``t[Y, X]`` is passed as ``t[None]``.  Lets 2-D stencils use machinery that exists for the 3-D march only (the
+    fused-step kernels).  Only for ``'zeros'`` boundary handling: an inferred ghost width would also apply to the new
+    dimension and leave nothing to iterate."""
+    if ir.ndim != 2:
+        raise ValueError('lift_to_3d expects a 2-D kernel')
+    if ir.boundary != 'zeros':
+        raise ValueError("lift_to_3d needs boundary_handling='zeros'")
+    if any(f.index_dimensions for f in ir.all_fields):
+        raise ValueError('lift_to_3d expects scalar fields')
+    cache = {}
+
+    def lifted(f):
+        if f.name not in cache:
+            cache[f.name] = Field.create_fixed_size(f.name, (1,) + tuple(f.spatial_shape), 0, f.dtype.numpy_dtype) \
+                if f.has_fixed_shape else Field.create_generic(f.name, 3, f.dtype.numpy_dtype)
+        return cache[f.name]
+
+    def conv(a):
+        return Field.Access(lifted(a.field), (0,) + tuple(a.offsets))
+
+    accesses = set()
+    for _, r in ir.subexpressions + ir.main:
+        accesses |= r.atoms(Field.Access)
+    repl = {a: conv(a) for a in accesses}
+    sub = {l: r.xreplace(repl) for l, r in ir.subexpressions}
+    main = {conv(l): r.xreplace(repl) for l, r in ir.main}
+    return lower_assignments(AssignmentCollection(main, sub), 'zeros', ir.function_name, data_type=ir.compute_dtype,
+                             fast_math=ir.fast_math)

@@ -318,3 +318,25 @@ def test_fused_steps_degenerate_halos_replay(case):
         emu.run(ek, arrays, full=(bh is None))
         ref = _twice(op.forward_assignments, 'u', 'out', named['u'].copy(), bh)
         np.testing.assert_allclose(named['out'], ref, rtol=1e-6, atol=1e-6)
+
+
+def test_fused_steps_two_dimensional_lifted_replay():
+    """2-D 'zeros' stencils reach the fused-pair emitter as 3-D fields of one plane (ir.lift_to_3d)."""
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    shape = (45, 124)
+    op = configs.diffusion2d_op(shape=shape)
+    for ir, assigns in ((op.forward_ast_gpu, op.forward_assignments), (op.backward_ast_gpu, op.backward_assignments)):
+        k = CompiledKernel(ir)
+        assert k.fused_steps_reason() is None
+        ek = k.emitted('march_x2')
+        assert ek.plan['ndim'] == 3 and ek.plan['fused_steps'] == 2
+        fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
+        u = emu.aligned_empty((1,) + shape, np.float32)
+        u[...] = np.random.default_rng(3).standard_normal((1,) + shape)
+        out = emu.aligned_empty((1,) + shape, np.float32, np.nan)
+        arrays = [out if f.name == fout else u for f in ek.fields]
+        emu.run(ek, arrays, full=True)
+        ref = _twice(assigns, fin, fout, u[0].copy(), 'zeros')
+        np.testing.assert_allclose(out[0], ref, rtol=0, atol=4e-7)
+    # interior iteration (boundary None) would also strip the new dimension: not offered
+    assert CompiledKernel(configs.diffusion2d_op(shape=shape, boundary_handling=None).forward_ast_gpu).fused_steps_reason()
