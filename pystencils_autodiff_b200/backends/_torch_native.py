@@ -196,8 +196,8 @@ class CompiledKernel:
         variant = _variant or self._select_variant(tensors)
         if variant == 'march_x2':
             self.emitted(variant)
-            if _range is not None:
-                raise ValueError('%s: fused steps run on whole arrays only' % self.function_name)
+            if _range is not None and nd != 3:
+                raise ValueError('%s: fused steps of 2-D kernels run on whole arrays only' % self.function_name)
             if self._select_variant(tensors) != 'march':
                 raise ValueError('%s: fused steps need dense, 16-byte aligned rows' % self.function_name)
             if tensors[0].data_ptr() == tensors[1].data_ptr():

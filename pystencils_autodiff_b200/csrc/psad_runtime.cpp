@@ -122,11 +122,17 @@ static int cu_fail(CUresult r, const char* what) {
 }
 #define CU_CHECK(call) do { CUresult _r = (call); if (_r != 0) return cu_fail(_r, #call); } while (0)
 
-// make sure the calling thread has a current context (torch's primary context when called from PyTorch)
-static int ensure_context() {
+// make sure the calling thread has a current context (torch's primary context when called from PyTorch).  A thread
+// without one (an autograd worker that has not touched the runtime API yet) gets `preferred` — the context a kernel
+// was loaded in — or, with no preference, the primary context of device 0.
+static int ensure_context(CUcontext preferred = nullptr) {
   CUcontext ctx = nullptr;
   CU_CHECK(g_drv.cuCtxGetCurrent(&ctx));
   if (ctx) return 0;
+  if (preferred) {
+    CU_CHECK(g_drv.cuCtxSetCurrent(preferred));
+    return 0;
+  }
   CUdevice dev;
   CU_CHECK(g_drv.cuDeviceGet(&dev, 0));
   CU_CHECK(g_drv.cuDevicePrimaryCtxRetain(&ctx, dev));
@@ -222,6 +228,7 @@ static bool read_file(const std::string& path, std::vector<char>& out) {
   if (!f) return false;
   fseek(f, 0, SEEK_END);
   long n = ftell(f);
+  if (n < 0) { fclose(f); return false; }
   fseek(f, 0, SEEK_SET);
   out.resize((size_t)n);
   size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
@@ -280,9 +287,15 @@ static int compile_to_cache(const char* source, const char* cache_key, const cha
   const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
   FILE* f = fopen(tmp.c_str(), "wb");
   if (!f) return fail(PSAD_ERR_IO, "cannot write %s", tmp.c_str());
-  fwrite(cubin.data(), 1, n, f);
-  fclose(f);
-  if (rename(tmp.c_str(), path.c_str()) != 0) return fail(PSAD_ERR_IO, "cannot rename %s", tmp.c_str());
+  const size_t written = fwrite(cubin.data(), 1, n, f);
+  if (fclose(f) != 0 || written != n) {
+    unlink(tmp.c_str());
+    return fail(PSAD_ERR_IO, "short write to %s (disk full?)", tmp.c_str());
+  }
+  if (rename(tmp.c_str(), path.c_str()) != 0) {
+    unlink(tmp.c_str());
+    return fail(PSAD_ERR_IO, "cannot rename %s", tmp.c_str());
+  }
   // keep the specialised source beside the cubin (the reference keeps its generated .cu too)
   FILE* s = fopen((cache + "/" + cache_key + ".cu").c_str(), "w");
   if (s) { fputs(source, s); fclose(s); }
@@ -300,6 +313,7 @@ struct psad_kernel {
   psad_plan_t plan;
   CUmodule module = nullptr;
   CUfunction fn = nullptr;
+  CUcontext ctx = nullptr;  // the context the module was loaded in
   int sm_count = 0;
   int occupancy = 1;  // resident CTAs per SM for this kernel (march: persistent grid = sm_count * occupancy)
   std::string name;
@@ -322,6 +336,7 @@ extern "C" int psad_kernel_create(const char* source, const char* kernel_name, c
   psad_kernel* k = new psad_kernel();
   k->plan = *plan;
   k->name = kernel_name;
+  g_drv.cuCtxGetCurrent(&k->ctx);
   CUresult r = g_drv.cuModuleLoadData(&k->module, cubin.data());
   if (r != 0) { delete k; return cu_fail(r, "cuModuleLoadData"); }
   r = g_drv.cuModuleGetFunction(&k->fn, k->module, kernel_name);
@@ -431,8 +446,9 @@ static int build_args(const psad_plan_t& P, const char* kname, int sm_count, int
     if (nd < 2) return fail(PSAD_ERR_INVALID, "march kernels need 2 or 3 spatial dims");
     if (A.wr_lo[2] != 0 || A.wr_hi[2] != A.shape[2] || A.wr_lo[1] < 0)
       return fail(PSAD_ERR_INVALID, "march kernels write full rows: the x range must be the whole axis");
-    if (P.reserved[1] > 1 && range)
-      return fail(PSAD_ERR_INVALID, "%s: kernels fusing %d steps run on whole arrays only (no launch range)", kname, P.reserved[1]);
+    // Kernels fusing several steps take launch ranges too: the iteration range bounds every intermediate field (0
+    // outside it, what the next single-step launch would have read there), the write range the stored planes.  A
+    // slab needs s * g valid ghost planes around the written planes for s fused steps (datahandling.slab_ranges).
     A.tiles_x = (int)cdiv(A.shape[2], P.tile_x);
     A.tiles_y = (int)cdiv(A.shape[1], P.tile_y);
     long long span = (nd == 3) ? (A.wr_hi[0] - A.wr_lo[0]) : A.tiles_y;
@@ -499,7 +515,7 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   int empty = 0;
   if (int rc = build_args(P, k->name.c_str(), k->sm_count, k->occupancy, fields, n_fields, scalars, n_scalars, range, A, grid, &empty)) return rc;
   if (empty) return 0;
-  if (int rc = ensure_context()) return rc;
+  if (int rc = ensure_context(k->ctx)) return rc;
   const int nd = P.ndim;
   void* params[2];
   params[0] = &A;

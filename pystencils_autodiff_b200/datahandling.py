@@ -63,29 +63,54 @@ class SlabDecomposition:
     def owned(self):
         return slice(self.g, self.g + self.n_local)
 
-    def ranges(self, boundary, ghost_width_of_kernel, ndim):
+    def ranges(self, boundary, ghost_width_of_kernel, ndim, steps=1, halo=None):
         """(interior, lo, hi) launch ranges in local coordinates (``psad_range_t`` dicts); lo/hi may be None.
 
-        ``boundary``: 'zeros' | 'none'; ``ghost_width_of_kernel``: iteration margin of the kernel in 'none' mode."""
+        ``boundary``: 'zeros' | 'none'; ``ghost_width_of_kernel``: iteration margin of the kernel in 'none' mode;
+        ``steps`` > 1: ranges of a kernel that applies the stencil ``steps`` times per launch (``halo``: its reach along
+        dim 0 per step)."""
         return slab_ranges(self.global_shape, self.start, self.n_local, self.g, self.lo_rank >= 0, self.hi_rank >= 0,
-                           boundary, ghost_width_of_kernel, ndim)
+                           boundary, ghost_width_of_kernel, ndim, steps, halo)
 
 
-def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndim):
+def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndim, steps=1, halo=None):
     """Launch ranges for the slab owning global planes ``[start, start+n)``, stored with ``g`` ghost planes.
 
-    Returns ``(interior, lo, hi)``: the planes that do not depend on the ghost planes of a neighbour, and the ``g``
-    planes next to each existing neighbour (None where there is none).  Cells inside ``[iter_lo, iter_hi)`` are
-    evaluated, the other cells of ``[write_lo, write_hi)`` are set to 0 (``boundary='none'``: the global border)."""
+    Returns ``(interior, lo, hi)``: the planes that do not depend on the ghost planes of a neighbour, and the planes
+    next to each existing neighbour that do (None where there is none).  Cells inside ``[iter_lo, iter_hi)`` are
+    evaluated, the other cells of ``[write_lo, write_hi)`` are set to 0 (``boundary='none'``: the global border).
+
+    ``steps`` > 1 (kernels fusing several applications of a stencil that reaches ``halo`` planes along dim 0,
+    emit_chain.py): a written plane depends on ``steps * halo`` planes on each side, so that many ghost planes must be
+    stored (and exchanged once per launch instead of ``halo`` planes once per step), and that many planes next to a
+    neighbour wait for the exchange.  The iteration range is then the part of the GLOBAL iteration space inside the local
+    array — it also bounds the intermediate fields, which are needed (and valid) on ghost planes too."""
     shape = (n + 2 * g,) + tuple(global_shape[1:ndim])
     full_lo = [0] * ndim
     full_hi = list(shape)
     it_lo, it_hi = list(full_lo), list(full_hi)
+    fused = steps > 1
+    if fused:
+        if halo is None or halo < 0:
+            raise ValueError('fused steps: the reach of the stencil along dim 0 (halo) is required')
+        if (has_lo or has_hi) and g < steps * halo:
+            raise ValueError('%d fused steps of a stencil reaching %d plane(s) need %d ghost planes, the slab stores %d'
+                             % (steps, halo, steps * halo, g))
+        if n < 2 * steps * halo and has_lo and has_hi:
+            raise ValueError('slab of %d planes is too thin for %d fused steps' % (n, steps))
     if boundary == 'none' and margin > 0:
         for d in range(1, ndim):
             it_lo[d], it_hi[d] = margin, shape[d] - margin
-        glo = max(margin, start) - start + g
-        ghi = min(global_shape[0] - margin, start + n) - start + g
+        dom_lo, dom_hi = margin, global_shape[0] - margin
+    else:
+        dom_lo, dom_hi = 0, global_shape[0]
+    if fused:
+        # global plane p lives at local index p - start + g
+        it_lo[0] = max(dom_lo, start - g) - start + g
+        it_hi[0] = max(it_lo[0], min(dom_hi, start + n + g) - start + g)
+    elif boundary == 'none' and margin > 0:
+        glo = max(dom_lo, start) - start + g
+        ghi = min(dom_hi, start + n) - start + g
         it_lo[0], it_hi[0] = glo, max(glo, ghi)
     else:
         it_lo[0], it_hi[0] = g, g + n
@@ -93,12 +118,15 @@ def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndi
     def rng(z0, z1):
         if z1 <= z0:
             return None
+        if fused:
+            return dict(iter_lo=list(it_lo), iter_hi=list(it_hi), write_lo=[z0] + full_lo[1:], write_hi=[z1] + full_hi[1:])
         lo = max(it_lo[0], z0)
         return dict(iter_lo=[lo] + it_lo[1:], iter_hi=[max(lo, min(it_hi[0], z1))] + it_hi[1:],
                     write_lo=[z0] + full_lo[1:], write_hi=[z1] + full_hi[1:])
 
-    lo_w = g if has_lo else 0
-    hi_w = g if has_hi else 0
+    w = steps * halo if fused else g
+    lo_w = min(w, n) if has_lo else 0
+    hi_w = min(w, n - lo_w) if has_hi else 0
     if lo_w == 0 and hi_w == 0:
         return rng(g, g + n), None, None
     return rng(g + lo_w, g + n - hi_w), (rng(g, g + lo_w) if lo_w else None), (rng(g + n - hi_w, g + n) if hi_w else None)
@@ -314,21 +342,39 @@ class SlabDataHandling:
         return TimeLoop(self, use_cuda_graph)
 
     # -- kernels ---------------------------------------------------------------------------------------------------
-    def run_kernel(self, kernel, halo_fields=(), **kwargs):
+    def run_kernel(self, kernel, halo_fields=(), fused_steps=1, **kwargs):
         """``kernel(**arrays, **kwargs)`` on the owned planes.  ``halo_fields``: inputs whose ghost planes must be
         fresh.  Their exchange runs on the communication stream while the interior planes are computed on the
         current stream; the ``g`` boundary planes on each side are launched on the communication stream right behind
         the exchange, so they overlap with (and fill the tail of) the interior launch instead of serialising after it.
-        The current stream then waits for that stream — a device-side dependency, no host synchronisation."""
+        The current stream then waits for that stream — a device-side dependency, no host synchronisation.
+
+        ``fused_steps=2``: the kernel's two-steps-per-launch instance (emit_chain.py) — ``out = S(S(u))`` from ONE
+        exchange of ``2 * halo`` ghost planes instead of two exchanges of ``halo`` planes; the data handling must store
+        that many ghost layers."""
         if not isinstance(kernel, CompiledKernel):
             raise TypeError('run_kernel expects a CompiledKernel (AutoDiffOp.forward_kernel_gpu / backward_kernel_gpu)')
-        self.call_queue.append(('KernelCall', kernel.function_name))
+        if fused_steps not in (1, 2):
+            raise ValueError('fused_steps must be 1 or 2')
+        self.call_queue.append(('KernelCall', kernel.function_name) if fused_steps == 1 else
+                               ('KernelCall', kernel.function_name, fused_steps))
         arrays = {f.name: self.gpu_arrays[f.name] for f in kernel.fields}
         ir = kernel.ir
-        key = id(kernel)
+        key = (id(kernel), fused_steps)
         if key not in self._range_cache:
-            self._range_cache[key] = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
+            if fused_steps > 1:
+                reason = kernel.fused_steps_reason()
+                if reason:
+                    raise ValueError('%s: steps cannot be fused: %s' % (kernel.function_name, reason))
+                if ir.ndim != 3:
+                    raise ValueError('%s: fused steps on slabs need 3-D fields' % kernel.function_name)
+                halo = max(ir.halo(ir.input_fields[0].name)[0])
+                self._range_cache[key] = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim, fused_steps, halo)
+            else:
+                self._range_cache[key] = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
         interior, lo, hi = self._range_cache[key]
+        if fused_steps > 1:
+            kwargs = dict(kwargs, _variant='march_x2')
         for n in halo_fields:
             self.call_queue.append(('Communication', n, None, True))
             self.start_exchange(n)
@@ -346,6 +392,30 @@ class SlabDataHandling:
                 kernel(**arrays, **kwargs, _range=r)
         elif side or halo_fields:
             self.finish_exchange()
+
+    def run_steps(self, kernel, steps, fuse=None, **scalars):
+        """``steps`` applications of a one-input / one-output stencil kernel as the reference's time loop runs them
+        (graph_datahandling.py:152-194: kernel call, ghost-layer synchronisation, ``swap``): after every launch the
+        input and output arrays are swapped, so the array registered under the INPUT field's name holds the current
+        state when this returns and the one under the output field's name is scratch.
+
+        ``fuse=True``: pairs of steps run as one launch with one exchange of ``2 * halo`` ghost planes
+        (``run_kernel(..., fused_steps=2)``): per pair the field is read and written once instead of twice and one
+        message per neighbour replaces two.  Needs ``default_ghost_layers >= 2 * halo``.  Default: single steps (the
+        slab form of the fused kernel is replayed on the CPU and bit-identical to the unsharded fused launch, but has not
+        been timed on a GPU yet)."""
+        ir = kernel.ir
+        if len(ir.input_fields) != 1 or len(ir.output_fields) != 1:
+            raise ValueError('%s: run_steps needs a kernel with one input and one output field' % kernel.function_name)
+        if steps < 0:
+            raise ValueError('steps must be >= 0')
+        fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
+        halo = [fin] if self.dec.world_size > 1 and self.dec.g > 0 and max(ir.halo(fin)[0]) > 0 else []
+        launches = [2] * (steps // 2) + [1] * (steps % 2) if fuse else [1] * steps
+        for n in launches:
+            self.run_kernel(kernel, halo_fields=halo, fused_steps=n, **scalars)
+            self.swap(fin, fout)
+        return self.gpu_arrays[fin]
 
 
 class TimeLoop:

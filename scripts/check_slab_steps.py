@@ -1,0 +1,62 @@
+"""Time loop on slabs, fused pairs of steps with one two-plane halo exchange per pair == unsharded fused launches
+(run under torchrun, one rank per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
+        scripts/check_slab_steps.py [c3|c4] [zeros|none] [steps]
+Every rank also runs the whole (small) global field on its own GPU with ``CompiledKernel.run_steps(fuse=True)`` and
+compares its slab with the matching planes: bit for bit.  Single steps (``fuse=False``) are compared the same way.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+from pystencils_autodiff_b200.configs import make_config
+from pystencils_autodiff_b200.datahandling import SlabDataHandling
+
+SHAPES = {'c3': (24, 40, 256), 'c4': (16, 24, 128)}
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else 'c3'
+    bh = None if (len(sys.argv) > 2 and sys.argv[2] == 'none') else 'zeros'
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    dev = torch.device('cuda', int(os.environ['LOCAL_RANK']))
+    dist.init_process_group('nccl', device_id=dev)
+    local = SHAPES[name]
+    gshape = (local[0] * world,) + local[1:]
+    op_g = make_config(name, shape=gshape, boundary_handling=bh)
+    ir_g = op_g.forward_ast_gpu
+    halo = max(ir_g.halo(ir_g.input_fields[0].name)[0])
+    dtype = ir_g.input_fields[0].dtype.numpy_dtype
+    g = torch.Generator(device='cpu')
+    g.manual_seed(7)
+    glob = torch.randn(gshape, generator=g, dtype=torch.float64).to(getattr(torch, str(dtype))).to(dev)
+    sl = slice(rank * local[0], (rank + 1) * local[0])
+    kg = CompiledKernel(ir_g)
+    ok = True
+    for fuse in (False, True):
+        dh = SlabDataHandling(gshape, rank, world, 2 * halo, dev)
+        dh.add_arrays('u, out', dtype=dtype)
+        op_l = make_config(name, shape=dh.dec.local_shape, boundary_handling=bh)
+        kl = CompiledKernel(op_l.forward_ast_gpu)
+        dh.owned('u').copy_(glob[sl])
+        res = dh.run_steps(kl, steps, fuse=fuse)
+        ref = kg.run_steps(glob, steps, fuse=fuse)
+        torch.cuda.synchronize()
+        same = torch.equal(res[dh.dec.owned], ref[sl])
+        ok = ok and same
+        print('[rank %d] %s %s steps=%d fuse=%s: %s' % (rank, name, bh, steps, fuse, 'IDENTICAL' if same else
+              'DIFFERENT (max %.3e)' % float((res[dh.dec.owned] - ref[sl]).abs().max())), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()

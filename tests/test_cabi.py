@@ -122,13 +122,20 @@ def test_plan_launch_work_decomposition():
             # the busiest CTA's steps stay within 15 % of a perfectly balanced split (chunks amortise warm-up planes)
             steps = -(-n_items // (sms * ctas)) * (chunk + 2 * halo)
             assert steps <= 1.15 * (tiles_x * tiles_y * shape[0] / (sms * ctas)) + chunk + 2 * halo
-        # wrong field count, wrong block size and a launch range on a fused-step kernel are rejected with a message
+        # wrong field count and wrong block size are rejected with a message
         assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 1, None, 0, None, args, 752, grid) != 0
         assert b'expected 2 fields' in L.psad_last_error()
         assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, None, args, 100, grid) != 0
-        if ek.plan.get('fused_steps', 1) > 1:
-            rng = runtime.Range()
-            for d in range(3):
-                rng.iter_hi[d] = rng.write_hi[d] = shape[d]
-            assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, 752, grid) != 0
-            assert b'whole arrays only' in L.psad_last_error()
+        # launch ranges (slabs): the chunks cover the WRITTEN planes only — also for fused-step kernels — and a write
+        # range outside the array is rejected
+        rng = runtime.Range()
+        for d in range(3):
+            rng.iter_hi[d] = rng.write_hi[d] = shape[d]
+        rng.write_lo[0], rng.write_hi[0] = 2 * halo, 2 * halo + 40
+        rc = L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, 752, grid)
+        assert rc == 0, L.psad_last_error()
+        tiles_x, tiles_y, n_chunks, chunk = struct.unpack_from('4i', args.raw, 736)
+        assert chunk * n_chunks >= 40 > chunk * (n_chunks - 1)
+        rng.write_hi[0] = shape[0] + 1
+        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, 752, grid) != 0
+        assert b'outside the array extent' in L.psad_last_error()

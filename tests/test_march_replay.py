@@ -340,3 +340,58 @@ def test_fused_steps_two_dimensional_lifted_replay():
         np.testing.assert_allclose(out[0], ref, rtol=0, atol=4e-7)
     # interior iteration (boundary None) would also strip the new dimension: not offered
     assert CompiledKernel(configs.diffusion2d_op(shape=shape, boundary_handling=None).forward_ast_gpu).fused_steps_reason()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('make, bh, world, tuning, full, tol', [
+    (configs.heat3d_op, 'zeros', 2, None, False, 5e-7),                          # shipped fused geometry, rows exchanged
+    (configs.heat3d_op, None, 3, MarchTuning(exchange=False), False, 5e-7),      # rows recomputed, global interior clipped
+    (configs.stencil27_op, 'zeros', 2, MarchTuning(exchange=False, ry=2, ty=4, sx=2), True, 1e-14),   # real psad_march.cuh
+    (configs.heat3d_op, None, 2, MarchTuning(exchange=True, ry=2, ty=6), True, 5e-7),                  # real psad_march.cuh
+])
+def test_slab_fused_steps_ranges_replay(make, bh, world, tuning, full, tol):
+    """Two fused steps on slabs: every rank's interior / boundary launches of the fused-pair kernel over its slab with
+    2 x halo ghost planes (datahandling.slab_ranges(..., steps=2)) reproduce the unsharded fused launch bit for bit —
+    the iteration range bounds the intermediate field on the ghost planes, the write range the stored planes."""
+    from pystencils_autodiff_b200.datahandling import slab_ranges
+    n, g, G = 5, 1, 2
+    shape = (n * world, 14 if full else 50, 68 if full else 132)
+    op = make(shape=shape, boundary_handling=bh)
+    ir = op.forward_ast_gpu
+    dt = ir.input_fields[0].dtype.numpy_dtype
+    rng = np.random.default_rng(11)
+    u = emu.aligned_empty(shape, dt)
+    u[...] = rng.standard_normal(shape)
+    whole = emu.aligned_empty(shape, dt, np.nan)
+    emu.run(emit_march_chain(ir, tuning), [whole, u])
+    ref = _twice(op.forward_assignments, 'u', 'out', u.copy(), bh)
+    np.testing.assert_allclose(whole, ref, rtol=0, atol=tol)
+    for rank in range(world):
+        start = rank * n
+        local_u = emu.aligned_empty((n + 2 * G,) + shape[1:], dt, 0.0)
+        lo, hi = max(0, start - G), min(shape[0], start + n + G)
+        local_u[lo - (start - G):hi - (start - G)] = u[lo:hi]        # owned planes + received ghost planes
+        local_out = emu.aligned_empty(local_u.shape, dt, np.nan)
+        local_kernel = emit_march_chain(make(shape=local_u.shape, boundary_handling=bh).forward_ast_gpu, tuning)
+        parts = slab_ranges(shape, start, n, G, rank > 0, rank < world - 1, 'zeros' if bh == 'zeros' else 'none',
+                            ir.ghost_layers, 3, steps=2, halo=g)
+        written = np.zeros(n + 2 * G, dtype=int)
+        for part in parts:
+            if part is None:
+                continue
+            written[part['write_lo'][0]:part['write_hi'][0]] += 1
+            emu.run(local_kernel, [local_out, local_u], launch_range=part, full=full)
+        assert list(written) == [0] * G + [1] * n + [0] * G
+        assert np.array_equal(local_out[G:G + n], whole[start:start + n]), rank
+        assert np.isnan(local_out[:G]).all() and np.isnan(local_out[G + n:]).all()      # ghost planes are not written
+
+
+def test_slab_ranges_fused_steps_preconditions():
+    from pystencils_autodiff_b200.datahandling import slab_ranges
+    with pytest.raises(ValueError, match='ghost planes'):
+        slab_ranges((12, 8, 8), 6, 6, 1, True, False, 'zeros', 0, 3, steps=2, halo=1)
+    with pytest.raises(ValueError, match='too thin'):
+        slab_ranges((12, 8, 8), 4, 3, 2, True, True, 'zeros', 0, 3, steps=2, halo=1)
+    # a single rank needs no ghost planes at all
+    interior, lo, hi = slab_ranges((12, 8, 8), 0, 12, 0, False, False, 'zeros', 0, 3, steps=2, halo=1)
+    assert lo is None and hi is None and interior['write_lo'] == [0, 0, 0] and interior['iter_hi'] == [12, 8, 8]

@@ -124,3 +124,109 @@ def test_data_handling_registry_and_call_queue_single_rank():
     assert np.array_equal(dh.gather_array('v'), dh.owned('v').numpy())
     with pytest.raises(ValueError):
         dh.add_array('u')
+
+
+def _replay_kernel_class():
+    """``CompiledKernel`` whose launch is the CPU replay of the emitted kernel (tests/march_emulator.py) on CPU tensors:
+    the instance selection mirrors ``CompiledKernel.__call__``, the parameter block comes from ``psad_plan_launch``."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import march_emulator as emu
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+
+    class ReplayKernel(CompiledKernel):
+        launches = None
+
+        def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
+            nd = self.ir.ndim
+            arrays = [kwargs[f.name].numpy() for f in self.fields]
+            scal = [float(kwargs[s_]) for s_ in self.scalars]
+            if _variant == 'march_x2':
+                ek = self.emitted('march_x2')
+            else:
+                if _range is not None:
+                    same = (list(_range['iter_lo'][:nd]) == list(_range['write_lo'][:nd]) and
+                            list(_range['iter_hi'][:nd]) == list(_range['write_hi'][:nd]))
+                else:
+                    same = self.ir.boundary == 'zeros' or self.ir.ghost_layers == 0
+                ek = self._emitted['march_nomask' if same else 'march']
+            type(self).launches.append(ek.name)
+            emu.run(ek, arrays, scal, launch_range=_range)
+
+    ReplayKernel.launches = []
+    return ReplayKernel, emu
+
+
+def _steps_worker(rank, world, port, bh, steps, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from pystencils_autodiff_b200 import configs
+        from pystencils_autodiff_b200.datahandling import SlabDataHandling
+        ReplayKernel, emu = _replay_kernel_class()
+        gshape = (6 * world, 20, 132)
+        rng = np.random.default_rng(3)
+        glob_u = rng.standard_normal(gshape).astype(np.float32)
+        res = {}
+        for fuse in (False, True):
+            dh = SlabDataHandling(gshape, rank, world, 2, device='cpu', backend='torch')   # 2 ghost planes = 2 x halo
+            dh.add_arrays('u, out', dtype=np.float32)
+            op_l = configs.heat3d_op(shape=dh.dec.local_shape, boundary_handling=bh)
+            kernel = ReplayKernel(op_l.forward_ast_gpu)
+            sl = slice(dh.dec.start, dh.dec.start + dh.dec.n_local)
+            dh.owned('u').copy_(torch.from_numpy(glob_u[sl]))
+            del ReplayKernel.launches[:]
+            dh.run_steps(kernel, steps, fuse=fuse)
+            res[fuse] = dh.gather_array('u')
+            kinds = [c[0] for c in dh.call_queue]
+            n_launch = (steps // 2 + steps % 2) if fuse else steps
+            assert kinds.count('Communication') == n_launch and kinds.count('Swap') == n_launch
+            parts = 1 + int(rank > 0) + int(rank < world - 1)     # interior + the planes next to each neighbour
+            assert sum('x2' in n for n in ReplayKernel.launches) == parts * (steps // 2 if fuse else 0)
+            assert len(ReplayKernel.launches) == parts * n_launch
+        q.put((rank, res[False], res[True]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('bh,world,steps', [('zeros', 2, 5), (None, 3, 4)])
+def test_run_steps_fused_on_slabs(bh, world, steps):
+    """``SlabDataHandling.run_steps``: single-step launches with one-plane exchanges and fused pairs with one two-plane
+    exchange per pair both reproduce the unsharded time loop (oracle); the fused slab launches equal the unsharded
+    fused launches bit for bit.  The kernels are the emitted march / fused-step kernels, replayed on the CPU."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29950 + world
+    procs = [ctx.Process(target=_steps_worker, args=(r, world, port, bh, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, ROOT)
+    from oracle import evaluate
+    from pystencils_autodiff_b200 import configs
+    from pystencils_autodiff_b200.emit_chain import emit_march_chain
+    from pystencils_autodiff_b200.emit import emit_march
+    _, emu = _replay_kernel_class()
+    gshape = (6 * world, 20, 132)
+    glob_u = np.random.default_rng(3).standard_normal(gshape).astype(np.float32)
+    op = configs.heat3d_op(shape=gshape, boundary_handling=bh)
+    ref = glob_u.astype(np.float64)
+    for _ in range(steps):
+        ref = evaluate(op.forward_assignments, {'u': ref}, boundary_handling=bh)['out']
+    # unsharded launches of the same kernels: pairs, then the odd step
+    x2 = emit_march_chain(op.forward_ast_gpu)
+    x1 = emit_march(op.forward_ast_gpu, None, masked=bh != 'zeros')
+    a = emu.aligned_empty(gshape, np.float32)
+    a[...] = glob_u
+    b = emu.aligned_empty(gshape, np.float32, 0.0)
+    for n in [2] * (steps // 2) + [1] * (steps % 2):
+        emu.run(x2 if n == 2 else x1, [b, a])
+        a, b = b, a
+    for rank, single, fused in results:
+        assert np.abs(single - ref).max() < 5e-6, rank
+        assert np.abs(fused - ref).max() < 5e-6, rank
+        assert np.array_equal(fused, a), rank
