@@ -1,7 +1,8 @@
 """Two fused steps per launch (emit_chain.py) against two single-step launches: agreement on a small grid and at full
 size, and timing over a few tile geometries.
     python scripts/steps_bench.py c4            # 27-point fp64, 768^3
-    python scripts/steps_bench.py c3 "2,30,4,0;2,22,4,0"   # candidates as ry,ty,sx,lookahead[,exchange]
+    python scripts/steps_bench.py c3 "2,30,4,0;2,22,4,0"   # candidates as ry,ty,sx,lookahead[,exchange[,min_ctas]]
+    python scripts/steps_bench.py c2                        # 2-D 'zeros' stencils: lifted to one-plane 3-D fields
     python scripts/steps_bench.py c4 "3,21,4,0,1" c3 "2,30,4,0,1"      # several workloads in one process"""
 import os
 import sys
@@ -12,7 +13,8 @@ from pystencils_autodiff_b200.configs import make_config, CONFIG_SHAPES
 from pystencils_autodiff_b200.backends._torch_native import CompiledKernel, numpy_dtype_to_torch
 from pystencils_autodiff_b200.emit import MarchTuning
 
-DEFAULT_CANDIDATES = {'c3': '0,0,0,0;2,22,4,0;4,28,4,0;3,33,4,0', 'c4': '0,0,0,0;4,28,2,0;3,21,2,0;2,22,2,0'}
+DEFAULT_CANDIDATES = {'c3': '0,0,0,0;2,22,4,0;4,28,4,0;3,33,4,0', 'c4': '0,0,0,0;4,28,2,0;3,21,2,0;2,22,2,0',
+                      'c2': '0,0,0,0;2,30,4,0,1;2,30,4,0,0;4,44,4,0,1'}
 
 
 def timed(fn, iters=8, warm=3):
@@ -31,7 +33,8 @@ def timed(fn, iters=8, warm=3):
 
 def _tuning(cand):
     v = [int(x) for x in cand.split(',')]
-    return MarchTuning(ry=v[0], ty=v[1], sx=v[2], lookahead=v[3], exchange=bool(v[4]) if len(v) > 4 else None)
+    return MarchTuning(ry=v[0], ty=v[1], sx=v[2], lookahead=v[3], exchange=bool(v[4]) if len(v) > 4 else None,
+                       min_ctas=v[5] if len(v) > 5 else 0)
 
 
 def main():
@@ -51,12 +54,16 @@ def run(name, cands):
     dev = torch.device('cuda:0')
     # ---- small grid, both boundary modes, forward and adjoint kernels: one fused launch against two single-step launches
     # (parity against the CPU oracle is the tests' job: tests/test_gpu_steps.py, tests/test_march_replay.py)
-    small = (19, 45, 252)
+    nd = len(CONFIG_SHAPES[name]['shape'])
+    small = (19, 45, 252)[-nd:]
     for bh in ('zeros', None):
         op = make_config(name, shape=small, boundary_handling=bh)
         for ir in (op.forward_ast_gpu, op.backward_ast_gpu):
             k = CompiledKernel(ir)
             k.tuning_x2 = _tuning(cands[0])          # the first candidate's geometry
+            if k.fused_steps_reason():
+                print('small %-28s bh=%-5s not fusable: %s' % (ir.function_name, bh, k.fused_steps_reason()), flush=True)
+                continue
             fin, fout = ir.input_fields[0], ir.output_fields[0]
             ut = torch.randn(small, dtype=numpy_dtype_to_torch(fin.dtype.numpy_dtype), device=dev)
             a, b, out = torch.empty_like(ut), torch.empty_like(ut), torch.full_like(ut, float('nan'))
