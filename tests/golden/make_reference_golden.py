@@ -117,7 +117,27 @@ def cases():
     c['constant_field'] = (quirk, 'constant_y', (0.5, 1.5))
     c['transposed_pointwise'] = (lambda: readme_op((6, 7), 'float64').forward_assignments,
                                  {'diff_mode': 'transposed'}, (0.5, 1.5))
+    # rows of a multiple of 16 bytes: on the GPU these take the march (TMA-staged) kernels, not the generic fallback
+    c['diffusion2d_aligned'] = (lambda: diffusion2d_op((20, 36), 'float64').forward_assignments, {}, (-1, 1))
+    c['heat3d_aligned'] = (lambda: heat3d_op((6, 10, 36), 'float64').forward_assignments, {}, (-1, 1))
+    c['stencil27_aligned'] = (lambda: stencil27_op((5, 9, 36), 'float64').forward_assignments, {}, (-1, 1))
+    c['tvgrad_aligned'] = (lambda: tv_gradient_op((2, 12, 36), 'float64').forward_assignments, {}, (0, 1))
+    # random multi-field stencils (tests/stencil_fuzz.py: products, exp, sqrt, sin; offsets up to +-4), float64 seeds only
+    for seed in RANDOM_SEEDS:
+        c['random_%d' % seed] = (lambda s=seed: random_case(s), {}, (0.5, 1.5))
     return c
+
+
+RANDOM_SEEDS = (0, 4, 5, 8, 13, 21, 24, 31)
+
+
+def random_case(seed):
+    sys.path.insert(0, os.path.dirname(HERE))
+    from stencil_fuzz import random_stencil
+    _, _, shape, dtype = random_stencil(seed)
+    assert dtype == 'float64', 'golden vectors are float64: pick another seed'
+    fa, _, _, _ = random_stencil(seed, shape=(11, 12) if len(shape) == 2 else (6, 7, 12))
+    return fa
 
 
 def resolve_kwargs(spec, fa):

@@ -395,3 +395,42 @@ def test_slab_ranges_fused_steps_preconditions():
     # a single rank needs no ghost planes at all
     interior, lo, hi = slab_ranges((12, 8, 8), 0, 12, 0, False, False, 'zeros', 0, 3, steps=2, halo=1)
     assert lo is None and hi is None and interior['write_lo'] == [0, 0, 0] and interior['iter_hi'] == [12, 8, 8]
+
+
+def _golden_march_names():
+    from golden_util import golden_names
+    return [n for n in golden_names() if n.endswith('_aligned') or n.startswith('random_')]
+
+
+@pytest.mark.parametrize('name', _golden_march_names())
+def test_march_kernels_against_reference_golden_vectors(name):
+    """The emitted march kernels (CPU replay) against the committed golden vectors — outputs and gradients of the
+    REFERENCE's own forward / backward assignments (tests/golden/make_reference_golden.py) on seeded float64 inputs."""
+    from golden_util import build_op, golden_arrays
+    from pystencils_autodiff_b200.emit import march_ineligible_reason
+    ran = 0
+    for mode in (None, 'zeros'):
+        op = build_op(name, mode)
+        ins, outs, grads = golden_arrays(name, mode)
+        for ir, gold in ((op.forward_ast_gpu, outs), (op.backward_ast_gpu, grads)):
+            if march_ineligible_reason(ir):
+                continue
+            try:
+                ek = emit_march(ir, None, masked=True)
+            except ValueError:
+                continue
+            arrays, named = [], {}
+            for f in ek.fields:
+                shape = next(iter(ins.values())).shape
+                a = emu.aligned_empty(shape, f.dtype.numpy_dtype, np.nan)
+                if f in ir.input_fields:
+                    a[...] = ins[f.name]
+                arrays.append(a)
+                named[f.name] = a
+            emu.run(ek, arrays)
+            for f in ir.output_fields:
+                scale = max(1.0, np.abs(gold[f.name]).max())
+                assert np.abs(named[f.name] - gold[f.name]).max() <= 1e-12 * scale, (name, mode, f.name)
+                ran += 1
+    if name.endswith('_aligned'):
+        assert ran >= 4            # forward + adjoint, both boundary modes
