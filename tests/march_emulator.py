@@ -17,6 +17,7 @@ from pystencils_autodiff_b200 import runtime
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIM = os.path.join(_HERE, 'cpu_shim')
 _SHIM_FULL = os.path.join(_HERE, 'cpu_shim_full')
+_SHIM_GENERIC = os.path.join(_HERE, 'cpu_shim_generic')
 _BUILD = os.path.join(_HERE, '..', 'oracle', '_build')
 
 
@@ -109,6 +110,57 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
     rc = so.psad_emulate(args, tf, len(tma), int(grid[0]))
     assert rc == 0, 'psad_emulate failed'
     return int(grid[0])
+
+
+def run_generic(emitted, arrays, scalars=(), launch_range=None, sm_count=4):
+    """Replay of an emitted GENERIC kernel (grid-stride loops, scalar accesses): the source is compiled unchanged against
+    ``tests/cpu_shim_generic/`` and called once per CUDA thread over the grid ``psad_plan_launch`` chose.  ``arrays``:
+    numpy arrays in plan order, any strides; a trailing index dimension is allowed."""
+    L = runtime.lib()
+    plan = runtime.make_plan(emitted.plan)
+    nd = emitted.plan['ndim']
+    n = len(arrays)
+    fa = (runtime.FieldArg * n)()
+    for i, a in enumerate(arrays):
+        fa[i].ptr = a.ctypes.data
+        for d in range(3):
+            fa[i].shape[d] = a.shape[d] if d < nd else 1
+            fa[i].stride[d] = a.strides[d] // a.itemsize if d < nd else 0
+        fa[i].stride[3] = a.strides[nd] // a.itemsize if a.ndim > nd else 0
+    sc = (ctypes.c_double * max(1, len(scalars)))(*scalars)
+    args = ctypes.create_string_buffer(4096)
+    grid = (ctypes.c_uint * 3)()
+    rng = None
+    if launch_range is not None:
+        rng = runtime.Range()
+        for d in range(nd):
+            rng.iter_lo[d], rng.iter_hi[d] = launch_range['iter_lo'][d], launch_range['iter_hi'][d]
+            rng.write_lo[d], rng.write_hi[d] = launch_range['write_lo'][d], launch_range['write_hi'][d]
+    runtime.check(L.psad_plan_launch(ctypes.byref(plan), sm_count, 1, fa, n, sc, len(scalars),
+                                     ctypes.byref(rng) if rng is not None else None, args, _args_size(), grid), 'psad_plan_launch')
+    if grid[0] == 0:
+        return (0, 0, 0)
+    os.makedirs(_BUILD, exist_ok=True)
+    h = hashlib.md5(emitted.source.encode())
+    for fn in sorted(os.listdir(_SHIM_GENERIC)) + ['psad_args.h']:
+        path = os.path.join(_SHIM_GENERIC, fn) if os.path.exists(os.path.join(_SHIM_GENERIC, fn)) else os.path.join(runtime.KERNEL_DIR, fn)
+        with open(path, 'rb') as fh:
+            h.update(fh.read())
+    base = os.path.join(_BUILD, 'emugen_%s_%s' % (emitted.name[:32], h.hexdigest()[:12]))
+    if not os.path.exists(base + '.so'):
+        with open(base + '.cpp', 'w') as fh:
+            fh.write(emitted.source)
+            with open(os.path.join(_SHIM_GENERIC, 'driver.inc')) as inc:
+                fh.write('\n' + inc.read())
+        subprocess.check_call(['g++', '-std=c++17', '-O1', '-ffp-contract=off', '-mfma', '-fPIC', '-shared', '-w',
+                               '-DPSAD_EMU_KERNEL=' + emitted.name, '-I', _SHIM_GENERIC, '-I', runtime.KERNEL_DIR,
+                               '-o', base + '.so.tmp', base + '.cpp'])
+        os.replace(base + '.so.tmp', base + '.so')
+    so = ctypes.CDLL(base + '.so')
+    so.psad_emulate_generic.argtypes = [ctypes.c_void_p] + [ctypes.c_uint] * 4
+    rc = so.psad_emulate_generic(args, grid[0], grid[1], grid[2], emitted.plan['threads'])
+    assert rc == 0
+    return tuple(int(g) for g in grid)
 
 
 def _args_size():
