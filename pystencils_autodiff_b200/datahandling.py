@@ -369,10 +369,11 @@ class SlabDataHandling:
                 if ir.ndim != 3:
                     raise ValueError('%s: fused steps on slabs need 3-D fields' % kernel.function_name)
                 halo = max(ir.halo(ir.input_fields[0].name)[0])
-                self._range_cache[key] = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim, fused_steps, halo)
+                ranges = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim, fused_steps, halo)
             else:
-                self._range_cache[key] = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
-        interior, lo, hi = self._range_cache[key]
+                ranges = self.dec.ranges(ir.boundary, ir.ghost_layers, ir.ndim)
+            self._range_cache[key] = (kernel, ranges)      # holds the kernel: its id() cannot be reused while cached
+        interior, lo, hi = self._range_cache[key][1]
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
         for n in halo_fields:
