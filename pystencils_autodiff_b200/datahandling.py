@@ -244,7 +244,59 @@ class SlabDataHandling:
         return self.add_array(name, dtype=np.dtype(str(t.dtype).replace('torch.', '')))
 
     def fill(self, array_name, val, **_):
+        self.call_queue.append(('Fill', array_name))        # graph_datahandling.py:324-327 records 'Fill <name>'
         self.gpu_arrays[array_name][self.dec.owned] = val
+
+    def require_autograd(self, bool_val, *names):
+        """framework_integration/datahandling.py:190-200 (which sets an attribute torch never reads — ``require_autograd``
+        instead of ``requires_grad``); here the tensors really start / stop recording."""
+        for n in names:
+            for arrays in (self.cpu_arrays, self.gpu_arrays):
+                if n in arrays:
+                    arrays[n].requires_grad_(bool(bool_val))
+
+    def extract_tensor(self, field, on_gpu=True, with_ghost_layers=False):
+        """The registered tensor of a field (graph_datahandling.py:352-355 records a ``GhostTensorExtraction`` marker
+        and returns nothing); ghost planes stripped unless asked for."""
+        name = field if isinstance(field, str) else field.name
+        self.call_queue.append(('GhostTensorExtraction', name, bool(on_gpu), bool(with_ghost_layers)))
+        t = (self.gpu_arrays if on_gpu else self.cpu_arrays)[name]
+        return t if with_ghost_layers else t[self.dec.owned]
+
+    def save_fields(self, fields, output_path, flag_field=None):
+        """Records a ``FieldOutput`` marker like the reference (graph_datahandling.py:346-350) and writes this rank's
+        owned planes to ``<output_path>.rank<r>.npz``."""
+        if isinstance(fields, str) or not hasattr(fields, '__iter__'):
+            fields = [fields]
+        names = [f if isinstance(f, str) else f.name for f in fields]
+        self.call_queue.append(('FieldOutput', tuple(names), output_path, flag_field))
+        np.savez('%s.rank%d.npz' % (output_path, self.dec.rank),
+                 **{n: self.owned(n).detach().cpu().numpy() for n in names})
+
+    def merge_swaps_with_kernel_calls(self, call_queue=None):
+        """A ``Swap`` recorded right after a ``KernelCall`` is folded into that call
+        (graph_datahandling.py:329-344: the swap becomes the call's ``tmp_field_swaps``): the schedule a replayed graph
+        needs is "kernel, then exchange roles of its buffers".  Returns the merged queue; ``call_queue`` defaults to
+        (and then replaces) the recorded one.  Swaps here are pointer swaps and cost nothing either way."""
+        own = call_queue is None
+        queue = self.call_queue if own else call_queue
+        merged = []
+        for entry in queue:
+            if (isinstance(entry, tuple) and entry[0] == 'Swap' and merged and isinstance(merged[-1], tuple)
+                    and merged[-1][0] in ('KernelCall', 'KernelCall+Swap')):
+                prev = merged[-1]
+                swaps = prev[-1] if prev[0] == 'KernelCall+Swap' else ()
+                body = prev[1:-1] if prev[0] == 'KernelCall+Swap' else prev[1:]
+                pair = (entry[1], entry[2])
+                merged[-1] = ('KernelCall+Swap',) + tuple(body) + (swaps + ((pair,) if pair not in swaps else ()),)
+            else:
+                merged.append(entry)
+        if own:
+            self.call_queue = merged
+        return merged
+
+    def __str__(self):
+        return '\n'.join(str(c) for c in self.call_queue)
 
     def owned(self, name):
         return self.gpu_arrays[name][self.dec.owned]

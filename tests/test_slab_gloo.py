@@ -120,7 +120,7 @@ def test_data_handling_registry_and_call_queue_single_rank():
     dh.to_gpu('v')
     assert float(dh.owned('v')[0, 0]) == 4.0
     dh.synchronization_function(['u'])()          # single rank: records the marker, moves nothing
-    assert [c[0] for c in dh.call_queue] == ['Swap', 'DataTransfer', 'DataTransfer', 'Communication']
+    assert [c[0] for c in dh.call_queue] == ['Fill', 'Swap', 'DataTransfer', 'DataTransfer', 'Communication']
     assert np.array_equal(dh.gather_array('v'), dh.owned('v').numpy())
     with pytest.raises(ValueError):
         dh.add_array('u')
@@ -230,3 +230,26 @@ def test_run_steps_fused_on_slabs(bh, world, steps):
         assert np.abs(single - ref).max() < 5e-6, rank
         assert np.abs(fused - ref).max() < 5e-6, rank
         assert np.array_equal(fused, a), rank
+
+
+def test_data_handling_queue_vocabulary(tmp_path):
+    """require_autograd, extract_tensor, save_fields and merge_swaps_with_kernel_calls (graph_datahandling.py:329-355,
+    framework_integration/datahandling.py:190-200) on CPU tensors."""
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    dh = SlabDataHandling((6, 8), 0, 1, 1, device='cpu', backend='torch')
+    dh.add_arrays('u, v', dtype=np.float64)
+    dh.fill('u', 2.0)
+    dh.require_autograd(True, 'u', 'nonexistent')
+    assert dh.gpu_arrays['u'].requires_grad and not dh.gpu_arrays['v'].requires_grad
+    dh.require_autograd(False, 'u')
+    assert dh.extract_tensor('u').shape == (6, 8) and dh.extract_tensor(dh.fields['u'], with_ghost_layers=True).shape == (8, 8)
+    dh.save_fields(['u', 'v'], str(tmp_path / 'snap'))
+    saved = np.load(str(tmp_path / 'snap') + '.rank0.npz')
+    assert saved['u'].shape == (6, 8) and float(saved['u'].sum()) == 96.0
+    assert 'FieldOutput' in str(dh) and "('Fill', 'u')" in str(dh)
+    queue = [('KernelCall', 'k1'), ('Swap', 'u', 'v'), ('Communication', 'u', None, True), ('Swap', 'u', 'v'),
+             ('KernelCall', 'k2', 2), ('Swap', 'a', 'b'), ('Swap', 'u', 'v'), ('Fill', 'u')]
+    merged = dh.merge_swaps_with_kernel_calls(queue)
+    assert merged == [('KernelCall+Swap', 'k1', (('u', 'v'),)), ('Communication', 'u', None, True), ('Swap', 'u', 'v'),
+                      ('KernelCall+Swap', 'k2', 2, (('a', 'b'), ('u', 'v'))), ('Fill', 'u')]
+    assert dh.merge_swaps_with_kernel_calls() is dh.call_queue          # the recorded queue, merged in place
