@@ -371,7 +371,8 @@ def main_ours(args):
                 'ms_per_step': e2e['ms_per_step'] if e2e_error is None else None, 'steps': args.e2e_steps, 'error': e2e_error,
                 'api': ('HostStreamedOp(AutoDiffOp)(host_in, host_out): pinned host fields streamed through the GPU in plane '
                         'chunks, H2D / forward+adjoint kernels / D2H overlapped on three streams') if world == 1 else
-                       'SlabStencilOp: H2D of the slab, halo exchange + kernels, D2H of outputs and input gradients'},
+                       'SlabStencilOp: H2D of the slab, halo exchange + kernels, D2H of outputs and input gradients; upload, '
+                       'compute and download streams (the upstream gradients go up while the outputs come down)'},
         'gpu_launches': launches,
         'host_issue_ms_per_step': host_ms,
         'fused_steps': steps_info,

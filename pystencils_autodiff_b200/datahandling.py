@@ -659,17 +659,42 @@ class SlabStencilOp:
             grad_names = [f.name for f in op.backward_input_fields if f not in op.forward_input_fields]
             dnames = [f.name for f in op.backward_output_fields]
 
+            # Three streams, so that PCIe runs in both directions at once: the upstream gradients are uploaded while the
+            # forward kernel runs and its outputs are downloaded; the input gradients follow the adjoint kernel.
+            #   upload:   H2D(inputs) ........ H2D(upstream gradients)
+            #   compute:  ........... forward ......................... adjoint
+            #   download: ................... D2H(outputs) ..................... D2H(input gradients)
+            if getattr(self, '_e2e_streams', None) is None:
+                self._e2e_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+                self._e2e_events = [torch.cuda.Event() for _ in range(5)]
+            s_up, s_dn = self._e2e_streams
+            ev_in, ev_grad, ev_fwd, ev_bwd, ev_done = self._e2e_events
+
             def step():
-                for f in in_fields:
-                    self.dh.owned(f.name).copy_(host_view(h_in, f.name), non_blocking=True)
-                for n, f in zip(grad_names, out_fields):
-                    self.dh.owned(n).copy_(host_view(h_in, f.name), non_blocking=True)
+                cur = torch.cuda.current_stream(self.device)
+                s_up.wait_stream(cur)            # the previous step's kernels have read their inputs
+                with torch.cuda.stream(s_up):
+                    for f in in_fields:
+                        self.dh.owned(f.name).copy_(host_view(h_in, f.name), non_blocking=True)
+                    ev_in.record(s_up)
+                    for n, f in zip(grad_names, out_fields):
+                        self.dh.owned(n).copy_(host_view(h_in, f.name), non_blocking=True)
+                    ev_grad.record(s_up)
+                cur.wait_event(ev_in)
                 self.forward()
+                ev_fwd.record(cur)
+                cur.wait_event(ev_grad)
                 self.backward()
-                for f in out_fields:
-                    host_view(h_out, f.name).copy_(self.dh.owned(f.name), non_blocking=True)
-                for n, f in zip(dnames, in_fields):
-                    host_view(h_out, f.name).copy_(self.dh.owned(n), non_blocking=True)
+                ev_bwd.record(cur)
+                with torch.cuda.stream(s_dn):
+                    s_dn.wait_event(ev_fwd)
+                    for f in out_fields:
+                        host_view(h_out, f.name).copy_(self.dh.owned(f.name), non_blocking=True)
+                    s_dn.wait_event(ev_bwd)
+                    for n, f in zip(dnames, in_fields):
+                        host_view(h_out, f.name).copy_(self.dh.owned(n), non_blocking=True)
+                    ev_done.record(s_dn)
+                cur.wait_event(ev_done)          # the step ends (and is timed) when its results are in host memory
 
         step()
         barrier()
