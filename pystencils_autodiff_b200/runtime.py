@@ -196,8 +196,8 @@ class NativeKernel:
                 fa[i].shape[d] = shape[d] if d < len(shape) else 1
             for d in range(4):
                 fa[i].stride[d] = strides[d] if d < len(strides) else 0
-        for i, s in enumerate(scalars):
-            self._scal[i] = float(s)
+        # per-call buffer: launches of one kernel from several threads (autograd workers) must not share it
+        scal = (ctypes.c_double * max(1, len(scalars)))(*[float(s) for s in scalars]) if scalars else self._scal
         r = None
         if rng is not None:
             r = rng.get('_ctypes') if isinstance(rng, dict) else None
@@ -208,7 +208,7 @@ class NativeKernel:
                     r.write_lo[d], r.write_hi[d] = rng['write_lo'][d], rng['write_hi'][d]
                 rng['_ctypes'] = r          # launch ranges are reused every step: build the struct once
             r = ctypes.byref(r)
-        check(lib().psad_kernel_launch(self._handle, fa, n, self._scal, len(scalars), r, ctypes.c_void_p(stream)),
+        check(lib().psad_kernel_launch(self._handle, fa, n, scal, len(scalars), r, ctypes.c_void_p(stream)),
               'psad_kernel_launch(%s)' % self.emitted.name)
 
     def __del__(self):
