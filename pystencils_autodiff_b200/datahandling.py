@@ -210,6 +210,7 @@ class SlabDataHandling:
         self.cpu_arrays = OrderedDict()
         self.fields = OrderedDict()
         self.call_queue = []
+        self._replicated = set()       # arrays with their own spatial shape: whole on every rank, no ghost planes
         self._range_cache = {}
         self._comm_stream = None
         self._ev_ready = None
@@ -224,20 +225,34 @@ class SlabDataHandling:
     def shape(self):
         return self.dec.global_shape
 
-    def add_array(self, name, values_per_cell=1, dtype=np.float32, **_):
+    def add_array(self, name, values_per_cell=1, dtype=np.float32, spatial_shape=None, **_):
+        """``spatial_shape``: an array of its own size (``MultiShapeDatahandling.add_array``,
+        framework_integration/datahandling.py:73-132, "communication free applications"): stored whole on every rank,
+        without ghost planes, never exchanged; kernels over such arrays run unsharded on every rank."""
         from .field import Field
         if name in self.gpu_arrays:
             raise ValueError('GPU Field with this name already exists')
         tail = () if values_per_cell in (1, (1,), ()) else (tuple(values_per_cell) if hasattr(values_per_cell, '__len__')
                                                               else (int(values_per_cell),))
-        arr = self.torch.zeros(self.dec.local_shape + tail, dtype=numpy_dtype_to_torch(dtype), device=self.device)
+        if spatial_shape is not None and tuple(int(v) for v in spatial_shape) != self.dec.global_shape:
+            shape = tuple(int(v) for v in spatial_shape)
+            self._replicated.add(name)
+        else:
+            shape = self.dec.local_shape
+        arr = self.torch.zeros(shape + tail, dtype=numpy_dtype_to_torch(dtype), device=self.device)
         self.gpu_arrays[name] = arr
-        self.fields[name] = Field.create_fixed_size(name, self.dec.local_shape + tail, index_dimensions=len(tail),
-                                                    dtype=dtype)
+        self.fields[name] = Field.create_fixed_size(name, shape + tail, index_dimensions=len(tail), dtype=dtype)
         return self.fields[name]
 
-    def add_arrays(self, description, dtype=np.float32):
-        return tuple(self.add_array(n.strip(), dtype=dtype) for n in description.split(','))
+    def add_arrays(self, description, dtype=np.float32, spatial_shape=None):
+        """``"u, out"`` or the field-description syntax ``"x, y(2): float32[20,30]"`` (data type and per-array shape from
+        the description, like ``MultiShapeDatahandling.add_arrays``, framework_integration/datahandling.py:54-71)."""
+        if ':' in description:
+            from .field import _parse_description
+            infos, dt, size = _parse_description(description)
+            shape = size if isinstance(size, tuple) and size else spatial_shape
+            return tuple(self.add_array(n, values_per_cell=idx or 1, dtype=dt, spatial_shape=shape) for n, idx in infos)
+        return tuple(self.add_array(n.strip(), dtype=dtype, spatial_shape=spatial_shape) for n in description.split(','))
 
     def add_array_like(self, name, name_of_template_field):
         t = self.gpu_arrays[name_of_template_field]
@@ -245,7 +260,7 @@ class SlabDataHandling:
 
     def fill(self, array_name, val, **_):
         self.call_queue.append(('Fill', array_name))        # graph_datahandling.py:324-327 records 'Fill <name>'
-        self.gpu_arrays[array_name][self.dec.owned] = val
+        self.owned(array_name)[...] = val
 
     def require_autograd(self, bool_val, *names):
         """framework_integration/datahandling.py:190-200 (which sets an attribute torch never reads — ``require_autograd``
@@ -261,7 +276,7 @@ class SlabDataHandling:
         name = field if isinstance(field, str) else field.name
         self.call_queue.append(('GhostTensorExtraction', name, bool(on_gpu), bool(with_ghost_layers)))
         t = (self.gpu_arrays if on_gpu else self.cpu_arrays)[name]
-        return t if with_ghost_layers else t[self.dec.owned]
+        return t if with_ghost_layers or name in self._replicated else t[self.dec.owned]
 
     def save_fields(self, fields, output_path, flag_field=None):
         """Records a ``FieldOutput`` marker like the reference (graph_datahandling.py:346-350) and writes this rank's
@@ -299,7 +314,7 @@ class SlabDataHandling:
         return '\n'.join(str(c) for c in self.call_queue)
 
     def owned(self, name):
-        return self.gpu_arrays[name][self.dec.owned]
+        return self.gpu_arrays[name] if name in self._replicated else self.gpu_arrays[name][self.dec.owned]
 
     # -- host mirrors (reference: GraphDataHandling.to_cpu / to_gpu record a DataTransfer, graph_datahandling.py:255-282)
     def to_cpu(self, name):
@@ -329,7 +344,7 @@ class SlabDataHandling:
         """Global array on every rank (host numpy), ghost planes stripped."""
         import torch.distributed as dist
         local = self.owned(name).contiguous()
-        if self.dec.world_size == 1:
+        if self.dec.world_size == 1 or name in self._replicated:
             return local.cpu().numpy()
         parts = [self.torch.empty((c,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
                  for c in self.dec.counts]
@@ -367,7 +382,7 @@ class SlabDataHandling:
     def start_exchange(self, name):
         """Asynchronous: exchange on the communication stream, ordered after everything already queued on the
         current stream."""
-        if self.dec.world_size == 1 or self.dec.g == 0:
+        if self.dec.world_size == 1 or self.dec.g == 0 or name in self._replicated:
             return
         t = self.gpu_arrays[name]
         if t.is_cuda:
@@ -411,6 +426,14 @@ class SlabDataHandling:
         self.call_queue.append(('KernelCall', kernel.function_name) if fused_steps == 1 else
                                ('KernelCall', kernel.function_name, fused_steps))
         arrays = {f.name: self.gpu_arrays[f.name] for f in kernel.fields}
+        replicated = [n for n in arrays if n in self._replicated]
+        if replicated:
+            if len(replicated) != len(arrays):
+                raise ValueError('%s mixes slab-decomposed arrays with arrays of their own shape (%s)'
+                                 % (kernel.function_name, ', '.join(sorted(replicated))))
+            if fused_steps > 1:
+                kwargs = dict(kwargs, _variant='march_x2')
+            return kernel(**arrays, **kwargs)          # whole arrays, every rank, no exchange
         ir = kernel.ir
         key = (id(kernel), fused_steps)
         if key not in self._range_cache:

@@ -253,3 +253,38 @@ def test_data_handling_queue_vocabulary(tmp_path):
     assert merged == [('KernelCall+Swap', 'k1', (('u', 'v'),)), ('Communication', 'u', None, True), ('Swap', 'u', 'v'),
                       ('KernelCall+Swap', 'k2', 2, (('a', 'b'), ('u', 'v'))), ('Fill', 'u')]
     assert dh.merge_swaps_with_kernel_calls() is dh.call_queue          # the recorded queue, merged in place
+
+
+def test_arrays_with_their_own_shape_are_replicated():
+    """MultiShapeDatahandling vocabulary (framework_integration/datahandling.py:54-132): ``spatial_shape`` / the
+    description syntax give arrays of their own size — whole on every rank, no ghost planes, run unsharded."""
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    dh = SlabDataHandling((6, 8), 0, 1, 1, device='cpu', backend='torch')
+    u, = dh.add_arrays('u', dtype=np.float64)
+    x, y = dh.add_arrays('x, y(2): float32[20,30]')
+    w = dh.add_array('w', spatial_shape=(5, 4))
+    assert dh.gpu_arrays['u'].shape == (8, 8) and dh.gpu_arrays['x'].shape == (20, 30)
+    assert dh.gpu_arrays['y'].shape == (20, 30, 2) and y.index_dimensions == 1 and dh.gpu_arrays['x'].dtype == torch.float32
+    assert w.spatial_shape == (5, 4) and dh.owned('w').shape == (5, 4) and dh.owned('u').shape == (6, 8)
+    dh.fill('x', 1.5)
+    assert float(dh.gpu_arrays['x'].sum()) == 1.5 * 600 and dh.gather_array('x').shape == (20, 30)
+    assert dh.extract_tensor('w').shape == (5, 4)
+    dh.synchronization_function(['x'])()           # never exchanged
+    # a kernel over replicated arrays is called on the whole arrays, without a launch range; mixing is an error
+    import pystencils_autodiff_b200 as ps
+    a, b = ps.fields('x, z: float32[20,30]')
+    dh.add_array('z', spatial_shape=(20, 30))
+    seen = {}
+
+    class Probe(CompiledKernel):
+        def __call__(self, *, _range=None, _variant=None, _stream=None, **kw):
+            seen.update(range=_range, names=sorted(kw))
+
+    op = ps.AutoDiffOp([ps.Assignment(b.center, 2 * a[0, 1])], op_name='rep', boundary_handling='zeros')
+    dh.run_kernel(Probe(op.forward_ast_gpu))
+    assert seen == dict(range=None, names=['x', 'z'])
+    c, d = ps.fields('u, z: float64[8,8]')
+    mixed = ps.AutoDiffOp([ps.Assignment(d.center, c[0, 0])], op_name='mixed')
+    with pytest.raises(ValueError, match='mixes'):
+        dh.run_kernel(Probe(mixed.forward_ast_gpu))
