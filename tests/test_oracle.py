@@ -134,3 +134,29 @@ def test_golden_vectors():
                 np.testing.assert_allclose(v, gold[tag + 'grad/' + k], rtol=1e-13, atol=1e-13)
                 checked += 1
     assert checked >= 24
+
+
+def test_c_restatement_against_golden_vectors():
+    """oracle/cgen.py — the C/OpenMP restatement of the pystencils CPU loop nest that ``bench.py --impl reference`` times
+    — against the committed golden vectors (strict flavour; the fast flavour is the same source with -Ofast)."""
+    import sys
+    sys.path.insert(0, HERE)
+    from golden_util import build_op, golden_arrays, golden_names
+    checked = 0
+    for name in golden_names():
+        if name.startswith('random_') and name not in ('random_0', 'random_4'):
+            continue                                   # two random stencils are enough for the C generator
+        for mode in (None, 'zeros'):
+            op = build_op(name, mode)
+            ins, outs, grads = golden_arrays(name, mode)
+            shape = next(iter(ins.values())).shape
+            for assigns, gold, tag in ((op.forward_assignments, outs, 'f'), (op.backward_assignments, grads, 'b')):
+                k = compile_c(assigns, mode, 'gold_%s_%s_%s' % (name, tag, 'z' if mode else 'n'), flavour='strict')
+                env = {}
+                for n in k.field_names:
+                    env[n] = np.ascontiguousarray(ins[n]) if (n in ins and n not in gold) else np.zeros(shape)
+                k(**env)
+                for key, ref in gold.items():
+                    np.testing.assert_allclose(env[key], ref, rtol=1e-12, atol=1e-12, err_msg='%s %s %s' % (name, mode, key))
+                    checked += 1
+    assert checked >= 60
