@@ -27,7 +27,6 @@ REF = '/root/reference/src/pystencils_autodiff'
 
 import pystencils_autodiff_b200 as ours  # noqa: E402
 from pystencils_autodiff_b200 import assignment as A, field as F, transformations as T  # noqa: E402
-from oracle import evaluate  # noqa: E402
 
 
 def install_shim():
@@ -151,6 +150,7 @@ def resolve_kwargs(spec, fa):
 
 
 def main():
+    from oracle import evaluate      # here, not at import time: the case list is also read by scripts/precompile_tests.py
     ad, tr = install_shim()
     sym, num = {}, {}
     rng = np.random.default_rng(2026)
