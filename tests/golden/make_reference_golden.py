@@ -150,6 +150,12 @@ def resolve_kwargs(spec, fa):
 
 
 def main():
+    # The reference's 'transposed' mode orders fields and assignments by SET iteration (_autodiff.py:430 ``list(read_fields)``),
+    # i.e. by string hashes: pin the hash seed so that regenerating the fixtures is reproducible.  (The consumer,
+    # tests/test_symbolic.py, compares that case order-insensitively.)
+    if os.environ.get('PYTHONHASHSEED') != '0':
+        os.environ['PYTHONHASHSEED'] = '0'
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     from oracle import evaluate      # here, not at import time: the case list is also read by scripts/precompile_tests.py
     ad, tr = install_shim()
     sym, num = {}, {}

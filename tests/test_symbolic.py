@@ -164,13 +164,17 @@ def test_matches_reference_symbolic_output(name):
     fa = factory()
     op = ps.AutoDiffOp(fa, **resolve_kwargs(spec, fa))
     g = _GOLD[name]
+    # the reference's 'transposed' mode orders fields and assignments by set iteration (_autodiff.py:430), i.e. by the
+    # process's string hashes; this package sorts them.  That case is compared up to order.
+    canon = (lambda text: sorted(text.splitlines())) if spec == {'diff_mode': 'transposed'} else (lambda text: text)
+    names = sorted if spec == {'diff_mode': 'transposed'} else list
     assert str(op.forward_assignments) == g['forward']
-    assert str(op.backward_assignments) == g['backward']
-    assert [f.name for f in op.forward_input_fields] == g['forward_input_fields']
+    assert canon(str(op.backward_assignments)) == canon(g['backward'])
+    assert names(f.name for f in op.forward_input_fields) == names(g['forward_input_fields'])
     assert [f.name for f in op.forward_output_fields] == g['forward_output_fields']
     assert sorted(f.name for f in op.backward_input_fields) == g['backward_input_fields']
     assert sorted(f.name for f in op.backward_output_fields) == g['backward_output_fields']
-    assert str(ps.add_fixed_constant_boundary_handling(op.backward_assignments)) == g['backward_zeros']
+    assert canon(str(ps.add_fixed_constant_boundary_handling(op.backward_assignments))) == canon(g['backward_zeros'])
 
 
 def test_fused_forward_adjoint_collection():
