@@ -28,7 +28,8 @@ import numpy as np
 from . import runtime
 from .backends._torch_native import CompiledKernel, numpy_dtype_to_torch
 
-__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
+__all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataHandling', 'PyTorchDataHandling',
+           'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
 
 
 class SlabDecomposition:
@@ -420,7 +421,18 @@ class SlabDataHandling:
         exchange of ``2 * halo`` ghost planes instead of two exchanges of ``halo`` planes; the data handling must store
         that many ghost layers."""
         if not isinstance(kernel, CompiledKernel):
-            raise TypeError('run_kernel expects a CompiledKernel (AutoDiffOp.forward_kernel_gpu / backward_kernel_gpu)')
+            if isinstance(kernel, type) and isinstance(getattr(kernel, 'forward_kernel', None), CompiledKernel):
+                # the Function class of op.create_tensorflow_op(backend='torch_native') (tests/test_datahandling.py:17-35
+                # passes the op itself): its forward kernel on the registered arrays, outputs written in place
+                return self.run_kernel(kernel.forward_kernel, halo_fields, fused_steps,
+                                       **{**getattr(kernel, 'class_kwargs', {}), **kwargs})
+            if callable(kernel) and self.dec.world_size == 1:
+                # any other callable gets every registered array by name, like PyTorchDataHandling.run_kernel
+                # (framework_integration/datahandling.py:185-188); it cannot be split into slab launches
+                self.call_queue.append(('KernelCall', getattr(kernel, '__name__', type(kernel).__name__)))
+                return kernel(**{n: self.owned(n) for n in self.gpu_arrays}, **kwargs)
+            raise TypeError('run_kernel expects a CompiledKernel (AutoDiffOp.forward_kernel_gpu / backward_kernel_gpu) or '
+                            'the Function class of a torch_native op; arbitrary callables only on a single rank')
         if fused_steps not in (1, 2):
             raise ValueError('fused_steps must be 1 or 2')
         self.call_queue.append(('KernelCall', kernel.function_name) if fused_steps == 1 else
@@ -492,6 +504,32 @@ class SlabDataHandling:
             self.run_kernel(kernel, halo_fields=halo, fused_steps=n, **scalars)
             self.swap(fin, fout)
         return self.gpu_arrays[fin]
+
+
+class GraphDataHandling(SlabDataHandling):
+    """``SlabDataHandling`` behind the reference's constructor (graph_datahandling.py:196-200 /
+    framework_integration/datahandling.py:176-183: ``(domain_size, default_ghost_layers, default_layout, periodicity,
+    default_target)``).  Rank and world size come from ``torch.distributed`` when a process group is initialised, so the
+    same script runs on one GPU or slab-decomposed under torchrun.  ``periodicity`` is not supported (the global boundary
+    is 'zeros' or interior iteration), layouts other than 'numpy' (C order) neither; ``default_target`` must be 'gpu'."""
+
+    def __init__(self, domain_size, default_ghost_layers=0, default_layout='numpy', periodicity=False,
+                 default_target='gpu', device=None, backend=None):
+        import torch.distributed as dist
+        if periodicity not in (False, None) and any(periodicity if hasattr(periodicity, '__iter__') else [periodicity]):
+            raise NotImplementedError('periodic domains are not supported: the global boundary is zeros / interior iteration')
+        if default_layout not in ('numpy', 'c', 'C'):
+            raise NotImplementedError("only the 'numpy' (C order) layout is supported")
+        if default_target not in ('gpu', None):
+            raise NotImplementedError("this backend has no CPU path: default_target must be 'gpu'")
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        if backend is None:
+            backend = 'nccl' if (world == 1 or dist.get_backend() == 'nccl') else 'torch'
+        super().__init__(domain_size, rank, world, default_ghost_layers, device, backend)
+        self.default_target = 'gpu'
+
+
+PyTorchDataHandling = GraphDataHandling     # framework_integration/datahandling.py:135
 
 
 class TimeLoop:

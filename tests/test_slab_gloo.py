@@ -288,3 +288,56 @@ def test_arrays_with_their_own_shape_are_replicated():
     mixed = ps.AutoDiffOp([ps.Assignment(d.center, c[0, 0])], op_name='mixed')
     with pytest.raises(ValueError, match='mixes'):
         dh.run_kernel(Probe(mixed.forward_ast_gpu))
+
+
+def test_run_kernel_accepts_the_op_like_the_reference_test():
+    """tests/test_datahandling.py:17-35: ``dh.run_kernel(op, a=3)`` with the torch op itself; here the op's forward kernel
+    runs on the registered arrays (CPU replay of the emitted generic kernel as the launch) and writes ``z`` in place.
+    Plain callables get every registered array by name (single rank only)."""
+    import sympy
+    import pystencils_autodiff_b200 as ps
+    from oracle.evaluate import evaluate
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import march_emulator as emu
+
+    class GenericReplay(CompiledKernel):
+        def __call__(self, *, _range=None, _variant=None, _stream=None, **kw):
+            ek = self._emitted['generic']
+            emu.run_generic(ek, [kw[f.name].numpy() for f in ek.fields], [float(kw[s_]) for s_ in self.scalars],
+                            launch_range=_range)
+
+    dh = SlabDataHandling((20, 30), 0, 1, 0, device='cpu', backend='torch')
+    for n in 'xyz':
+        dh.add_array(n)
+    a = sympy.Symbol('a')
+    z, y, x = ps.fields('z, y, x: float32[20,30]')
+    op = ps.AutoDiffOp(ps.AssignmentCollection({z[0, 0]: x[0, 0] * sympy.log(a * x[0, 0] * y[0, 0])}), op_name='dhop')
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    fn.forward_kernel = GenericReplay(op.forward_ast_gpu)
+    rng = np.random.default_rng(0)
+    X, Y = rng.uniform(0.5, 1.5, (20, 30)).astype(np.float32), rng.uniform(0.5, 1.5, (20, 30)).astype(np.float32)
+    dh.owned('x').copy_(torch.from_numpy(X))
+    dh.owned('y').copy_(torch.from_numpy(Y))
+    dh.run_kernel(fn, a=3)
+    ref = evaluate(op.forward_assignments, {'x': X.astype(np.float64), 'y': Y.astype(np.float64)}, None, scalars={'a': 3.0})['z']
+    np.testing.assert_allclose(dh.owned('z').numpy(), ref, rtol=0, atol=2e-6)
+    seen = {}
+    dh.run_kernel(lambda **kw: seen.update(kw), b=1)
+    assert sorted(seen) == ['b', 'x', 'y', 'z'] and seen['x'].shape == (20, 30)
+    with pytest.raises(TypeError):
+        dh.run_kernel(42)
+
+
+def test_reference_constructor_aliases():
+    """``GraphDataHandling`` / ``PyTorchDataHandling`` with the reference's constructor arguments (single process)."""
+    from pystencils_autodiff_b200.datahandling import GraphDataHandling, PyTorchDataHandling
+    dh = PyTorchDataHandling((20, 30), device='cpu')
+    assert dh.dec.world_size == 1 and dh.dec.g == 0 and dh.add_array('x').spatial_shape == (20, 30)
+    dh = GraphDataHandling((10, 15), default_ghost_layers=1, periodicity=False, default_target='gpu', device='cpu')
+    assert dh.dec.local_shape == (12, 15) and dh.create_timeloop(use_cuda_graph=False).time_steps_run == 0
+    with pytest.raises(NotImplementedError):
+        GraphDataHandling((10, 15), periodicity=True, device='cpu')
+    with pytest.raises(NotImplementedError):
+        GraphDataHandling((10, 15), default_target='cpu', device='cpu')
