@@ -12,25 +12,21 @@ ADJOINT_FIELD_LATEX_HIGHLIGHT = r"\hat{%s}"
 
 
 class AdjointField(Field):
-    """Field representing adjoint variables to a Field representing the forward variables"""
+    """The adjoint companion ``<prefix><name>`` of a forward field: same element type, layout, shape and strides."""
 
     def __init__(self, forward_field, name_prefix='diff'):
-        new_name = name_prefix + forward_field.name
-        field_type = FieldType.GENERIC if forward_field.field_type != FieldType.BUFFER else FieldType.BUFFER
-        super().__init__(new_name, field_type, forward_field.dtype, forward_field.layout,
-                         forward_field.shape, forward_field.strides)
+        adjoint_name = name_prefix + forward_field.name
+        kind = FieldType.BUFFER if forward_field.field_type == FieldType.BUFFER else FieldType.GENERIC
+        super().__init__(adjoint_name, kind, forward_field.dtype, forward_field.layout, forward_field.shape,
+                         forward_field.strides)
         self._index_dimensions = forward_field.index_dimensions
         self.corresponding_forward_field = forward_field
         self.name_prefix = name_prefix
 
-        def rekey(sym, kind, i):
-            if isinstance(sym, sp.Symbol):
-                return sp.Symbol('_%s_%s_%d' % (kind, new_name, i), integer=True)
-            return sym
-        self.shape = tuple(rekey(s, 'size', i) for i, s in enumerate(self.shape))
-        self.strides = tuple(rekey(s, 'stride', i) for i, s in enumerate(self.strides))
+        # symbolic extents / strides must not refer to the forward field, which a backward kernel may not receive
+        def own(sym, what, axis):
+            return sp.Symbol('_%s_%s_%d' % (what, adjoint_name, axis), integer=True) if isinstance(sym, sp.Symbol) else sym
 
-        if forward_field.latex_name:
-            self.latex_name = ADJOINT_FIELD_LATEX_HIGHLIGHT % forward_field.latex_name
-        else:
-            self.latex_name = ADJOINT_FIELD_LATEX_HIGHLIGHT % forward_field.name
+        self.shape = tuple(own(s, 'size', i) for i, s in enumerate(self.shape))
+        self.strides = tuple(own(s, 'stride', i) for i, s in enumerate(self.strides))
+        self.latex_name = ADJOINT_FIELD_LATEX_HIGHLIGHT % (forward_field.latex_name or forward_field.name)
