@@ -29,6 +29,7 @@ from . import runtime
 from .backends._torch_native import CompiledKernel, numpy_dtype_to_torch
 
 __all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataHandling', 'PyTorchDataHandling',
+           'create_slab_autograd_function',
            'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
 
 
@@ -504,6 +505,146 @@ class SlabDataHandling:
             self.run_kernel(kernel, halo_fields=halo, fused_steps=n, **scalars)
             self.swap(fin, fout)
         return self.gpu_arrays[fin]
+
+
+def create_slab_autograd_function(op, data_handling, op_name=None, tuning=None, scalars=None, kernel_class=None):
+    """``torch.autograd.Function`` of an ``AutoDiffOp`` on THIS RANK'S SLAB of slab-decomposed fields: the
+    sharded counterpart of ``op.create_tensorflow_op(backend='torch_native')`` with the same calling convention
+    (backends/_torch_native.py:43-118 of the reference) — ``Op.apply(*inputs)`` takes the forward input fields in
+    ``op.forward_input_fields`` order and returns a tuple in ``op.forward_output_fields`` order — where every tensor is
+    the rank's OWNED planes ``[n_local, ...]`` of a field whose global extent along dim 0 is split over the ranks.
+
+    forward: ghost planes of the inputs are exchanged with the neighbours (overlapped with the interior launch), the
+    forward kernel runs on the owned planes.  backward: the SAME exchange on the upstream gradients ``diff<out>``, then
+    the local adjoint kernel — the adjoint is in gather form, so there is no reverse exchange and nothing is accumulated
+    across ranks.
+
+    Slab tensors live inside padded buffers (``g`` ghost planes per side).  Outputs and gradients are returned as views
+    of such buffers, and a tensor that already is such a view (an output of this Function, ``data_handling.owned(name)``)
+    is used in place, so chained steps copy nothing; any other tensor is copied into a fresh padded buffer once.
+
+    ``kernel_class``: the ``CompiledKernel`` subclass that launches (tests replay the emitted kernels on the CPU)."""
+    import weakref
+    import torch
+    dh = data_handling
+    dec = dh.dec
+    g, n = dec.g, dec.n_local
+    KC = kernel_class or CompiledKernel
+    fwd_ir, bwd_ir = op.forward_ast_gpu, op.backward_ast_gpu
+    fwd_k, bwd_k = KC(fwd_ir, tuning), KC(bwd_ir, tuning)
+    scalars = dict(scalars or {})
+    for kern in (fwd_k, bwd_k):
+        missing = [s_ for s_ in kern.scalars if s_ not in scalars]
+        if missing:
+            raise TypeError('%s: missing scalar argument(s) %s (pass scalars={...})' % (kern.function_name, missing))
+    fwd_inputs, fwd_outputs = list(op.forward_input_fields), list(op.forward_output_fields)
+    bwd_outputs = {f.name: f for f in op.backward_output_fields}
+    fields = {f.name: f for f in list(op.forward_fields) + list(op.backward_fields)}
+    # adjoint fields carry the forward field they belong to (AdjointField.corresponding_forward_field)
+    grad_of, adjoint_of = {}, {}         # forward output -> upstream gradient field; forward input -> its gradient field
+    for f in fields.values():
+        fwd = getattr(f, 'corresponding_forward_field', None)
+        if fwd is not None:
+            (grad_of if fwd in fwd_outputs else adjoint_of)[fwd.name] = f.name
+    sharded = dec.world_size > 1
+
+    def reach(ir, name):
+        return max(ir.halo(name)[0])
+    need = max([reach(ir, f.name) for ir in (fwd_ir, bwd_ir) for f in ir.input_fields] + [0])
+    if sharded and g < need:
+        raise ValueError('the stencils reach %d plane(s) along dim 0, the data handling stores %d ghost layer(s)' % (need, g))
+    fwd_halo = [f.name for f in fwd_ir.input_fields if sharded and reach(fwd_ir, f.name) > 0]
+    bwd_halo = [f.name for f in bwd_ir.input_fields if sharded and reach(bwd_ir, f.name) > 0 and f.name not in fwd_halo]
+    fwd_reads = {f.name for f in fwd_ir.input_fields}
+    bwd_reads = {f.name for f in bwd_ir.input_fields}
+    ours = weakref.WeakValueDictionary()    # id -> padded buffer allocated here: its ghost planes are ours to write
+
+    def tail(f):
+        return tuple(int(v) for v in f.index_shape) if f.index_dimensions else ()
+
+    def new_padded(f, like, zero):
+        shape = (n + 2 * g,) + tuple(like.shape[1:])
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=like.device)
+        if not zero and g:
+            t[:g].zero_()             # ghost planes at the global border are never received: they must read as 0
+            t[g + n:].zero_()
+        ours[id(t)] = t
+        return t
+
+    def padded_of(t, f):
+        """The padded buffer ``t`` is the owned part of, else a fresh one holding a copy of ``t``."""
+        if t.shape[0] != n:
+            raise ValueError('%s: expected this rank\'s %d owned planes of %r, got shape %s'
+                             % (op.op_name, n, f.name, tuple(t.shape)))
+        want = numpy_dtype_to_torch(f.dtype.numpy_dtype)
+        if t.dtype != want:
+            raise TypeError('%s: field %r expects dtype %s, got %s' % (op.op_name, f.name, want, t.dtype))
+        base = t._base
+        if (base is not None and base.dim() == t.dim() and base.shape[0] == n + 2 * g and base.is_contiguous()
+                and t.stride() == base.stride() and t.storage_offset() == base.storage_offset() + g * base.stride(0)
+                and (ours.get(id(base)) is base or any(base is a for a in dh.gpu_arrays.values()))):
+            return base
+        p = new_padded(f, t, zero=False)
+        p[g:g + n].copy_(t.detach())
+        return p
+
+    def launch(kernel, arrays, halo):
+        keep = {k: dh.gpu_arrays.get(k) for k in arrays}
+        dh.gpu_arrays.update(arrays)                 # run_kernel looks its fields up by name at call time
+        try:
+            dh.run_kernel(kernel, halo_fields=halo, **{k: v for k, v in scalars.items() if k in kernel.scalars})
+        finally:
+            for k, v in keep.items():
+                if v is None:
+                    dh.gpu_arrays.pop(k, None)
+                else:
+                    dh.gpu_arrays[k] = v
+
+    def forward(ctx, *inputs):
+        if len(inputs) != len(fwd_inputs):
+            raise TypeError('%s takes %d input tensors (%s), got %d' % (op.op_name, len(fwd_inputs),
+                                                                         [f.name for f in fwd_inputs], len(inputs)))
+        arrays = {f.name: padded_of(t, f) for f, t in zip(fwd_inputs, inputs)}
+        like = inputs[0]
+        for f in fwd_outputs:
+            arrays[f.name] = new_padded(f, like if not tail(f) else like.new_empty(like.shape[:len(dec.global_shape)] + tail(f)),
+                                        zero=f.name in fwd_reads)
+        launch(fwd_k, {k: v for k, v in arrays.items() if k in {f.name for f in fwd_k.fields}}, fwd_halo)
+        saved = [k for k in arrays if k in bwd_reads]
+        ctx.saved_names = saved
+        ctx.save_for_backward(*[arrays[k] for k in saved])
+        ctx.like = like
+        return tuple(arrays[f.name][g:g + n] for f in fwd_outputs)
+
+    def backward(ctx, *grad_outputs):
+        arrays = dict(zip(ctx.saved_names, ctx.saved_tensors))
+        like = ctx.like
+        for f, go in zip(fwd_outputs, grad_outputs):
+            name = grad_of.get(f.name)
+            if name is None or name not in bwd_reads:
+                continue
+            gf = fields[name]
+            if go is None:
+                arrays[name] = new_padded(gf, like, zero=True)
+            else:
+                arrays[name] = padded_of(go.contiguous() if not go.is_contiguous() else go, gf)
+        for name, f in bwd_outputs.items():
+            arrays[name] = new_padded(f, like, zero=name in bwd_reads)
+        launch(bwd_k, {k: v for k, v in arrays.items() if k in {f.name for f in bwd_k.fields}},
+               [h for h in bwd_halo if h in arrays])
+        result = []
+        for f in fwd_inputs:
+            name = adjoint_of.get(f.name)
+            result.append(arrays[name][g:g + n] if name in bwd_outputs else None)
+        return tuple(result)
+
+    cls = type(op_name or op.op_name + '_slab', (torch.autograd.Function,),
+               {'forward': staticmethod(forward), 'backward': staticmethod(backward)})
+    cls.forward_kernel, cls.backward_kernel = fwd_k, bwd_k
+    cls.forward_ast, cls.backward_ast = fwd_ir, bwd_ir
+    cls.data_handling = dh
+    cls.class_kwargs = scalars
+    return cls
 
 
 class GraphDataHandling(SlabDataHandling):

@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
         scripts/check_slab_steps.py [c3|c4] [zeros|none] [steps]
 Every rank also runs the whole (small) global field on its own GPU with ``CompiledKernel.run_steps(fuse=True)`` and
-compares its slab with the matching planes: bit for bit.  Single steps (``fuse=False``) are compared the same way.
+compares its slab with the matching planes: bit for bit.  Single steps (``fuse=False``) are compared the same way, and
+so is a chain of two steps through the slab autograd Function (``create_slab_autograd_function``), outputs and gradients.
 """
 import os
 import sys
@@ -53,6 +54,24 @@ def main():
         ok = ok and same
         print('[rank %d] %s %s steps=%d fuse=%s: %s' % (rank, name, bh, steps, fuse, 'IDENTICAL' if same else
               'DIFFERENT (max %.3e)' % float((res[dh.dec.owned] - ref[sl]).abs().max())), flush=True)
+    # autograd: two chained steps through the slab Function == the unsharded Function on the global field
+    from pystencils_autodiff_b200.datahandling import create_slab_autograd_function
+    dh = SlabDataHandling(gshape, rank, world, halo, dev)
+    Step = create_slab_autograd_function(make_config(name, shape=local, boundary_handling=bh), dh)
+    r = torch.randn(gshape, generator=g, dtype=torch.float64).to(glob.dtype).to(dev)
+    u = glob[sl].clone().requires_grad_(True)
+    (o1,) = Step.apply(u)
+    (o2,) = Step.apply(o1)
+    (o2 * r[sl]).sum().backward()
+    Whole = op_g.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    ug = glob.clone().requires_grad_(True)
+    (g1,) = Whole.apply(ug)
+    (g2,) = Whole.apply(g1)
+    (g2 * r).sum().backward()
+    torch.cuda.synchronize()
+    same = torch.equal(o2, g2[sl]) and torch.equal(u.grad, ug.grad[sl])
+    ok = ok and same
+    print('[rank %d] %s %s autograd chain of 2 slab steps: %s' % (rank, name, bh, 'IDENTICAL' if same else 'DIFFERENT'), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

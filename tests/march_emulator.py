@@ -41,15 +41,15 @@ def _compile(emitted, full=False):
             h.update(fh.read())
     base = os.path.join(_BUILD, 'emu%s_%s_%s' % ('full' if full else '', emitted.name[:32], h.hexdigest()[:12]))
     if not os.path.exists(base + '.so'):
-        with open(base + '.cpp', 'w') as fh:
+        with open(base + '.%d.cpp' % os.getpid(), 'w') as fh:
             fh.write(emitted.source)
             if full:   # the real psad_march.cuh was included by the source; add the emulated machine + launch loop
                 with open(os.path.join(_SHIM_FULL, 'driver.inc')) as inc:
                     fh.write('\n' + inc.read())
         # -ffp-contract=off mirrors -fmad=false; fma()/fmaf() map to the hardware FMA like on the GPU
         subprocess.check_call(['g++', '-std=c++20', '-O1', '-ffp-contract=off', '-mfma', '-fPIC', '-shared', '-pthread', '-w', '-Wno-psabi',
-                               '-I', shim, '-I', runtime.KERNEL_DIR, '-o', base + '.so.tmp', base + '.cpp'])
-        os.replace(base + '.so.tmp', base + '.so')
+                               '-I', shim, '-I', runtime.KERNEL_DIR, '-o', base + '.so.tmp%d' % os.getpid(), base + '.%d.cpp' % os.getpid()])
+        os.replace(base + '.so.tmp%d' % os.getpid(), base + '.so')
     return ctypes.CDLL(base + '.so')
 
 
@@ -148,14 +148,14 @@ def run_generic(emitted, arrays, scalars=(), launch_range=None, sm_count=4):
             h.update(fh.read())
     base = os.path.join(_BUILD, 'emugen_%s_%s' % (emitted.name[:32], h.hexdigest()[:12]))
     if not os.path.exists(base + '.so'):
-        with open(base + '.cpp', 'w') as fh:
+        with open(base + '.%d.cpp' % os.getpid(), 'w') as fh:
             fh.write(emitted.source)
             with open(os.path.join(_SHIM_GENERIC, 'driver.inc')) as inc:
                 fh.write('\n' + inc.read())
         subprocess.check_call(['g++', '-std=c++17', '-O1', '-ffp-contract=off', '-mfma', '-fPIC', '-shared', '-w',
                                '-DPSAD_EMU_KERNEL=' + emitted.name, '-I', _SHIM_GENERIC, '-I', runtime.KERNEL_DIR,
-                               '-o', base + '.so.tmp', base + '.cpp'])
-        os.replace(base + '.so.tmp', base + '.so')
+                               '-o', base + '.so.tmp%d' % os.getpid(), base + '.%d.cpp' % os.getpid()])
+        os.replace(base + '.so.tmp%d' % os.getpid(), base + '.so')
     so = ctypes.CDLL(base + '.so')
     so.psad_emulate_generic.argtypes = [ctypes.c_void_p] + [ctypes.c_uint] * 4
     rc = so.psad_emulate_generic(args, grid[0], grid[1], grid[2], emitted.plan['threads'])

@@ -60,4 +60,35 @@ def test_fused_steps_sharded_equals_unsharded(name, bh):
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [l for l in out.stdout.splitlines() if l.startswith('[rank')]
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert len(lines) == 2 * world and all('IDENTICAL' in l for l in lines)
+    assert len(lines) == 3 * world and all('IDENTICAL' in l for l in lines)
+
+
+@pytest.mark.parametrize('make, tol', [(heat3d_op, 1e-6), (stencil27_op, 1e-12)])
+def test_slab_autograd_function_on_one_rank(make, tol):
+    """``create_slab_autograd_function`` with a single rank and one ghost plane per side: a chain of two steps equals the
+    plain torch_native Function bit for bit (outputs and gradients) and the oracle within tolerance; chained steps reuse
+    the padded buffers."""
+    import torch
+    from pystencils_autodiff_b200.datahandling import create_slab_autograd_function
+    shape = (12, 30, 124)
+    op = make(shape=shape, boundary_handling='zeros')
+    dt = op.forward_ast_gpu.input_fields[0].dtype.numpy_dtype
+    rng = np.random.default_rng(9)
+    U, R = rng.standard_normal(shape).astype(dt), rng.standard_normal(shape).astype(dt)
+    dh = SlabDataHandling(shape, 0, 1, 1, 'cuda')
+    Step = create_slab_autograd_function(op, dh)
+    Plain = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    grads, outs = [], []
+    for F in (Step, Plain):
+        u = torch.from_numpy(U).cuda().requires_grad_(True)
+        (o1,) = F.apply(u)
+        (o2,) = F.apply(o1)
+        (o2 * torch.from_numpy(R).cuda()).sum().backward()
+        outs.append(o2.detach())
+        grads.append(u.grad)
+        if F is Step:
+            assert o1._base is not None and o1._base.shape[0] == shape[0] + 2
+    assert torch.equal(outs[0], outs[1]) and torch.equal(grads[0], grads[1])
+    r1 = evaluate(op.forward_assignments, {'u': U.astype(np.float64)}, 'zeros')['out']
+    r2 = evaluate(op.forward_assignments, {'u': r1}, 'zeros')['out']
+    assert np.abs(outs[0].cpu().numpy() - r2).max() <= tol * max(1.0, np.abs(r2).max())

@@ -15,6 +15,27 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _collect(procs, q, world, timeout=600):
+    """Results of all workers; fails as soon as one of them has died instead of waiting for the queue to time out."""
+    import queue as _queue
+    import time
+    results, t0 = [], time.time()
+    while len(results) < world:
+        try:
+            results.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError('worker exit codes %s after %.0f s' % ([p.exitcode for p in procs], time.time() - t0))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return results
+
+
 def _worker(rank, world, port, name, bh, q):
     sys.path.insert(0, ROOT)
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -201,10 +222,7 @@ def test_run_steps_fused_on_slabs(bh, world, steps):
     procs = [ctx.Process(target=_steps_worker, args=(r, world, port, bh, steps, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    results = _collect(procs, q, world)
     sys.path.insert(0, ROOT)
     from oracle import evaluate
     from pystencils_autodiff_b200 import configs
@@ -341,3 +359,91 @@ def test_reference_constructor_aliases():
         GraphDataHandling((10, 15), periodicity=True, device='cpu')
     with pytest.raises(NotImplementedError):
         GraphDataHandling((10, 15), default_target='cpu', device='cpu')
+
+
+def _autograd_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import sympy as sp
+        import pystencils_autodiff_b200 as ps
+        from oracle import evaluate, forward_backward
+        from pystencils_autodiff_b200 import configs
+        from pystencils_autodiff_b200.datahandling import SlabDataHandling, create_slab_autograd_function
+        from replay_kernels import ReplayKernel
+        res = {}
+        # ---- A: two chained steps of the 7-point stencil (fp32, march kernels), loss = sum(out2 * r) ----------------------
+        gshape = (6 * world, 10, 132)
+        n = gshape[0] // world
+        sl = slice(rank * n, (rank + 1) * n)
+        rng = np.random.default_rng(8)
+        U = rng.standard_normal(gshape).astype(np.float32)
+        R = rng.standard_normal(gshape).astype(np.float32)
+        dh = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch')
+        op_l = configs.heat3d_op(shape=(n,) + gshape[1:], boundary_handling='zeros')
+        Step = create_slab_autograd_function(op_l, dh, kernel_class=ReplayKernel)
+        u = torch.from_numpy(U[sl].copy()).requires_grad_(True)
+        del ReplayKernel.launches[:]
+        (o1,) = Step.apply(u)
+        (o2,) = Step.apply(o1)
+        assert o1._base is not None and o1._base.shape[0] == n + 2          # outputs are views of padded buffers
+        (o2 * torch.from_numpy(R[sl])).sum().backward()
+        assert all('march' in name for name in ReplayKernel.launches) and len(ReplayKernel.launches) == 4 * 2
+        op_g = configs.heat3d_op(shape=gshape, boundary_handling='zeros')
+        r1 = evaluate(op_g.forward_assignments, {'u': U.astype(np.float64)}, 'zeros')['out']
+        r2 = evaluate(op_g.forward_assignments, {'u': r1}, 'zeros')['out']
+        d2 = evaluate(op_g.backward_assignments, {'diffout': R.astype(np.float64)}, 'zeros')['diffu']
+        d1 = evaluate(op_g.backward_assignments, {'diffout': d2}, 'zeros')['diffu']
+        res['chain_out'] = float(np.abs(o2.detach().numpy() - r2[sl]).max())
+        res['chain_grad'] = float(np.abs(u.grad.numpy() - d1[sl]).max())
+        kinds = [c[0] for c in dh.call_queue]
+        assert kinds.count('Communication') == 4 and kinds.count('KernelCall') == 4
+        # ---- B: two inputs, non-linear, offsets along dim 0 on both, one constant field (fp64, generic kernels) ---------
+        gshape = (5 * world, 6, 7)
+        n = gshape[0] // world
+        sl = slice(rank * n, (rank + 1) * n)
+
+        def make(shape, consts=True):
+            a, b, c, out = ps.fields('a, b, c, out: float64[%d,%d,%d]' % shape)
+            asg = ps.AssignmentCollection({out.center: a[1, 0, 0] * b[0, 0, 0] + sp.sin(a[0, -1, 0]) + 0.3 * b[-1, 0, 1] * c[0, 0, 0]})
+            return ps.AutoDiffOp(asg, op_name='nl', boundary_handling='zeros', constant_fields=[c] if consts else [])
+        op_l, op_g = make((n,) + gshape[1:]), make(gshape)
+        ins = {k: rng.uniform(0.5, 1.5, gshape) for k in 'abc'}
+        G = rng.standard_normal(gshape)
+        dh2 = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch')
+        F = create_slab_autograd_function(op_l, dh2, kernel_class=ReplayKernel)
+        tens = [torch.from_numpy(ins[f.name][sl].copy()).requires_grad_(f.name != 'c') for f in op_l.forward_input_fields]
+        (out,) = F.apply(*tens)
+        out.backward(torch.from_numpy(G[sl].copy()))
+        ref_out, ref_grads = forward_backward(op_g, ins, {'out': G})
+        res['nl_out'] = float(np.abs(out.detach().numpy() - ref_out['out'][sl]).max())
+        for f, t in zip(op_l.forward_input_fields, tens):
+            if f.name == 'c':
+                assert t.grad is None
+            else:
+                res['nl_d' + f.name] = float(np.abs(t.grad.numpy() - ref_grads['diff' + f.name][sl]).max())
+        with pytest.raises(ValueError, match='owned planes'):
+            F.apply(*[torch.zeros((n + 1,) + gshape[1:], dtype=torch.float64)] * 3)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_autograd_function_two_ranks():
+    """``create_slab_autograd_function`` (SURVEY.md §8e "Autograd"): forward = halo exchange + forward kernel on the owned
+    planes, backward = the same exchange on the upstream gradient + the adjoint kernel; chained steps reuse the padded
+    buffers.  Two gloo ranks, emitted kernels replayed on the CPU, compared with the oracle on the GLOBAL field."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_autograd_worker, args=(r, world, 29877, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(_collect(procs, q, world))
+    for r in range(world):
+        assert results[r]['chain_out'] < 2e-6 and results[r]['chain_grad'] < 2e-6, results[r]
+        for k in ('nl_out', 'nl_da', 'nl_db'):
+            assert results[r][k] < 1e-12, (r, k, results[r])
