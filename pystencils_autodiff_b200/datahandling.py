@@ -212,11 +212,18 @@ class SlabDataHandling:
         self.cpu_arrays = OrderedDict()
         self.fields = OrderedDict()
         self.call_queue = []
+        self._swap_count = 0
         self._replicated = set()       # arrays with their own spatial shape: whole on every rank, no ghost planes
         self._range_cache = {}
         self._comm_stream = None
         self._ev_ready = None
         self._ev_halo = None
+
+    max_recorded_calls = 1 << 16      # the reference records without bound; a long-running time loop must not leak
+
+    def _record(self, entry):
+        if len(self.call_queue) < self.max_recorded_calls:
+            self.call_queue.append(entry)
 
     # -- arrays ------------------------------------------------------------------------------------------------
     @property
@@ -261,7 +268,7 @@ class SlabDataHandling:
         return self.add_array(name, dtype=np.dtype(str(t.dtype).replace('torch.', '')))
 
     def fill(self, array_name, val, **_):
-        self.call_queue.append(('Fill', array_name))        # graph_datahandling.py:324-327 records 'Fill <name>'
+        self._record(('Fill', array_name))        # graph_datahandling.py:324-327 records 'Fill <name>'
         self.owned(array_name)[...] = val
 
     def require_autograd(self, bool_val, *names):
@@ -276,7 +283,7 @@ class SlabDataHandling:
         """The registered tensor of a field (graph_datahandling.py:352-355 records a ``GhostTensorExtraction`` marker
         and returns nothing); ghost planes stripped unless asked for."""
         name = field if isinstance(field, str) else field.name
-        self.call_queue.append(('GhostTensorExtraction', name, bool(on_gpu), bool(with_ghost_layers)))
+        self._record(('GhostTensorExtraction', name, bool(on_gpu), bool(with_ghost_layers)))
         t = (self.gpu_arrays if on_gpu else self.cpu_arrays)[name]
         return t if with_ghost_layers or name in self._replicated else t[self.dec.owned]
 
@@ -286,7 +293,7 @@ class SlabDataHandling:
         if isinstance(fields, str) or not hasattr(fields, '__iter__'):
             fields = [fields]
         names = [f if isinstance(f, str) else f.name for f in fields]
-        self.call_queue.append(('FieldOutput', tuple(names), output_path, flag_field))
+        self._record(('FieldOutput', tuple(names), output_path, flag_field))
         np.savez('%s.rank%d.npz' % (output_path, self.dec.rank),
                  **{n: self.owned(n).detach().cpu().numpy() for n in names})
 
@@ -320,12 +327,12 @@ class SlabDataHandling:
 
     # -- host mirrors (reference: GraphDataHandling.to_cpu / to_gpu record a DataTransfer, graph_datahandling.py:255-282)
     def to_cpu(self, name):
-        self.call_queue.append(('DataTransfer', name, 'DEVICE_TO_HOST'))
+        self._record(('DataTransfer', name, 'DEVICE_TO_HOST'))
         self.cpu_arrays[name] = self.gpu_arrays[name].detach().to('cpu', copy=True)
         return self.cpu_arrays[name]
 
     def to_gpu(self, name):
-        self.call_queue.append(('DataTransfer', name, 'HOST_TO_DEVICE'))
+        self._record(('DataTransfer', name, 'HOST_TO_DEVICE'))
         if name not in self.cpu_arrays:
             raise KeyError('no host copy of %r: call to_cpu(%r) first or fill cpu_arrays[%r]' % (name, name, name))
         self.gpu_arrays[name].copy_(self.cpu_arrays[name])
@@ -339,7 +346,8 @@ class SlabDataHandling:
             self.to_gpu(n)
 
     def swap(self, name1, name2, gpu=True):
-        self.call_queue.append(('Swap', name1, name2))
+        self._record(('Swap', name1, name2))
+        self._swap_count += 1
         self.gpu_arrays[name1], self.gpu_arrays[name2] = self.gpu_arrays[name2], self.gpu_arrays[name1]
 
     def gather_array(self, name):
@@ -376,7 +384,7 @@ class SlabDataHandling:
 
         def sync():
             for n in names:
-                self.call_queue.append(('Communication', n, stencil, target == 'gpu'))
+                self._record(('Communication', n, stencil, target == 'gpu'))
                 self.start_exchange(n)
             self.finish_exchange()
         return sync
@@ -430,13 +438,13 @@ class SlabDataHandling:
             if callable(kernel) and self.dec.world_size == 1:
                 # any other callable gets every registered array by name, like PyTorchDataHandling.run_kernel
                 # (framework_integration/datahandling.py:185-188); it cannot be split into slab launches
-                self.call_queue.append(('KernelCall', getattr(kernel, '__name__', type(kernel).__name__)))
+                self._record(('KernelCall', getattr(kernel, '__name__', type(kernel).__name__)))
                 return kernel(**{n: self.owned(n) for n in self.gpu_arrays}, **kwargs)
             raise TypeError('run_kernel expects a CompiledKernel (AutoDiffOp.forward_kernel_gpu / backward_kernel_gpu) or '
                             'the Function class of a torch_native op; arbitrary callables only on a single rank')
         if fused_steps not in (1, 2):
             raise ValueError('fused_steps must be 1 or 2')
-        self.call_queue.append(('KernelCall', kernel.function_name) if fused_steps == 1 else
+        self._record(('KernelCall', kernel.function_name) if fused_steps == 1 else
                                ('KernelCall', kernel.function_name, fused_steps))
         arrays = {f.name: self.gpu_arrays[f.name] for f in kernel.fields}
         replicated = [n for n in arrays if n in self._replicated]
@@ -465,7 +473,7 @@ class SlabDataHandling:
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
         for n in halo_fields:
-            self.call_queue.append(('Communication', n, None, True))
+            self._record(('Communication', n, None, True))
             self.start_exchange(n)
         side = [r for r in (lo, hi) if r is not None]
         on_comm = bool(side) and self._comm_stream is not None and all(t.is_cuda for t in arrays.values())
@@ -725,10 +733,10 @@ class TimeLoop:
         if graph_ok and time_steps >= 4:
             # warm up (NVRTC / module load must not happen during capture), then capture TWO steps: a step that
             # swaps buffers is only periodic with period 2
-            n0 = len([c for c in self.dh.call_queue if c[0] == 'Swap'])
+            n0 = self.dh._swap_count
             self._one_step()
             self._one_step()
-            swaps_per_step = (len([c for c in self.dh.call_queue if c[0] == 'Swap']) - n0) // 2
+            swaps_per_step = (self.dh._swap_count - n0) // 2
             done = 2
             if self._graph is None:
                 stream = torch.cuda.Stream(self.dh.device)
