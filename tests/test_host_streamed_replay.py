@@ -1,0 +1,46 @@
+"""``HostStreamedOp`` (bench.py's ``e2e`` leg at N = 1: host-resident fields streamed through the GPU in chunks of planes on
+three streams) executed on CPU tensors: stand-in streams / events (tests/fake_cuda.py), the emitted kernels replayed as
+the launches (tests/replay_kernels.py).  Checks the chunk / halo / launch-range bookkeeping against the oracle on the
+whole field; the GPU suite checks the real thing (tests/test_gpu_parity.py::test_host_streamed_equals_resident)."""
+import numpy as np
+import pytest
+import torch
+
+from fake_cuda import fake_cuda
+from oracle import forward_backward
+from pystencils_autodiff_b200 import configs
+from pystencils_autodiff_b200.datahandling import HostStreamedOp
+from replay_kernels import ReplayKernel
+
+
+@pytest.mark.parametrize('make, shape, bh, chunk, tol', [
+    (configs.heat3d_op, (23, 10, 132), 'zeros', 6, 2e-6),         # 4 chunks, the last one partial, ring of 3 buffers reused
+    (configs.heat3d_op, (17, 10, 132), None, 5, 2e-6),            # interior iteration: global border clipped per chunk
+    (configs.stencil27_op, (11, 9, 36), 'zeros', 4, 1e-13),
+    (configs.tv_gradient_op, (5, 12, 36), 'zeros', 2, 2e-5),      # no reach along dim 0: chunks without ghost planes
+])
+def test_host_streamed_chunks_equal_whole_field(make, shape, bh, chunk, tol):
+    op = make(shape=shape, boundary_handling=bh)
+    rng = np.random.default_rng(3)
+    ins = {f.name: rng.uniform(0.1, 1.0, shape).astype(f.dtype.numpy_dtype) for f in op.forward_input_fields}
+    grads = {f.name: rng.standard_normal(shape).astype(f.dtype.numpy_dtype) for f in op.forward_output_fields}
+    with fake_cuda():
+        streamed = HostStreamedOp(op, shape, device='cpu', chunk_planes=chunk, stages=3)
+        streamed.fwd, streamed.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
+        assert streamed.n_chunks == -(-shape[0] // chunk)
+        host_in = {n: torch.from_numpy(ins[n]) for n in ins}
+        host_in.update({'diff' + n: torch.from_numpy(g) for n, g in grads.items()})
+        host_out = {n: torch.full(shape, float('nan'), dtype=host_in[next(iter(ins))].dtype) for n in streamed.output_names}
+        assert sorted(host_in) == sorted(streamed.input_names)
+        streamed(host_in, host_out)
+    ref_out, ref_grads = forward_backward(op, ins, grads)
+    for name, ref in list(ref_out.items()) + list(ref_grads.items()):
+        got = host_out[name].numpy()
+        assert np.isfinite(got).all(), name
+        assert np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max()), name
+    g = streamed.g
+    planes_up = sum(min(shape[0], k * chunk + min(chunk, shape[0] - k * chunk) + g) - max(0, k * chunk - g)
+                    for k in range(streamed.n_chunks))
+    per_plane = int(np.prod(shape[1:])) * host_in[next(iter(ins))].element_size()
+    assert streamed.h2d_bytes == planes_up * per_plane * len(streamed.input_names)
+    assert streamed.d2h_bytes == shape[0] * per_plane * len(streamed.output_names)

@@ -447,3 +447,49 @@ def test_slab_autograd_function_two_ranks():
         assert results[r]['chain_out'] < 2e-6 and results[r]['chain_grad'] < 2e-6, results[r]
         for k in ('nl_out', 'nl_da', 'nl_db'):
             assert results[r][k] < 1e-12, (r, k, results[r])
+
+
+def _e2e_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from fake_cuda import fake_cuda
+        from oracle import evaluate
+        from pystencils_autodiff_b200 import configs
+        from pystencils_autodiff_b200.datahandling import SlabStencilOp
+        from replay_kernels import ReplayKernel
+        local = (6, 10, 132)
+        gshape = (local[0] * world,) + local[1:]
+        op = configs.heat3d_op(shape=local, boundary_handling='zeros')
+        with fake_cuda():
+            slab = SlabStencilOp(op, local, rank, world, device='cpu', backend='torch')
+            slab.fwd, slab.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
+            r = slab.end_to_end(2, dist.barrier)
+        cells = int(np.prod(local))
+        assert r['ms_per_step'] > 0 and r['h2d'] == 2 * 4 * cells and r['d2h'] == 2 * 4 * cells
+        # what the last step left on the "device": forward and adjoint of the uploaded (synthetic) host data
+        got = {n: slab.dh.gather_array(n) for n in ('u', 'out', 'diffout', 'diffu')}
+        op_g = configs.heat3d_op(shape=gshape, boundary_handling='zeros')
+        ref_out = evaluate(op_g.forward_assignments, {'u': got['u'].astype(np.float64)}, 'zeros')['out']
+        ref_du = evaluate(op_g.backward_assignments, {'diffout': got['diffout'].astype(np.float64)}, 'zeros')['diffu']
+        scale = max(np.abs(ref_out).max(), np.abs(ref_du).max(), 1e-300)
+        assert np.abs(got['u']).max() > 0
+        q.put((rank, float(np.abs(got['out'] - ref_out).max() / scale), float(np.abs(got['diffu'] - ref_du).max() / scale)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_end_to_end_leg_with_host_buffers_two_ranks():
+    """``SlabStencilOp.end_to_end`` at N > 1 (bench.py's ``e2e`` leg: upload / compute / download streams) executed on CPU
+    tensors with stand-in streams and events (tests/fake_cuda.py) and replayed kernels, two gloo ranks."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_e2e_worker, args=(r, world, 29891, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for rank, e_out, e_du in _collect(procs, q, world):
+        assert e_out < 1e-6 and e_du < 1e-6, (rank, e_out, e_du)
