@@ -148,32 +148,11 @@ def test_data_handling_registry_and_call_queue_single_rank():
 
 
 def _replay_kernel_class():
-    """``CompiledKernel`` whose launch is the CPU replay of the emitted kernel (tests/march_emulator.py) on CPU tensors:
-    the instance selection mirrors ``CompiledKernel.__call__``, the parameter block comes from ``psad_plan_launch``."""
+    """The shared ``ReplayKernel`` (tests/replay_kernels.py: the launch is a CPU replay of the emitted kernel) and the
+    emulator module."""
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import march_emulator as emu
-    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
-
-    class ReplayKernel(CompiledKernel):
-        launches = None
-
-        def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
-            nd = self.ir.ndim
-            arrays = [kwargs[f.name].numpy() for f in self.fields]
-            scal = [float(kwargs[s_]) for s_ in self.scalars]
-            if _variant == 'march_x2':
-                ek = self.emitted('march_x2')
-            else:
-                if _range is not None:
-                    same = (list(_range['iter_lo'][:nd]) == list(_range['write_lo'][:nd]) and
-                            list(_range['iter_hi'][:nd]) == list(_range['write_hi'][:nd]))
-                else:
-                    same = self.ir.boundary == 'zeros' or self.ir.ghost_layers == 0
-                ek = self._emitted['march_nomask' if same else 'march']
-            type(self).launches.append(ek.name)
-            emu.run(ek, arrays, scal, launch_range=_range)
-
-    ReplayKernel.launches = []
+    from replay_kernels import ReplayKernel
     return ReplayKernel, emu
 
 
