@@ -472,3 +472,43 @@ def test_end_to_end_leg_with_host_buffers_two_ranks():
         p.start()
     for rank, e_out, e_du in _collect(procs, q, world):
         assert e_out < 1e-6 and e_du < 1e-6, (rank, e_out, e_du)
+
+
+def test_slab_ranges_cover_the_owned_planes_exactly_once():
+    """Pure index logic over many decompositions: the interior / lo / hi write ranges tile the owned planes exactly once
+    (single steps and fused pairs), iteration ranges stay inside the local array, and — fused pairs — contain every
+    written plane that belongs to the global iteration space."""
+    import itertools
+    from pystencils_autodiff_b200.datahandling import slab_ranges
+    checked = 0
+    for N, world, halo, steps, boundary in itertools.product([12, 17, 40], [1, 2, 3, 4], [1, 2], [1, 2], ['zeros', 'none']):
+        g = steps * halo
+        base, rem = divmod(N, world)
+        counts = [base + (1 if r < rem else 0) for r in range(world)]
+        if world > 1 and min(counts) < 2 * g:
+            continue
+        for rank in range(world):
+            start, n = sum(counts[:rank]), counts[rank]
+            parts = slab_ranges((N, 9, 11), start, n, g, rank > 0, rank < world - 1, boundary, halo, 3,
+                                steps=steps, halo=halo if steps > 1 else None)
+            cover = np.zeros(n + 2 * g, dtype=int)
+            for p in parts:
+                if p is None:
+                    continue
+                cover[p['write_lo'][0]:p['write_hi'][0]] += 1
+                assert p['write_lo'][1:] == [0, 0] and p['write_hi'][1:] == [9, 11]
+                assert 0 <= p['iter_lo'][0] <= p['iter_hi'][0] <= n + 2 * g
+                if steps > 1:
+                    dom_lo, dom_hi = (halo, N - halo) if boundary == 'none' else (0, N)
+                    for z in range(p['write_lo'][0], p['write_hi'][0]):
+                        inside = dom_lo <= z - g + start < dom_hi
+                        assert (p['iter_lo'][0] <= z < p['iter_hi'][0]) == inside
+            assert list(cover) == [0] * g + [1] * n + [0] * g, (N, world, halo, steps, boundary, rank)
+            interior = parts[0]
+            if interior is not None and steps > 1 and world > 1:
+                # planes of the interior launch depend on no ghost plane
+                lo_dep = interior['write_lo'][0] - steps * halo
+                hi_dep = interior['write_hi'][0] + steps * halo
+                assert lo_dep >= (g if rank > 0 else 0) and hi_dep <= n + g + (0 if rank < world - 1 else g)
+            checked += 1
+    assert checked > 100
