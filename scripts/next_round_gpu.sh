@@ -25,8 +25,11 @@ for w in c3 c4 c2 c5; do
   python bench.py --workload $w --steps 50 --warmup 5 > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err; echo "bench $w rc=$?"
 done
 # 3. fused-pair candidates: two CTAs per SM so that one CTA's per-plane barrier does not idle the SM
-python scripts/steps_bench.py c3 "0,0,0,0;2,14,4,0,1,2;2,22,4,0,1,2;2,30,4,0,1" c4 "0,0,0,0;2,14,2,0,1,2;2,14,2,0,0,2;2,10,2,0,1,3" \
-    c2 > gpurun_out/r2_steps_bench.log 2>&1; echo "steps_bench rc=$?"
+#    (all of these emit, compile without local memory beyond a few spill bytes, and sit in the in-tree cubin cache)
+python scripts/steps_bench.py \
+    c3 "0,0,0,0;2,14,4,0,1,2;2,18,4,0,1,2;2,22,4,0,1,2;4,20,4,0,1,2;4,28,4,0,1,2;2,30,4,0,1;3,33,4,0,1;4,36,4,0,1;4,40,4,0,1;4,44,4,2,1;4,44,4,4,1" \
+    c4 "0,0,0,0;2,14,2,0,1,2;2,14,2,0,0,2;2,10,2,0,1,3;2,18,2,0,1,2;2,22,2,3,0;2,22,2,5,0" \
+    c2 "0,0,0,0;2,30,4,0,1;2,14,4,0,1,2" > gpurun_out/r2_steps_bench.log 2>&1; echo "steps_bench rc=$?"
 # 4. time loop on one slab with ghost planes: ranged fused launches against ranged single steps
 python scripts/slab_steps_bench.py c3 8 > gpurun_out/r2_slab_steps_c3_n1.json 2> gpurun_out/r2_slab_steps_c3_n1.err; echo "slab steps rc=$?"
 # 5. ncu of the exchange variant of the fused pair (after its plain run above exited 0)
