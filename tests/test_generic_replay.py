@@ -80,3 +80,30 @@ def test_generic_kernel_one_dimensional_and_index_dimension():
     emu.run_generic(ek, [C if f.name == 'c' else U for f in ek.fields])
     ref = evaluate(op.forward_assignments, {'u': U}, 'zeros')['c']
     np.testing.assert_allclose(C, ref, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_random_stencils_generic_replay(seed):
+    """Every random stencil of the GPU fuzz test (tests/test_gpu_fuzz.py) through the GENERIC kernels on the CPU: several
+    inputs and outputs, offsets up to +-4, non-linear terms, both boundary modes, fp32 / fp64, 2-D / 3-D."""
+    import pystencils_autodiff_b200 as ps
+    from stencil_fuzz import random_stencil
+    asg, bh, shape, dtype = random_stencil(seed)
+    op = ps.AutoDiffOp(asg, boundary_handling=bh, op_name='fuzz%d' % seed)
+    rng = np.random.default_rng(seed)
+    tol = 2e-5 if dtype == 'float32' else 1e-11
+    for collection, ir in ((op.forward_assignments, op.forward_ast_gpu), (op.backward_assignments, op.backward_ast_gpu)):
+        ek = emit_generic(ir)
+        arrays, named = [], {}
+        for f in ek.fields:
+            a = np.full(shape, np.nan, dtype=f.dtype.numpy_dtype)
+            if f in ir.input_fields:
+                a[...] = rng.uniform(-1, 1, size=shape)
+            arrays.append(a)
+            named[f.name] = a
+        emu.run_generic(ek, arrays)
+        ref = evaluate(collection, {f.name: named[f.name].copy() for f in ir.input_fields}, bh)
+        for f in ir.output_fields:
+            scale = max(1.0, np.abs(ref[f.name]).max())
+            assert np.isfinite(named[f.name]).all(), (seed, f.name)
+            assert np.abs(named[f.name] - ref[f.name]).max() <= tol * scale, (seed, f.name)
