@@ -420,6 +420,19 @@ class AutoDiffOp:
         from .backends._torch_native import create_unrolled_function
         return create_unrolled_function(self, steps, op_name=op_name, tuning=tuning)
 
+    def create_slab_torch_op(self, data_handling, **kwargs):
+        """``Function`` of this op on one rank's slab of slab-decomposed fields (halo exchange in forward and on the
+        upstream gradient in backward); see ``datahandling.create_slab_autograd_function``.  Not part of the reference
+        API, which has no distributed path."""
+        from .datahandling import create_slab_autograd_function
+        return create_slab_autograd_function(self, data_handling, **kwargs)
+
+    def create_slab_unrolled_torch_op(self, data_handling, steps, fuse=None, **kwargs):
+        """``steps`` unrolled steps of this one-field linear stencil on one rank's slab as one ``Function``; see
+        ``datahandling.create_slab_unrolled_function``."""
+        from .datahandling import create_slab_unrolled_function
+        return create_slab_unrolled_function(self, data_handling, steps, fuse=fuse, **kwargs)
+
     def create_tensorflow_op(self, inputfield_tensor_dict={}, forward_loop=None, backward_loop=None,
                              use_cuda=True, backend='tensorflow'):
         """Same dispatch signature as the reference (:611-616); only ``backend='torch_native', use_cuda=True`` exists."""

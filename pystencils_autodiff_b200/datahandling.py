@@ -29,7 +29,7 @@ from . import runtime
 from .backends._torch_native import CompiledKernel, numpy_dtype_to_torch
 
 __all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataHandling', 'PyTorchDataHandling',
-           'create_slab_autograd_function',
+           'create_slab_autograd_function', 'create_slab_unrolled_function',
            'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
 
 
@@ -515,6 +515,75 @@ class SlabDataHandling:
         return self.gpu_arrays[fin]
 
 
+class _SlabTensors:
+    """Padded slab buffers of one data handling (``g`` ghost planes on each side of the ``n`` owned planes) for the slab
+    autograd Functions: allocation, recognition of tensors that already are the owned part of such a buffer, and kernel
+    launches on explicitly given buffers."""
+
+    def __init__(self, data_handling):
+        import weakref
+        self.dh = data_handling
+        self.g, self.n = data_handling.dec.g, data_handling.dec.n_local
+        self.ours = weakref.WeakValueDictionary()    # id -> buffer allocated here: its ghost planes are ours to write
+
+    def new_padded(self, dtype, like, zero):
+        torch = self.dh.torch
+        g, n = self.g, self.n
+        t = (torch.zeros if zero else torch.empty)((n + 2 * g,) + tuple(like.shape[1:]), dtype=dtype, device=like.device)
+        if not zero and g:
+            t[:g].zero_()             # ghost planes at the global border are never received: they must read as 0
+            t[g + n:].zero_()
+        self.ours[id(t)] = t
+        return t
+
+    def padded_of(self, t, dtype, what):
+        """The padded buffer ``t`` is the owned part of, else a fresh one holding a copy of ``t``."""
+        g, n = self.g, self.n
+        if t.shape[0] != n:
+            raise ValueError('%s: expected this rank\'s %d owned planes, got shape %s' % (what, n, tuple(t.shape)))
+        if t.dtype != dtype:
+            raise TypeError('%s expects dtype %s, got %s' % (what, dtype, t.dtype))
+        base = t._base
+        if (base is not None and base.dim() == t.dim() and base.shape[0] == n + 2 * g and base.is_contiguous()
+                and t.stride() == base.stride() and t.storage_offset() == base.storage_offset() + g * base.stride(0)
+                and (self.ours.get(id(base)) is base or any(base is a for a in self.dh.gpu_arrays.values()))):
+            return base
+        p = self.new_padded(dtype, t, zero=False)
+        p[g:g + n].copy_(t.detach())
+        return p
+
+    def owned(self, padded):
+        return padded[self.g:self.g + self.n]
+
+    def launch(self, kernel, arrays, halo, scalars, fused_steps=1):
+        dh = self.dh
+        arrays = {k: v for k, v in arrays.items() if k in {f.name for f in kernel.fields}}
+        keep = {k: dh.gpu_arrays.get(k) for k in arrays}
+        dh.gpu_arrays.update(arrays)                 # run_kernel looks its fields up by name at call time
+        try:
+            dh.run_kernel(kernel, halo_fields=[h for h in halo if h in arrays], fused_steps=fused_steps,
+                          **{k: v for k, v in scalars.items() if k in kernel.scalars})
+        finally:
+            for k, v in keep.items():
+                if v is None:
+                    dh.gpu_arrays.pop(k, None)
+                else:
+                    dh.gpu_arrays[k] = v
+
+
+def _slab_tensors(data_handling):
+    if getattr(data_handling, '_slab_tensor_pool', None) is None:
+        data_handling._slab_tensor_pool = _SlabTensors(data_handling)      # shared by every Function of this data handling
+    return data_handling._slab_tensor_pool
+
+
+def _check_scalars(kernels, scalars):
+    for kern in kernels:
+        missing = [s_ for s_ in kern.scalars if s_ not in scalars]
+        if missing:
+            raise TypeError('%s: missing scalar argument(s) %s (pass scalars={...})' % (kern.function_name, missing))
+
+
 def create_slab_autograd_function(op, data_handling, op_name=None, tuning=None, scalars=None, kernel_class=None):
     """``torch.autograd.Function`` of an ``AutoDiffOp`` on THIS RANK'S SLAB of slab-decomposed fields: the
     sharded counterpart of ``op.create_tensorflow_op(backend='torch_native')`` with the same calling convention
@@ -528,23 +597,21 @@ def create_slab_autograd_function(op, data_handling, op_name=None, tuning=None, 
     across ranks.
 
     Slab tensors live inside padded buffers (``g`` ghost planes per side).  Outputs and gradients are returned as views
-    of such buffers, and a tensor that already is such a view (an output of this Function, ``data_handling.owned(name)``)
-    is used in place, so chained steps copy nothing; any other tensor is copied into a fresh padded buffer once.
+    of such buffers, and a tensor that already is such a view (an output of a slab Function of the same data handling,
+    ``data_handling.owned(name)``) is used in place, so chained steps copy nothing; any other tensor is copied into a
+    fresh padded buffer once.
 
     ``kernel_class``: the ``CompiledKernel`` subclass that launches (tests replay the emitted kernels on the CPU)."""
-    import weakref
     import torch
     dh = data_handling
     dec = dh.dec
-    g, n = dec.g, dec.n_local
+    g = dec.g
+    pool = _slab_tensors(dh)
     KC = kernel_class or CompiledKernel
     fwd_ir, bwd_ir = op.forward_ast_gpu, op.backward_ast_gpu
     fwd_k, bwd_k = KC(fwd_ir, tuning), KC(bwd_ir, tuning)
     scalars = dict(scalars or {})
-    for kern in (fwd_k, bwd_k):
-        missing = [s_ for s_ in kern.scalars if s_ not in scalars]
-        if missing:
-            raise TypeError('%s: missing scalar argument(s) %s (pass scalars={...})' % (kern.function_name, missing))
+    _check_scalars((fwd_k, bwd_k), scalars)
     fwd_inputs, fwd_outputs = list(op.forward_input_fields), list(op.forward_output_fields)
     bwd_outputs = {f.name: f for f in op.backward_output_fields}
     fields = {f.name: f for f in list(op.forward_fields) + list(op.backward_fields)}
@@ -565,64 +632,30 @@ def create_slab_autograd_function(op, data_handling, op_name=None, tuning=None, 
     bwd_halo = [f.name for f in bwd_ir.input_fields if sharded and reach(bwd_ir, f.name) > 0 and f.name not in fwd_halo]
     fwd_reads = {f.name for f in fwd_ir.input_fields}
     bwd_reads = {f.name for f in bwd_ir.input_fields}
-    ours = weakref.WeakValueDictionary()    # id -> padded buffer allocated here: its ghost planes are ours to write
 
-    def tail(f):
-        return tuple(int(v) for v in f.index_shape) if f.index_dimensions else ()
+    def tdtype(f):
+        return numpy_dtype_to_torch(f.dtype.numpy_dtype)
 
-    def new_padded(f, like, zero):
-        shape = (n + 2 * g,) + tuple(like.shape[1:])
-        t = (torch.zeros if zero else torch.empty)(shape, dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=like.device)
-        if not zero and g:
-            t[:g].zero_()             # ghost planes at the global border are never received: they must read as 0
-            t[g + n:].zero_()
-        ours[id(t)] = t
-        return t
-
-    def padded_of(t, f):
-        """The padded buffer ``t`` is the owned part of, else a fresh one holding a copy of ``t``."""
-        if t.shape[0] != n:
-            raise ValueError('%s: expected this rank\'s %d owned planes of %r, got shape %s'
-                             % (op.op_name, n, f.name, tuple(t.shape)))
-        want = numpy_dtype_to_torch(f.dtype.numpy_dtype)
-        if t.dtype != want:
-            raise TypeError('%s: field %r expects dtype %s, got %s' % (op.op_name, f.name, want, t.dtype))
-        base = t._base
-        if (base is not None and base.dim() == t.dim() and base.shape[0] == n + 2 * g and base.is_contiguous()
-                and t.stride() == base.stride() and t.storage_offset() == base.storage_offset() + g * base.stride(0)
-                and (ours.get(id(base)) is base or any(base is a for a in dh.gpu_arrays.values()))):
-            return base
-        p = new_padded(f, t, zero=False)
-        p[g:g + n].copy_(t.detach())
-        return p
-
-    def launch(kernel, arrays, halo):
-        keep = {k: dh.gpu_arrays.get(k) for k in arrays}
-        dh.gpu_arrays.update(arrays)                 # run_kernel looks its fields up by name at call time
-        try:
-            dh.run_kernel(kernel, halo_fields=halo, **{k: v for k, v in scalars.items() if k in kernel.scalars})
-        finally:
-            for k, v in keep.items():
-                if v is None:
-                    dh.gpu_arrays.pop(k, None)
-                else:
-                    dh.gpu_arrays[k] = v
+    def like_for(f, like):
+        if not f.index_dimensions:
+            return like
+        return like.new_empty(tuple(like.shape[:len(dec.global_shape)]) + tuple(int(v) for v in f.index_shape))
 
     def forward(ctx, *inputs):
         if len(inputs) != len(fwd_inputs):
             raise TypeError('%s takes %d input tensors (%s), got %d' % (op.op_name, len(fwd_inputs),
                                                                          [f.name for f in fwd_inputs], len(inputs)))
-        arrays = {f.name: padded_of(t, f) for f, t in zip(fwd_inputs, inputs)}
+        arrays = {f.name: pool.padded_of(t, tdtype(f), '%s: field %r' % (op.op_name, f.name))
+                  for f, t in zip(fwd_inputs, inputs)}
         like = inputs[0]
         for f in fwd_outputs:
-            arrays[f.name] = new_padded(f, like if not tail(f) else like.new_empty(like.shape[:len(dec.global_shape)] + tail(f)),
-                                        zero=f.name in fwd_reads)
-        launch(fwd_k, {k: v for k, v in arrays.items() if k in {f.name for f in fwd_k.fields}}, fwd_halo)
+            arrays[f.name] = pool.new_padded(tdtype(f), like_for(f, like), zero=f.name in fwd_reads)
+        pool.launch(fwd_k, arrays, fwd_halo, scalars)
         saved = [k for k in arrays if k in bwd_reads]
         ctx.saved_names = saved
         ctx.save_for_backward(*[arrays[k] for k in saved])
         ctx.like = like
-        return tuple(arrays[f.name][g:g + n] for f in fwd_outputs)
+        return tuple(pool.owned(arrays[f.name]) for f in fwd_outputs)
 
     def backward(ctx, *grad_outputs):
         arrays = dict(zip(ctx.saved_names, ctx.saved_tensors))
@@ -633,21 +666,86 @@ def create_slab_autograd_function(op, data_handling, op_name=None, tuning=None, 
                 continue
             gf = fields[name]
             if go is None:
-                arrays[name] = new_padded(gf, like, zero=True)
+                arrays[name] = pool.new_padded(tdtype(gf), like_for(gf, like), zero=True)
             else:
-                arrays[name] = padded_of(go.contiguous() if not go.is_contiguous() else go, gf)
+                arrays[name] = pool.padded_of(go if go.is_contiguous() else go.contiguous(), tdtype(gf),
+                                              '%s: gradient %r' % (op.op_name, name))
         for name, f in bwd_outputs.items():
-            arrays[name] = new_padded(f, like, zero=name in bwd_reads)
-        launch(bwd_k, {k: v for k, v in arrays.items() if k in {f.name for f in bwd_k.fields}},
-               [h for h in bwd_halo if h in arrays])
+            arrays[name] = pool.new_padded(tdtype(f), like_for(f, like), zero=name in bwd_reads)
+        pool.launch(bwd_k, arrays, bwd_halo, scalars)
         result = []
         for f in fwd_inputs:
             name = adjoint_of.get(f.name)
-            result.append(arrays[name][g:g + n] if name in bwd_outputs else None)
+            result.append(pool.owned(arrays[name]) if name in bwd_outputs else None)
         return tuple(result)
 
     cls = type(op_name or op.op_name + '_slab', (torch.autograd.Function,),
                {'forward': staticmethod(forward), 'backward': staticmethod(backward)})
+    cls.forward_kernel, cls.backward_kernel = fwd_k, bwd_k
+    cls.forward_ast, cls.backward_ast = fwd_ir, bwd_ir
+    cls.data_handling = dh
+    cls.class_kwargs = scalars
+    return cls
+
+
+def create_slab_unrolled_function(op, data_handling, steps, fuse=None, op_name=None, tuning=None, scalars=None,
+                                  kernel_class=None):
+    """``steps`` unrolled applications of a one-field linear stencil on this rank's slab, ``u_T = S^T(u_0)``, as ONE
+    autograd Function: the sharded counterpart of ``AutoDiffOp.create_unrolled_torch_op`` (backends/_torch_native.py:
+    ``create_unrolled_function``).  forward = ``steps`` launches of the forward kernel with a ghost-plane exchange before
+    each, ping-ponging between two padded buffers (the input is never written); backward = the adjoint kernel applied
+    ``steps`` times to the upstream gradient the same way; nothing is saved.  ``fuse=True``: pairs of steps as one launch
+    with ONE exchange of ``2 x reach`` ghost planes per pair (needs that many ghost layers; not timed on a GPU yet, hence
+    not the default)."""
+    import torch
+    dh = data_handling
+    dec = dh.dec
+    pool = _slab_tensors(dh)
+    KC = kernel_class or CompiledKernel
+    fwd_ir, bwd_ir = op.forward_ast_gpu, op.backward_ast_gpu
+    for ir, what in ((fwd_ir, 'a stencil with one input and one output field'),
+                     (bwd_ir, 'an adjoint that reads only the upstream gradient (a linear stencil)')):
+        if len(ir.input_fields) != 1 or len(ir.output_fields) != 1:
+            raise ValueError('unrolled steps need ' + what)
+    steps = int(steps)
+    if steps < 1:
+        raise ValueError('steps must be >= 1')
+    fwd_k, bwd_k = KC(fwd_ir, tuning), KC(bwd_ir, tuning)
+    scalars = dict(scalars or {})
+    _check_scalars((fwd_k, bwd_k), scalars)
+    sharded = dec.world_size > 1
+    launches = [2] * (steps // 2) + [1] * (steps % 2) if fuse else [1] * steps
+    for kern in (fwd_k, bwd_k):
+        ir = kern.ir
+        reach = max(ir.halo(ir.input_fields[0].name)[0])
+        if fuse and kern.fused_steps_reason():
+            raise ValueError('%s: steps cannot be fused: %s' % (kern.function_name, kern.fused_steps_reason()))
+        if sharded and dec.g < reach * max(launches):
+            raise ValueError('%s reaches %d plane(s) per step: %d fused step(s) need %d ghost layers, the data handling '
+                             'stores %d' % (kern.function_name, reach, max(launches), reach * max(launches), dec.g))
+
+    def run(kernel, t):
+        ir = kernel.ir
+        fin, fout = ir.input_fields[0], ir.output_fields[0]
+        dtype = numpy_dtype_to_torch(fin.dtype.numpy_dtype)
+        cur = pool.padded_of(t if t.is_contiguous() else t.contiguous(), dtype, '%s: field %r' % (op.op_name, fin.name))
+        halo = [fin.name] if sharded and max(ir.halo(fin.name)[0]) > 0 else []
+        spare = [pool.new_padded(dtype, t, zero=False) for _ in range(min(2, len(launches)))]
+        for i, k in enumerate(launches):
+            dst = spare[i % len(spare)]
+            pool.launch(kernel, {fin.name: cur, fout.name: dst}, halo, scalars, fused_steps=k)
+            cur = dst
+        return pool.owned(cur)
+
+    def forward(ctx, u):
+        return (run(fwd_k, u),)
+
+    def backward(ctx, grad):
+        return run(bwd_k, grad)
+
+    cls = type(op_name or '%s_slab_x%d' % (op.op_name, steps), (torch.autograd.Function,),
+               {'forward': staticmethod(forward), 'backward': staticmethod(backward)})
+    cls.steps, cls.launches = steps, launches
     cls.forward_kernel, cls.backward_kernel = fwd_k, bwd_k
     cls.forward_ast, cls.backward_ast = fwd_ir, bwd_ir
     cls.data_handling = dh

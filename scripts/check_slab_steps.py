@@ -72,6 +72,24 @@ def main():
     same = torch.equal(o2, g2[sl]) and torch.equal(u.grad, ug.grad[sl])
     ok = ok and same
     print('[rank %d] %s %s autograd chain of 2 slab steps: %s' % (rank, name, bh, 'IDENTICAL' if same else 'DIFFERENT'), flush=True)
+    # the same chain as ONE Function: `steps` unrolled steps on the slab == create_unrolled_torch_op on the global field
+    # (pairs fused where the unsharded op fuses them by default: 4-byte fields)
+    from pystencils_autodiff_b200.datahandling import create_slab_unrolled_function
+    fuse = glob.element_size() == 4
+    dh2 = SlabDataHandling(gshape, rank, world, (2 if fuse else 1) * halo, dev)
+    Many = create_slab_unrolled_function(make_config(name, shape=local, boundary_handling=bh), dh2, steps, fuse=fuse)
+    WholeMany = op_g.create_unrolled_torch_op(steps)
+    u = glob[sl].clone().requires_grad_(True)
+    (o,) = Many.apply(u)
+    (o * r[sl]).sum().backward()
+    ug = glob.clone().requires_grad_(True)
+    (og,) = WholeMany.apply(ug)
+    (og * r).sum().backward()
+    torch.cuda.synchronize()
+    same = torch.equal(o, og[sl]) and torch.equal(u.grad, ug.grad[sl])
+    ok = ok and same
+    print('[rank %d] %s %s %d unrolled slab steps as one Function (fuse=%s): %s'
+          % (rank, name, bh, steps, fuse, 'IDENTICAL' if same else 'DIFFERENT'), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

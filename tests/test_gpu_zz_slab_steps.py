@@ -60,7 +60,7 @@ def test_fused_steps_sharded_equals_unsharded(name, bh):
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [l for l in out.stdout.splitlines() if l.startswith('[rank')]
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert len(lines) == 3 * world and all('IDENTICAL' in l for l in lines)
+    assert len(lines) == 4 * world and all('IDENTICAL' in l for l in lines)
 
 
 @pytest.mark.parametrize('make, tol', [(heat3d_op, 1e-6), (stencil27_op, 1e-12)])

@@ -380,6 +380,26 @@ def _autograd_worker(rank, world, port, q):
         res['chain_grad'] = float(np.abs(u.grad.numpy() - d1[sl]).max())
         kinds = [c[0] for c in dh.call_queue]
         assert kinds.count('Communication') == 4 and kinds.count('KernelCall') == 4
+        # ---- A': five unrolled steps as ONE Function (single launches, then fused pairs with two-plane exchanges) ---------
+        from pystencils_autodiff_b200.datahandling import create_slab_unrolled_function
+        dh5 = SlabDataHandling(gshape, rank, world, 2, device='cpu', backend='torch')
+        ref, dref = U.astype(np.float64), R.astype(np.float64)
+        for _ in range(5):
+            ref = evaluate(op_g.forward_assignments, {'u': ref}, 'zeros')['out']
+            dref = evaluate(op_g.backward_assignments, {'diffout': dref}, 'zeros')['diffu']
+        for fuse in (False, True):
+            Five = create_slab_unrolled_function(op_l, dh5, 5, fuse=fuse, kernel_class=ReplayKernel)
+            assert Five.launches == ([2, 2, 1] if fuse else [1] * 5)
+            u5 = torch.from_numpy(U[sl].copy()).requires_grad_(True)
+            n_comm = sum(1 for c in dh5.call_queue if c[0] == 'Communication')
+            (o5,) = Five.apply(u5)
+            (o5 * torch.from_numpy(R[sl])).sum().backward()
+            assert sum(1 for c in dh5.call_queue if c[0] == 'Communication') - n_comm == 2 * len(Five.launches)
+            assert torch.equal(u5.detach(), torch.from_numpy(U[sl]))                 # the input is never written
+            res['x5_out_%s' % fuse] = float(np.abs(o5.detach().numpy() - ref[sl]).max())
+            res['x5_grad_%s' % fuse] = float(np.abs(u5.grad.numpy() - dref[sl]).max())
+        with pytest.raises(ValueError, match='ghost layers'):
+            create_slab_unrolled_function(op_l, dh, 4, fuse=True, kernel_class=ReplayKernel)     # dh stores one ghost plane
         # ---- B: two inputs, non-linear, offsets along dim 0 on both, one constant field (fp64, generic kernels) ---------
         gshape = (5 * world, 6, 7)
         n = gshape[0] // world
@@ -426,6 +446,8 @@ def test_slab_autograd_function_two_ranks():
         assert results[r]['chain_out'] < 2e-6 and results[r]['chain_grad'] < 2e-6, results[r]
         for k in ('nl_out', 'nl_da', 'nl_db'):
             assert results[r][k] < 1e-12, (r, k, results[r])
+        for k in ('x5_out_False', 'x5_grad_False', 'x5_out_True', 'x5_grad_True'):
+            assert results[r][k] < 5e-6, (r, k, results[r])
 
 
 def _e2e_worker(rank, world, port, q):
