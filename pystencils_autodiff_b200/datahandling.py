@@ -1024,8 +1024,10 @@ class HostStreamedOp:
     which serialises H2D, compute and D2H.  Here the fields are cut into chunks of planes along dim 0 (the same slab
     decomposition as the multi-GPU path, with the chunks of one GPU playing the role of the ranks): chunk k+1 is
     uploaded on a copy-in stream while chunk k is computed and chunk k-1 is downloaded on a copy-out stream, so the
-    PCIe link runs in both directions at once and the kernels hide behind it.  Ghost planes come straight from the
-    host array (contiguous), global boundary handling is the same range logic as ``SlabDecomposition``.
+    PCIe link runs in both directions at once and the kernels hide behind it.  A chunk's ghost planes are its neighbours'
+    planes of the (contiguous) host array; the ``2g`` planes two consecutive chunks share are copied from the previous
+    chunk's device buffer, so every input plane crosses PCIe exactly once.  Global boundary handling is the same range
+    logic as ``SlabDecomposition``.
     """
 
     def __init__(self, op, shape, device=None, chunk_planes=None, stages=3, tuning=None):
@@ -1090,15 +1092,23 @@ class HostStreamedOp:
                 if k >= self.stages:
                     self.s_in.wait_event(self.ev_out[st])      # the buffer's previous chunk has been downloaded
                     self.s_in.wait_event(self.ev_cmp[st])
+                # planes [z0 - g, z0 + g) are already on the device — the previous chunk uploaded them into ITS buffer (same
+                # stream, so ordered; a different ring slot, so intact): a device copy instead of a second trip over PCIe
+                prev = self.buffers[(k - 1) % self.stages] if (k > 0 and g > 0 and self.stages > 1) else None
                 for n in self.input_names:
                     dst = buf[n]
                     off = lo - (z0 - g)
                     if off > 0:
                         dst[:off].zero_()                       # planes below the domain: the 'zeros' boundary
-                    dst[off:off + (hi - lo)].copy_(host_in[n][lo:hi], non_blocking=True)
+                    up_lo = lo
+                    if prev is not None:
+                        dst[:2 * g].copy_(prev[n][C:C + 2 * g], non_blocking=True)
+                        up_lo = z0 + g                          # the previous chunk had C planes: it reached z0 + g
+                    if hi > up_lo:
+                        dst[up_lo - (z0 - g):off + (hi - lo)].copy_(host_in[n][up_lo:hi], non_blocking=True)
+                        self.h2d_bytes += (hi - up_lo) * host_in[n][0].numel() * host_in[n].element_size()
                     if off + (hi - lo) < n_k + 2 * g:
                         dst[off + (hi - lo):n_k + 2 * g].zero_()
-                    self.h2d_bytes += (hi - lo) * host_in[n][0].numel() * host_in[n].element_size()
                 self.ev_in[st].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self.ev_in[st])
