@@ -1030,7 +1030,7 @@ class HostStreamedOp:
     logic as ``SlabDecomposition``.
     """
 
-    def __init__(self, op, shape, device=None, chunk_planes=None, stages=3, tuning=None):
+    def __init__(self, op, shape, device=None, chunk_planes=None, stages=3, tuning=None, ramp=True):
         import torch
         self.torch = torch
         self.op = op
@@ -1043,7 +1043,13 @@ class HostStreamedOp:
         if chunk_planes is None:
             chunk_planes = max(4 * max(1, self.g), min(self.shape[0], (192 << 20) // max(1, plane_bytes)))
         self.chunk = int(min(chunk_planes, self.shape[0]))
-        self.n_chunks = -(-self.shape[0] // self.chunk)
+        # Chunk sizes: full chunks in the middle, a quarter and a half chunk at either end — the pipeline fills with the
+        # upload of the FIRST chunk and drains with the download of the LAST one, so those are kept short (the planes
+        # shared by consecutive chunks are copied on the device, extra chunks cost two launches each).
+        self.sizes = self._chunk_sizes(self.shape[0], self.chunk, max(1, 2 * self.g)) if ramp else \
+            [min(self.chunk, self.shape[0] - z) for z in range(0, self.shape[0], self.chunk)]
+        self.starts = [sum(self.sizes[:i]) for i in range(len(self.sizes))]
+        self.n_chunks = len(self.sizes)
         self.stages = int(stages)
         fields = OrderedDict()
         for f in list(op.forward_fields) + list(op.backward_fields):
@@ -1062,9 +1068,21 @@ class HostStreamedOp:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _ranges(self, kernel, k, n_k):
+    @staticmethod
+    def _chunk_sizes(n0, chunk, smallest):
+        """Sizes summing to ``n0``: ``chunk // 4, chunk // 2, chunk, ..., chunk, chunk // 2, chunk // 4`` (ends no smaller than
+        ``smallest`` planes; fields too short for the ramp are cut uniformly)."""
+        q, h = max(smallest, chunk // 4), max(smallest, chunk // 2)
+        if n0 < 2 * (q + h) + chunk or q >= h or h >= chunk:
+            return [min(chunk, n0 - z) for z in range(0, n0, chunk)]
+        middle = n0 - 2 * (q + h)
+        n_mid = -(-middle // chunk)
+        base, rem = divmod(middle, n_mid)
+        return [q, h] + [base + (1 if i < rem else 0) for i in range(n_mid)] + [h, q]
+
+    def _ranges(self, kernel, z0, n_k):
         ir = kernel.ir   # the chunk's ghost planes are filled from the host array, so one launch covers it
-        return slab_ranges(self.shape, k * self.chunk, n_k, self.g, False, False, ir.boundary, ir.ghost_layers, ir.ndim)[0]
+        return slab_ranges(self.shape, z0, n_k, self.g, False, False, ir.boundary, ir.ghost_layers, ir.ndim)[0]
 
     def __call__(self, host_in, host_out, **scalars):
         """``host_in``: name -> pinned CPU tensor for every input field (forward inputs and ``diff<out>`` gradients);
@@ -1085,8 +1103,7 @@ class HostStreamedOp:
         for k in range(self.n_chunks):
             st = k % self.stages
             buf = self.buffers[st]
-            z0 = k * C
-            n_k = min(C, N0 - z0)
+            z0, n_k = self.starts[k], self.sizes[k]
             lo, hi = max(0, z0 - g), min(N0, z0 + n_k + g)
             with torch.cuda.stream(self.s_in):
                 if k >= self.stages:
@@ -1102,8 +1119,9 @@ class HostStreamedOp:
                         dst[:off].zero_()                       # planes below the domain: the 'zeros' boundary
                     up_lo = lo
                     if prev is not None:
-                        dst[:2 * g].copy_(prev[n][C:C + 2 * g], non_blocking=True)
-                        up_lo = z0 + g                          # the previous chunk had C planes: it reached z0 + g
+                        n_prev = self.sizes[k - 1]
+                        dst[:2 * g].copy_(prev[n][n_prev:n_prev + 2 * g], non_blocking=True)
+                        up_lo = min(N0, z0 + g)                 # the previous chunk's buffer reached plane z0 + g
                     if hi > up_lo:
                         dst[up_lo - (z0 - g):off + (hi - lo)].copy_(host_in[n][up_lo:hi], non_blocking=True)
                         self.h2d_bytes += (hi - up_lo) * host_in[n][0].numel() * host_in[n].element_size()
@@ -1119,7 +1137,7 @@ class HostStreamedOp:
                         if f in kern.ir.input_fields:       # ``+=`` form: accumulates onto a zero-initialised output
                             buf[f.name].zero_()
                     views = {f.name: buf[f.name][:n_k + 2 * g] for f in kern.fields}
-                    kern(**views, **{s_: scalars[s_] for s_ in kern.scalars}, _range=self._ranges(kern, k, n_k))
+                    kern(**views, **{s_: scalars[s_] for s_ in kern.scalars}, _range=self._ranges(kern, z0, n_k))
                 self.ev_cmp[st].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_cmp[st])

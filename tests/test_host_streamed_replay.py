@@ -19,15 +19,19 @@ from replay_kernels import ReplayKernel
     (configs.stencil27_op, (11, 9, 36), 'zeros', 4, 1e-13),
     (configs.tv_gradient_op, (5, 12, 36), 'zeros', 2, 2e-5),      # no reach along dim 0: chunks without ghost planes
 ])
-def test_host_streamed_chunks_equal_whole_field(make, shape, bh, chunk, tol):
+@pytest.mark.parametrize('ramp', [True, False])
+def test_host_streamed_chunks_equal_whole_field(make, shape, bh, chunk, tol, ramp):
     op = make(shape=shape, boundary_handling=bh)
     rng = np.random.default_rng(3)
     ins = {f.name: rng.uniform(0.1, 1.0, shape).astype(f.dtype.numpy_dtype) for f in op.forward_input_fields}
     grads = {f.name: rng.standard_normal(shape).astype(f.dtype.numpy_dtype) for f in op.forward_output_fields}
     with fake_cuda():
-        streamed = HostStreamedOp(op, shape, device='cpu', chunk_planes=chunk, stages=3)
+        streamed = HostStreamedOp(op, shape, device='cpu', chunk_planes=chunk, stages=3, ramp=ramp)
         streamed.fwd, streamed.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
-        assert streamed.n_chunks == -(-shape[0] // chunk)
+        assert sum(streamed.sizes) == shape[0] and max(streamed.sizes) <= chunk and min(streamed.sizes) >= 1
+        assert streamed.starts == [sum(streamed.sizes[:i]) for i in range(streamed.n_chunks)]
+        if not ramp:
+            assert streamed.n_chunks == -(-shape[0] // chunk)
         host_in = {n: torch.from_numpy(ins[n]) for n in ins}
         host_in.update({'diff' + n: torch.from_numpy(g) for n, g in grads.items()})
         host_out = {n: torch.full(shape, float('nan'), dtype=host_in[next(iter(ins))].dtype) for n in streamed.output_names}
@@ -42,3 +46,16 @@ def test_host_streamed_chunks_equal_whole_field(make, shape, bh, chunk, tol):
     per_plane = int(np.prod(shape[1:])) * host_in[next(iter(ins))].element_size()
     assert streamed.h2d_bytes == shape[0] * per_plane * len(streamed.input_names)
     assert streamed.d2h_bytes == shape[0] * per_plane * len(streamed.output_names)
+
+
+def test_chunk_sizes_ramp():
+    """Short chunks at both ends (pipeline fill / drain), full ones in between; short fields fall back to uniform cuts."""
+    f = HostStreamedOp._chunk_sizes
+    c3 = f(1024, 48, 2)                                # the C3 field: 48-plane chunks of 4 MiB planes
+    assert sum(c3) == 1024 and c3[:2] == [12, 24] and c3[-2:] == [24, 12] and set(c3[2:-2]) <= {47, 48}
+    assert f(23, 6, 2) == [2, 3, 5, 4, 4, 3, 2]
+    assert f(10, 6, 2) == [6, 4]                       # too short for a ramp
+    assert f(16, 64, 2) == [16]
+    for n0, c, m in ((768, 40, 2), (100, 7, 4), (5, 2, 1), (4096, 48, 1)):
+        sizes = f(n0, c, m)
+        assert sum(sizes) == n0 and max(sizes) <= c and all(v >= 1 for v in sizes)
