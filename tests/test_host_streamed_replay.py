@@ -59,3 +59,27 @@ def test_chunk_sizes_ramp():
     for n0, c, m in ((768, 40, 2), (100, 7, 4), (5, 2, 1), (4096, 48, 1)):
         sizes = f(n0, c, m)
         assert sum(sizes) == n0 and max(sizes) <= c and all(v >= 1 for v in sizes)
+
+
+def test_host_streamed_scalar_parameter_and_accumulate_form():
+    """The CPU twin of tests/test_gpu_api.py::test_host_streamed_op_with_scalar_and_accumulate_form."""
+    import sympy as sp
+    import pystencils_autodiff_b200 as ps
+    shape = (21, 16, 64)
+    u, out = ps.fields('u, out: float64[%d,%d,%d]' % shape)
+    al = sp.Symbol('alpha')
+    fa = [ps.Assignment(out.center, u[0, 0, 0] + al * (u[1, 0, 0] + u[-1, 0, 0] + u[0, 0, 1] - 3 * u[0, 0, 0]))]
+    op = ps.AutoDiffOp(fa, boundary_handling='zeros', time_constant_fields=[u])
+    rng = np.random.default_rng(21)
+    U, G = rng.normal(size=shape), rng.normal(size=shape)
+    host = {'u': torch.from_numpy(U), 'diffout': torch.from_numpy(G),
+            'out': torch.full(shape, float('nan'), dtype=torch.float64), 'diffu': torch.full(shape, float('nan'), dtype=torch.float64)}
+    with fake_cuda():
+        st = HostStreamedOp(op, shape, 'cpu', chunk_planes=4)
+        st.fwd, st.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
+        with pytest.raises(TypeError):
+            st({n: host[n] for n in st.input_names}, {n: host[n] for n in st.output_names})
+        st({n: host[n] for n in st.input_names}, {n: host[n] for n in st.output_names}, alpha=0.3)
+    ref_o, ref_d = forward_backward(op, dict(u=U), dict(out=G), scalars=dict(alpha=0.3))
+    np.testing.assert_allclose(host['out'].numpy(), ref_o['out'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host['diffu'].numpy(), ref_d['diffu'], rtol=1e-12, atol=1e-12)
