@@ -83,3 +83,36 @@ def test_host_streamed_scalar_parameter_and_accumulate_form():
     ref_o, ref_d = forward_backward(op, dict(u=U), dict(out=G), scalars=dict(alpha=0.3))
     np.testing.assert_allclose(host['out'].numpy(), ref_o['out'], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(host['diffu'].numpy(), ref_d['diffu'], rtol=1e-12, atol=1e-12)
+
+
+def test_end_to_end_leg_one_rank_checks_itself():
+    """``SlabStencilOp.end_to_end`` at N = 1 (bench.py's ``e2e``): after the timed steps a few planes of every streamed
+    output are compared bit for bit with the resident kernels; the line carries ``matches_resident``."""
+    from pystencils_autodiff_b200.datahandling import SlabStencilOp
+    shape = (40, 10, 132)
+    op = configs.heat3d_op(shape=shape, boundary_handling='zeros')
+    with fake_cuda():
+        slab = SlabStencilOp(op, shape, 0, 1, device='cpu', backend='torch')
+        slab.fwd, slab.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
+        slab.randomize(torch.Generator().manual_seed(0))
+        slab._fn = HostStreamedOp(op, shape, 'cpu', chunk_planes=8)
+        slab._fn.fwd, slab._fn.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
+        slab._host = {n: torch.empty(shape, dtype=slab.dh.gpu_arrays[n].dtype) for n in slab._fn.fields}
+        for n in slab._fn.input_names:
+            slab._host[n].copy_(slab.dh.owned(n))
+        r = slab.end_to_end(1, lambda: None)
+        assert r['matches_resident'] is True
+        assert r['checked_planes'][0] == 0 and r['checked_planes'][-1] == shape[0] - 1 and len(r['checked_planes']) >= 4
+        assert r['h2d'] == 2 * 4 * int(np.prod(shape)) and r['d2h'] == r['h2d']
+        # a corrupted download is noticed
+        slab._fn.output_names = list(slab._fn.output_names)
+        real_call = HostStreamedOp.__call__
+
+        def corrupting(self, host_in, host_out, **kw):
+            real_call(self, host_in, host_out, **kw)
+            host_out['out'][0, 0, 0] += 1.0
+        HostStreamedOp.__call__ = corrupting
+        try:
+            assert slab.end_to_end(1, lambda: None)['matches_resident'] is False
+        finally:
+            HostStreamedOp.__call__ = real_call
