@@ -1027,6 +1027,13 @@ class SlabStencilOp:
             result['matches_resident'] = all(
                 bool(torch.equal(self._host[n][p].to(self.device), self.dh.owned(n)[p]))
                 for n in self._fn.output_names for p in planes)
+        else:
+            # the staging buffer is shared by all downloads: what it holds now is the last one — the gradient of the last
+            # forward input — which must equal the device array it came from
+            last_field, last_grad = in_fields[-1], dnames[-1] if len(dnames) >= len(in_fields) else None
+            if last_grad is not None:
+                result['matches_resident'] = bool(torch.equal(host_view(h_out, last_field.name).to(self.device),
+                                                              self.dh.owned(last_grad)))
         return result
 
 

@@ -471,6 +471,7 @@ def _e2e_worker(rank, world, port, q):
             r = slab.end_to_end(2, dist.barrier)
         cells = int(np.prod(local))
         assert r['ms_per_step'] > 0 and r['h2d'] == 2 * 4 * cells and r['d2h'] == 2 * 4 * cells
+        assert r['matches_resident'] is True
         # what the last step left on the "device": forward and adjoint of the uploaded (synthetic) host data
         got = {n: slab.dh.gather_array(n) for n in ('u', 'out', 'diffout', 'diffu')}
         op_g = configs.heat3d_op(shape=gshape, boundary_handling='zeros')
