@@ -355,13 +355,13 @@ def _autograd_worker(rank, world, port, q):
         from replay_kernels import ReplayKernel
         res = {}
         # ---- A: two chained steps of the 7-point stencil (fp32, march kernels), loss = sum(out2 * r) ----------------------
-        gshape = (6 * world, 10, 132)
-        n = gshape[0] // world
-        sl = slice(rank * n, (rank + 1) * n)
+        gshape = (6 * world + 1, 10, 132)                    # uneven slabs: rank 0 owns one plane more
         rng = np.random.default_rng(8)
         U = rng.standard_normal(gshape).astype(np.float32)
         R = rng.standard_normal(gshape).astype(np.float32)
         dh = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch')
+        n = dh.dec.n_local
+        sl = slice(dh.dec.start, dh.dec.start + n)
         op_l = configs.heat3d_op(shape=(n,) + gshape[1:], boundary_handling='zeros')
         Step = create_slab_autograd_function(op_l, dh, kernel_class=ReplayKernel)
         u = torch.from_numpy(U[sl].copy()).requires_grad_(True)
@@ -370,7 +370,8 @@ def _autograd_worker(rank, world, port, q):
         (o2,) = Step.apply(o1)
         assert o1._base is not None and o1._base.shape[0] == n + 2          # outputs are views of padded buffers
         (o2 * torch.from_numpy(R[sl])).sum().backward()
-        assert all('march' in name for name in ReplayKernel.launches) and len(ReplayKernel.launches) == 4 * 2
+        parts = 1 + int(rank > 0) + int(rank < world - 1)          # interior + the planes next to each neighbour
+        assert all('march' in name for name in ReplayKernel.launches) and len(ReplayKernel.launches) == 4 * parts
         op_g = configs.heat3d_op(shape=gshape, boundary_handling='zeros')
         r1 = evaluate(op_g.forward_assignments, {'u': U.astype(np.float64)}, 'zeros')['out']
         r2 = evaluate(op_g.forward_assignments, {'u': r1}, 'zeros')['out']
@@ -401,9 +402,10 @@ def _autograd_worker(rank, world, port, q):
         with pytest.raises(ValueError, match='ghost layers'):
             create_slab_unrolled_function(op_l, dh, 4, fuse=True, kernel_class=ReplayKernel)     # dh stores one ghost plane
         # ---- B: two inputs, non-linear, offsets along dim 0 on both, one constant field (fp64, generic kernels) ---------
-        gshape = (5 * world, 6, 7)
-        n = gshape[0] // world
-        sl = slice(rank * n, (rank + 1) * n)
+        gshape = (5 * world + 1, 6, 7)
+        dh2 = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch')
+        n = dh2.dec.n_local
+        sl = slice(dh2.dec.start, dh2.dec.start + n)
 
         def make(shape, consts=True):
             a, b, c, out = ps.fields('a, b, c, out: float64[%d,%d,%d]' % shape)
@@ -412,7 +414,6 @@ def _autograd_worker(rank, world, port, q):
         op_l, op_g = make((n,) + gshape[1:]), make(gshape)
         ins = {k: rng.uniform(0.5, 1.5, gshape) for k in 'abc'}
         G = rng.standard_normal(gshape)
-        dh2 = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch')
         F = create_slab_autograd_function(op_l, dh2, kernel_class=ReplayKernel)
         tens = [torch.from_numpy(ins[f.name][sl].copy()).requires_grad_(f.name != 'c') for f in op_l.forward_input_fields]
         (out,) = F.apply(*tens)
@@ -431,14 +432,14 @@ def _autograd_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_slab_autograd_function_two_ranks():
+@pytest.mark.parametrize('world', [2, 3])
+def test_slab_autograd_function_two_ranks(world):
     """``create_slab_autograd_function`` (SURVEY.md §8e "Autograd"): forward = halo exchange + forward kernel on the owned
     planes, backward = the same exchange on the upstream gradient + the adjoint kernel; chained steps reuse the padded
     buffers.  Two gloo ranks, emitted kernels replayed on the CPU, compared with the oracle on the GLOBAL field."""
-    world = 2
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_autograd_worker, args=(r, world, 29877, q)) for r in range(world)]
+    procs = [ctx.Process(target=_autograd_worker, args=(r, world, 29877 + world, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(_collect(procs, q, world))
