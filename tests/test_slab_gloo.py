@@ -427,6 +427,29 @@ def _autograd_worker(rank, world, port, q):
                 res['nl_d' + f.name] = float(np.abs(t.grad.numpy() - ref_grads['diff' + f.name][sl]).max())
         with pytest.raises(ValueError, match='owned planes'):
             F.apply(*[torch.zeros((n + 1,) + gshape[1:], dtype=torch.float64)] * 3)
+        # ---- C: scalar input, vector output (index dimension): the curl-like case of tests/test_tfmad.py:341-401, 2-D ------
+        gshape = (4 * world + 1, 10)
+        dh3 = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch')
+        n = dh3.dec.n_local
+        sl = slice(dh3.dec.start, dh3.dec.start + n)
+
+        def curl(shape):
+            v = ps.Field.create_fixed_size('v', shape, index_dimensions=0, dtype=np.float64)
+            c = ps.Field.create_fixed_size('c', shape + (2,), index_dimensions=1, dtype=np.float64)
+            disc = ps.fd.Discretization2ndOrder(dx=1)
+            return ps.AutoDiffOp(ps.AssignmentCollection([ps.Assignment(c.center(0), disc(ps.fd.Diff(v, 0))),
+                                                          ps.Assignment(c.center(1), disc(ps.fd.Diff(v, 1)))], []),
+                                 op_name='curl', boundary_handling='zeros')
+        op_l, op_g = curl((n, gshape[1])), curl(gshape)
+        V, GC = rng.standard_normal(gshape), rng.standard_normal(gshape + (2,))
+        C = create_slab_autograd_function(op_l, dh3, kernel_class=ReplayKernel)
+        v = torch.from_numpy(V[sl].copy()).requires_grad_(True)
+        (c,) = C.apply(v)
+        assert tuple(c.shape) == (n, gshape[1], 2)
+        c.backward(torch.from_numpy(GC[sl].copy()))
+        ref_out, ref_grads = forward_backward(op_g, {'v': V}, {'c': GC})
+        res['curl_out'] = float(np.abs(c.detach().numpy() - ref_out['c'][sl]).max())
+        res['curl_grad'] = float(np.abs(v.grad.numpy() - ref_grads['diffv'][sl]).max())
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -445,7 +468,7 @@ def test_slab_autograd_function_two_ranks(world):
     results = dict(_collect(procs, q, world))
     for r in range(world):
         assert results[r]['chain_out'] < 2e-6 and results[r]['chain_grad'] < 2e-6, results[r]
-        for k in ('nl_out', 'nl_da', 'nl_db'):
+        for k in ('nl_out', 'nl_da', 'nl_db', 'curl_out', 'curl_grad'):
             assert results[r][k] < 1e-12, (r, k, results[r])
         for k in ('x5_out_False', 'x5_grad_False', 'x5_out_True', 'x5_grad_True'):
             assert results[r][k] < 5e-6, (r, k, results[r])
