@@ -77,9 +77,28 @@ def _finish(backward_list, do_cse):
     return AssignmentCollection(main, sub)
 
 
+def _shifted(expr, shift):
+    """``expr`` evaluated at the cell ``shift`` away: every field access moves by ``shift``."""
+    if not any(shift):
+        return expr
+    return expr.xreplace({a: a.get_shifted(*shift) for a in expr.atoms(Field.Access)})
+
+
 def tf_mad_backward(forward_assignments, constant_fields=(), time_constant_fields=None, diff_fields_prefix='diff',
-                    do_common_subexpression_elimination=True):
-    """Gather-form adjoint.  Returns ``(backward_collection, field_map, read_accesses, write_accesses)``."""
+                    do_common_subexpression_elimination=True, adjoint_mode='reference'):
+    """Gather-form adjoint.  Returns ``(backward_collection, field_map, read_accesses, write_accesses)``.
+
+    ``adjoint_mode='reference'`` restates the reference's rule (:104-109): the contribution of a read ``f[o]`` in
+    ``out[l] = rhs`` to ``diff_f[0]`` is ``(d rhs / d f[o]) * diff_out[-o - l]`` with the coefficient left AT THE CENTRE
+    CELL — exact for coefficients that do not depend on fields (linear stencils) and for centre reads, not otherwise
+    (SURVEY.md Appendix B-1).  ``'exact'`` is the transpose of the Jacobian: cell ``p`` of ``f`` is read by the evaluation
+    at cell ``c = p - o``, which writes ``out[c + l]``, so the contribution is
+    ``(d rhs / d f[o])(evaluated at p - o) * diff_out[-o + l]`` — the coefficient's own accesses shift by ``-o``.  It is
+    what ``torch.autograd.gradcheck`` expects for non-linear stencils with ``boundary_handling='zeros'``; with interior
+    iteration (``None``) it additionally needs upstream gradients that vanish on the un-iterated border."""
+    if adjoint_mode not in ('reference', 'exact'):
+        raise ValueError("adjoint_mode must be 'reference' or 'exact'")
+    exact = adjoint_mode == 'exact'
     fwd = _inline_main(forward_assignments)
     reads = sorted([s for s in fwd.free_symbols if isinstance(s, Field.Access)], key=str)
     writes = [a.lhs for a in fwd.main_assignments]
@@ -106,8 +125,13 @@ def tf_mad_backward(forward_assignments, constant_fields=(), time_constant_field
                 for ra in reads:
                     if ra.field != f:
                         continue
-                    flipped = tuple(-o - l for o, l in zip(ra.offsets, lhs.offsets))
-                    total += sp.diff(rhs, ra) * d_out[flipped](*lhs.index)
+                    coef = sp.diff(rhs, ra)
+                    if exact:
+                        coef = _shifted(coef, tuple(-o for o in ra.offsets))
+                        flipped = tuple(-o + l for o, l in zip(ra.offsets, lhs.offsets))
+                    else:
+                        flipped = tuple(-o - l for o, l in zip(ra.offsets, lhs.offsets))
+                    total += coef * d_out[flipped](*lhs.index)
                 targets = {d_in.center(): total}
             elif d_in.index_dimensions == 1:
                 # one adjoint component per index of the input field (the reference's loop :138-152 keeps only
@@ -116,9 +140,14 @@ def tf_mad_backward(forward_assignments, constant_fields=(), time_constant_field
                 for ra in reads:
                     if ra.field != f:
                         continue
-                    flipped = tuple(-o - l for o, l in zip(ra.offsets, lhs.offsets))
+                    coef = sp.diff(rhs, ra)
+                    if exact:
+                        coef = _shifted(coef, tuple(-o for o in ra.offsets))
+                        flipped = tuple(-o + l for o, l in zip(ra.offsets, lhs.offsets))
+                    else:
+                        flipped = tuple(-o - l for o, l in zip(ra.offsets, lhs.offsets))
                     key = d_in.center.at_index(*ra.index)
-                    targets[key] = targets.get(key, sp.Integer(0)) + sp.diff(rhs, ra) * d_out[flipped](*lhs.index)
+                    targets[key] = targets.get(key, sp.Integer(0)) + coef * d_out[flipped](*lhs.index)
             else:
                 raise NotImplementedError()
             for target, total in targets.items():
@@ -183,6 +212,11 @@ class AutoDiffOp:
             assert kwargs['target'].lower() in ['cpu', 'gpu'], "AutoDiffOp always supports both cpu and gpu"
             del kwargs['target']
         kwargs.pop('no_chaching', None)  # stray kwarg the reference forwards (:725)
+        # not a reference argument: 'reference' (default, parity) or 'exact' (see tf_mad_backward); keyword-only, so the
+        # reference's positional signature is unchanged
+        self._adjoint_mode = kwargs.pop('adjoint_mode', 'reference')
+        if self._adjoint_mode != 'reference' and diff_mode != DiffModes.TF_MAD:
+            raise NotImplementedError("adjoint_mode='exact' is implemented for diff_mode='transposed-forward'")
 
         forward_assignments = coerce_assignments(forward_assignments)
         if boundary_handling == AutoDiffBoundaryHandling.VALID:
@@ -210,7 +244,7 @@ class AutoDiffOp:
             (self._backward_assignments, self._backward_field_map,
              self._forward_read_accesses, self._forward_write_accesses) = tf_mad_backward(
                 forward_assignments, self._constant_fields, time_constant_fields, diff_fields_prefix,
-                do_common_subexpression_elimination)
+                do_common_subexpression_elimination, self._adjoint_mode)
         elif diff_mode == DiffModes.TRANSPOSED:
             (self._backward_assignments, self._backward_field_map,
              self._forward_read_accesses, self._forward_write_accesses) = transposed_backward(
@@ -455,14 +489,16 @@ def create_backward_assignments(forward_assignments,
                                 time_constant_fields=[],
                                 constant_fields=[],
                                 diff_mode=DiffModes.TF_MAD,
-                                do_common_sub_expression_elimination=True):
-    """Reference signature: _autodiff.py:713-718."""
+                                do_common_sub_expression_elimination=True,
+                                adjoint_mode='reference'):
+    """Reference signature: _autodiff.py:713-718 (``adjoint_mode`` is this package's, see ``tf_mad_backward``)."""
     auto_diff = AutoDiffOp(forward_assignments,
                            diff_fields_prefix=diff_fields_prefix,
                            time_constant_fields=time_constant_fields,
                            constant_fields=constant_fields,
                            diff_mode=diff_mode,
-                           do_common_subexpression_elimination=do_common_sub_expression_elimination)
+                           do_common_subexpression_elimination=do_common_sub_expression_elimination,
+                           adjoint_mode=adjoint_mode)
     return auto_diff.backward_assignments
 
 

@@ -40,6 +40,14 @@ def main():
         for bh in (None, 'zeros'):
             op = make_config(name, shape=shape, dtype=dtype, boundary_handling=bh)
             kernels += [CompiledKernel(op.forward_ast_gpu), CompiledKernel(op.backward_ast_gpu)]
+    import sympy as sp                                          # tests/test_gpu_zz_golden.py: exact adjoint mode
+    from pystencils_autodiff_b200.configs import tv_gradient_op
+    x, y, z = ps.fields('x, y, z: float64[7,8]')
+    asg = ps.AssignmentCollection({z.center: x[1, 0] * y[0, 0] + sp.sin(x[0, -1]) * y[-1, 1]})
+    for mode in ('exact', 'reference'):
+        for op in (ps.AutoDiffOp(asg, op_name='nl_' + mode, boundary_handling='zeros', adjoint_mode=mode),
+                   tv_gradient_op(shape=(2, 6, 8), dtype='float64', adjoint_mode=mode)):
+            kernels += [CompiledKernel(op.forward_ast_gpu), CompiledKernel(op.backward_ast_gpu)]
     t0 = time.time()
     hits = misses = 0
     for k in kernels:

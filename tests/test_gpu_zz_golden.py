@@ -36,3 +36,26 @@ def test_function_matches_reference_golden_vectors(name, mode):
     assert checked >= 1
     if name.endswith('_aligned'):
         assert fn.forward_kernel.last_variant == 'march' and fn.backward_kernel.last_variant == 'march'
+
+
+def test_exact_adjoint_mode_passes_gradcheck_on_the_gpu():
+    """``AutoDiffOp(..., adjoint_mode='exact')``: ``torch.autograd.gradcheck`` on random non-zero float64 inputs for a
+    non-linear two-field stencil and for the TV gradient (C5), 'zeros' boundary.  The default mode restates the reference's
+    rule (coefficients left at the centre cell), which is not the transpose there."""
+    import sympy as sp
+    import torch
+    import pystencils_autodiff_b200 as ps
+    from pystencils_autodiff_b200.configs import tv_gradient_op
+    x, y, z = ps.fields('x, y, z: float64[7,8]')
+    asg = ps.AssignmentCollection({z.center: x[1, 0] * y[0, 0] + sp.sin(x[0, -1]) * y[-1, 1]})
+    gen = torch.Generator().manual_seed(0)
+    for make_op, shape in ((lambda m: ps.AutoDiffOp(asg, op_name='nl_' + m, boundary_handling='zeros', adjoint_mode=m), (7, 8)),
+                           (lambda m: tv_gradient_op(shape=(2, 6, 8), dtype='float64', adjoint_mode=m), (2, 6, 8))):
+        ok = {}
+        for mode in ('exact', 'reference'):
+            fn = make_op(mode).create_tensorflow_op(backend='torch_native', use_cuda=True)
+            ins = [(torch.rand(shape, generator=gen, dtype=torch.float64) + 0.5).cuda().requires_grad_(True)
+                   for _ in fn.forward_ast.input_fields]
+            ok[mode] = torch.autograd.gradcheck(fn.apply, ins, atol=1e-4, raise_exception=False)   # the reference tests' atol
+        assert ok['exact'] is True
+        assert ok['reference'] is False

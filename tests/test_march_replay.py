@@ -434,3 +434,23 @@ def test_march_kernels_against_reference_golden_vectors(name):
                 ran += 1
     if name.endswith('_aligned'):
         assert ran >= 4            # forward + adjoint, both boundary modes
+
+
+def test_exact_adjoint_mode_tv_kernel_replay():
+    """``adjoint_mode='exact'`` (shifted coefficients: the true transpose for non-linear stencils) goes through the same
+    march emitter: the TV-gradient adjoint kernel of that mode against the oracle on its own assignments."""
+    shape = (2, 33, 132)
+    op = configs.tv_gradient_op(shape=shape, adjoint_mode='exact')
+    ir = op.backward_ast_gpu
+    ek = emit_march(ir, None, masked=True)
+    rng = np.random.default_rng(0)
+    arrays, named = [], {}
+    for f in ek.fields:
+        a = emu.aligned_empty(shape, f.dtype.numpy_dtype)
+        a[...] = rng.random(shape) if f in ir.input_fields else np.nan
+        arrays.append(a)
+        named[f.name] = a
+    emu.run(ek, arrays)
+    ref = evaluate(op.backward_assignments, {f.name: named[f.name].copy() for f in ir.input_fields}, boundary_handling='zeros')
+    for f in ir.output_fields:
+        assert np.abs(named[f.name] - ref[f.name]).max() <= 2e-6 * max(1.0, np.abs(ref[f.name]).max())

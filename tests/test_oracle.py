@@ -160,3 +160,67 @@ def test_c_restatement_against_golden_vectors():
                     np.testing.assert_allclose(env[key], ref, rtol=1e-12, atol=1e-12, err_msg='%s %s %s' % (name, mode, key))
                     checked += 1
     assert checked >= 60
+
+
+def _fd_vjp_error(op, shape, seed=0, eps=1e-6, border=0):
+    """max |J^T g - backward(g)| with J from central finite differences of the oracle's forward evaluation; ``border``:
+    upstream gradients are zero within that many cells of the array border."""
+    rng = np.random.default_rng(seed)
+    bh = op.boundary_handling
+    ins = {f.name: rng.uniform(0.5, 1.5, shape) for f in op.forward_input_fields}
+    grads = {f.name: rng.standard_normal(shape) for f in op.forward_output_fields}
+    if border:
+        for g in grads.values():
+            mask = np.zeros(shape, dtype=bool)
+            mask[tuple(slice(border, -border) for _ in shape)] = True
+            g[~mask] = 0.0
+    _, din = forward_backward(op, ins, grads)
+    worst = 0.0
+    for f in op.forward_input_fields:
+        key = 'diff' + f.name
+        if key not in din:
+            continue
+        fd = np.zeros(shape)
+        for idx in np.ndindex(*shape):
+            plus, minus = {k: v.copy() for k, v in ins.items()}, {k: v.copy() for k, v in ins.items()}
+            plus[f.name][idx] += eps
+            minus[f.name][idx] -= eps
+            op_, om_ = evaluate(op.forward_assignments, plus, bh), evaluate(op.forward_assignments, minus, bh)
+            fd[idx] = sum(((op_[o] - om_[o]) * grads[o]).sum() for o in grads) / (2 * eps)
+        worst = max(worst, float(np.abs(fd - din[key]).max()))
+    return worst
+
+
+def test_exact_adjoint_mode_passes_the_gradient_check_for_nonlinear_stencils():
+    """the reference leaves field-dependent coefficients at the centre cell, which is not
+    the transpose of the Jacobian when the read is at an offset.  ``adjoint_mode='exact'`` shifts them: finite-difference
+    vector-Jacobian products agree for the TV gradient (C5) and a two-field non-linear stencil with an off-centre write;
+    the default mode does not, and for linear stencils / centre reads the two modes emit the same assignments."""
+    import sympy as sp
+    from pystencils_autodiff_b200 import configs
+    shape = (2, 5, 6)
+    tv = {m: configs.tv_gradient_op(shape=shape, dtype='float64', boundary_handling='zeros', adjoint_mode=m)
+          for m in ('reference', 'exact')}
+    assert _fd_vjp_error(tv['exact'], shape) < 1e-6
+    assert _fd_vjp_error(tv['reference'], shape) > 1e-2
+
+    x, y, z = ps.fields('x, y, z: float64[5,6]')
+    asg = ps.AssignmentCollection({z.center: x[1, 0] * y[0, 0] + sp.sin(x[0, -1]) * y[-1, 1]})
+    err = {m: _fd_vjp_error(ps.AutoDiffOp(asg, boundary_handling='zeros', adjoint_mode=m), (5, 6), seed=1)
+           for m in ('reference', 'exact')}
+    assert err['exact'] < 1e-6 < 1e-2 < err['reference']
+    # an off-centre write (interior iteration; upstream gradients away from the border): diff_out is read at -o + l
+    X, Y, Z = ps.fields('X, Y, Z: float64[11,12]')
+    off = ps.AssignmentCollection({Z[0, 1]: X[1, 0] * Y[0, 0] + 0.5 * X[0, -1]})
+    err = {m: _fd_vjp_error(ps.AutoDiffOp(off, boundary_handling=None, adjoint_mode=m), (11, 12), seed=2, border=4)
+           for m in ('reference', 'exact')}
+    assert err['exact'] < 1e-6 < 1e-2 < err['reference']
+
+    for make, shp in ((configs.heat3d_op, (4, 5, 6)), (configs.stencil27_op, (4, 5, 6)), (configs.readme_op, (5, 6))):
+        a = make(shape=shp, adjoint_mode='reference').backward_assignments
+        b = make(shape=shp, adjoint_mode='exact').backward_assignments
+        assert str(a) == str(b)
+    with pytest.raises(ValueError):
+        ps.AutoDiffOp(asg, adjoint_mode='almost')
+    with pytest.raises(NotImplementedError):
+        ps.AutoDiffOp(ps.AssignmentCollection({z.center: x.center * y.center}), diff_mode='transposed', adjoint_mode='exact')
