@@ -32,6 +32,8 @@ def main():
             tun[k] = bool(int(v)) if k in ("carry", "shuffle", "plane_sums", "arrival", "linopt", "cross_cse") else int(v)
     tuning = MarchTuning(**tun) if tun else None
     extra = {'fast_math': True} if os.environ.get('PSAD_FAST_MATH') else {}
+    if os.environ.get('PSAD_ADJOINT_MODE'):          # 'exact': the true transpose for non-linear stencils (C5)
+        extra['adjoint_mode'] = os.environ['PSAD_ADJOINT_MODE']
     if os.environ.get('PSAD_BH'):
         extra['boundary_handling'] = None if os.environ['PSAD_BH'] == 'none' else os.environ['PSAD_BH']
     op = make_config(name, shape=shape, **extra)

@@ -35,6 +35,10 @@ python scripts/steps_bench.py \
     c2 "0,0,0,0;2,30,4,0,1;2,14,4,0,1,2" > gpurun_out/r2_steps_bench.log 2>&1; echo "steps_bench rc=$?"
 # 4. time loop on one slab with ghost planes: ranged fused launches against ranged single steps
 python scripts/slab_steps_bench.py c3 8 > gpurun_out/r2_slab_steps_c3_n1.json 2> gpurun_out/r2_slab_steps_c3_n1.err; echo "slab steps rc=$?"
+# 4b. the TV adjoint in both adjoint modes (the exact one has 7.5 % fewer instructions in its step loop)
+PSAD_MARCH_ONLY=1 python scripts/kbench.py c5 > gpurun_out/r2_kbench_c5_reference.log 2>&1
+PSAD_MARCH_ONLY=1 PSAD_ADJOINT_MODE=exact python scripts/kbench.py c5 > gpurun_out/r2_kbench_c5_exact.log 2>&1
+echo "kbench c5 rc=$?"; grep backward gpurun_out/r2_kbench_c5_*.log
 # 5. ncu of the exchange variant of the fused pair (after its plain run above exited 0)
 ncu --set full --clock-control none --import-source on -k regex:march_x2e -c 1 -o gpurun_out/r2_c3_x2e \
     python scripts/steps_bench.py c3 "0,0,0,0" > gpurun_out/r2_ncu_x2e.log 2>&1; echo "ncu rc=$?"
