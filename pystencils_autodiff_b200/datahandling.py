@@ -212,6 +212,7 @@ class SlabDataHandling:
         self.cpu_arrays = OrderedDict()
         self.fields = OrderedDict()
         self.call_queue = []
+        self.kernel_io = {}            # kernel name -> (read field names, written field names) of the kernels run here
         self._swap_count = 0
         self._replicated = set()       # arrays with their own spatial shape: whole on every rank, no ghost planes
         self._range_cache = {}
@@ -444,9 +445,14 @@ class SlabDataHandling:
                             'the Function class of a torch_native op; arbitrary callables only on a single rank')
         if fused_steps not in (1, 2):
             raise ValueError('fused_steps must be 1 or 2')
+        for n in halo_fields:           # recorded in the reference's order: synchronisation, then the kernel call
+            self._record(('Communication', n, None, True))
         self._record(('KernelCall', kernel.function_name) if fused_steps == 1 else
-                               ('KernelCall', kernel.function_name, fused_steps))
+                     ('KernelCall', kernel.function_name, fused_steps))
         arrays = {f.name: self.gpu_arrays[f.name] for f in kernel.fields}
+        if kernel.function_name not in self.kernel_io:          # for computationgraph.ComputationGraph
+            self.kernel_io[kernel.function_name] = ([f.name for f in kernel.ir.input_fields],
+                                                    [f.name for f in kernel.ir.output_fields])
         replicated = [n for n in arrays if n in self._replicated]
         if replicated:
             if len(replicated) != len(arrays):
@@ -473,7 +479,6 @@ class SlabDataHandling:
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
         for n in halo_fields:
-            self._record(('Communication', n, None, True))
             self.start_exchange(n)
         side = [r for r in (lo, hi) if r is not None]
         on_comm = bool(side) and self._comm_stream is not None and all(t.is_cuda for t in arrays.values())

@@ -559,3 +559,43 @@ def test_slab_ranges_cover_the_owned_planes_exactly_once():
                 assert lo_dep >= (g if rank > 0 else 0) and hi_dep <= n + g + (0 if rank < world - 1 else g)
             checked += 1
     assert checked > 100
+
+
+def test_computation_graph_of_a_recorded_time_loop(tmp_path):
+    """``ComputationGraph`` over the queue a ``SlabDataHandling`` records (tests/test_graph_datahandling.py:77-88 builds the
+    reference's from ``call_queue`` and writes a dot file): array versions, read / write maps, levels of independent calls."""
+    from pystencils_autodiff_b200 import configs
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.computationgraph import ComputationGraph
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+
+    class Silent(CompiledKernel):
+        def __call__(self, **kw):
+            pass
+
+    dh = SlabDataHandling((8, 10, 12), 0, 1, 1, device='cpu', backend='torch')
+    dh.add_arrays('u, out, diffout, diffu')
+    op = configs.heat3d_op(shape=dh.dec.local_shape)
+    fwd, bwd = Silent(op.forward_ast_gpu), Silent(op.backward_ast_gpu)
+    dh.run_kernel(fwd, halo_fields=['u'])
+    dh.run_kernel(bwd, halo_fields=['diffout'])          # independent of the forward kernel
+    dh.swap('u', 'out')
+    dh.run_kernel(fwd, halo_fields=['u'])
+    g = ComputationGraph(dh)
+    assert dh.kernel_io['heat3d_forward_gpu'] == (['u'], ['out']) and dh.kernel_io['heat3d_backward_gpu'] == (['diffout'], ['diffu'])
+    assert [n.kind for n in g.computation_nodes] == ['communication', 'kernel', 'communication', 'kernel', 'swap',
+                                                     'communication', 'kernel']
+    assert 'out #1' in g.writes and g.writes['out #1'].label == 'heat3d_forward_gpu'
+    assert [n.label for n in g.reads['u #1']] == ['heat3d_forward_gpu', 'Swap u <-> out']
+    levels = g.levels()
+    assert {n.label for n in levels[0]} == {'ghost planes of u', 'ghost planes of diffout'}
+    assert {n.label for n in levels[1]} == {'heat3d_forward_gpu', 'heat3d_backward_gpu'}      # may run concurrently
+    assert [n.kind for n in levels[2]] == ['swap'] and [n.kind for n in levels[-1]] == ['kernel']
+    dot = g.to_dot()
+    assert dot.startswith('digraph') and '"u #0" -> ' in dot and 'heat3d_backward_gpu' in dot
+    g.to_dot_file(str(tmp_path / 'graph.dot'), with_code=False)
+    assert (tmp_path / 'graph.dot').read_text() == dot
+    merged = ComputationGraph(dh.merge_swaps_with_kernel_calls(list(dh.call_queue)), dh.kernel_io)
+    assert len(merged.computation_nodes) == len(g.computation_nodes)
+    with pytest.raises(KeyError):
+        ComputationGraph([('KernelCall', 'unknown_kernel')])
