@@ -15,6 +15,9 @@ class ReplayKernel(CompiledKernel):
         tensors = [kwargs[f.name] for f in self.fields]
         scal = [float(kwargs[s_]) for s_ in self.scalars]
         variant = _variant or self._select_variant(tensors)
+        if variant.startswith('march') and self._components:
+            import pytest
+            pytest.skip('replay: structure-of-arrays component kernels are not modelled (per-component pointers)')
         if variant == 'march_x2':
             ek = self.emitted('march_x2')
         elif variant == 'march':
@@ -34,3 +37,5 @@ class ReplayKernel(CompiledKernel):
         else:
             emu.run(ek, arrays, scal, launch_range=rng)
         self.last_variant = 'march' if variant.startswith('march') else variant
+        self.last_instance = variant if variant != 'march' else \
+            ('march_nomask' if ek is self._emitted.get('march_nomask') else 'march')

@@ -16,7 +16,7 @@ def test_function_matches_reference_golden_vectors(name, mode):
     op = build_op(name, mode)
     ins, outs, grads = golden_arrays(name, mode)
     fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
-    constant = {f.name for f in op.constant_fields}
+    constant = {getattr(f, 'name', f) for f in op.constant_fields}        # the list also holds the name 'indexVector'
     tens = [torch.from_numpy(np.ascontiguousarray(ins[f.name])).cuda().requires_grad_(f.name not in constant)
             for f in op.forward_input_fields]
     res = fn.apply(*tens)
