@@ -19,7 +19,7 @@ if [ "${1:-single}" = "multi" ]; then
   exit 0
 fi
 # 1. the whole GPU suite (includes the CPU-replayed-only paths of round 1: slab fused steps, 2-D lifted pairs)
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
+python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
 #    the files added without a GPU at hand, without -x: every failure at once
 python -m pytest tests/test_gpu_zz_golden.py tests/test_gpu_zz_slab_steps.py -m gpu -q > gpurun_out/r2_pytest_gpu_new.log 2>&1
 echo "pytest (new files) rc=$?"; tail -15 gpurun_out/r2_pytest_gpu_new.log

@@ -5,7 +5,7 @@ import pytest
 
 from oracle import evaluate
 from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
-from pystencils_autodiff_b200.configs import heat3d_op, stencil27_op, tv_gradient_op
+from pystencils_autodiff_b200.configs import diffusion2d_op, heat3d_op, stencil27_op, tv_gradient_op
 
 pytestmark = pytest.mark.gpu
 
@@ -109,9 +109,20 @@ def test_fused_steps_error_behaviour():
     u = torch.zeros((8, 16, 32), device='cuda')
     with pytest.raises(ValueError, match='different tensors'):
         k(u=u, out=u, _variant='march_x2')
+    # a launch range is accepted for 3-D fused pairs (slab launches): whole-array range == no range, bit for bit
+    rng = np.random.default_rng(3)
+    u.copy_(torch.from_numpy(rng.standard_normal((8, 16, 32)).astype(np.float32)))
+    whole, ranged = torch.empty_like(u), torch.empty_like(u)
+    k(u=u, out=whole, _variant='march_x2')
+    k(u=u, out=ranged, _variant='march_x2',
+      _range=dict(iter_lo=[0, 0, 0], iter_hi=[8, 16, 32], write_lo=[0, 0, 0], write_hi=[8, 16, 32]))
+    assert torch.equal(whole, ranged)
+    # ... and still rejected for 2-D kernels lifted to one plane
+    k2 = CompiledKernel(diffusion2d_op(shape=(16, 32), boundary_handling='zeros').forward_ast_gpu)
+    u2 = torch.zeros((16, 32), device='cuda')
     with pytest.raises(ValueError, match='whole arrays'):
-        k(u=u, out=torch.empty_like(u), _variant='march_x2',
-          _range=dict(iter_lo=[0, 0, 0], iter_hi=[8, 16, 32], write_lo=[0, 0, 0], write_hi=[8, 16, 32]))
+        k2(u=u2, out=torch.empty_like(u2), _variant='march_x2',
+           _range=dict(iter_lo=[0, 0], iter_hi=[16, 32], write_lo=[0, 0], write_hi=[16, 32]))
     ut = torch.zeros((8, 16, 34), device='cuda')[:, :, 1:33]           # rows not 16-byte aligned -> generic kernel only
     with pytest.raises(ValueError, match='cannot be fused'):
         CompiledKernel(heat3d_op(shape=(8, 16, 32)).forward_ast_gpu).run_steps(ut, 2, fuse=True)
