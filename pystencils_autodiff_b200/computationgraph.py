@@ -29,7 +29,14 @@ class ComputationGraph:
             queue = data_handling_or_queue.call_queue
         else:
             queue = data_handling_or_queue
-        self.call_list = list(queue)
+        # a ``TimeloopRun`` contributes the calls of ONE of its steps (the reference nests a sub-graph of the loop's
+        # ``_single_step_asts``, computationgraph.py:71-74, sharing the write counter: the same versions result)
+        self.call_list = []
+        for c in queue:
+            if isinstance(c, tuple) and c and c[0] == 'TimeloopRun':
+                self.call_list.extend(c[2])
+            else:
+                self.call_list.append(c)
         self.kernel_io = dict(kernel_io or {})
         self.write_counter = {}
         self.reads = OrderedDict()          # snapshot -> nodes reading it

@@ -483,6 +483,11 @@ class SlabDataHandling:
         side = [r for r in (lo, hi) if r is not None]
         on_comm = bool(side) and self._comm_stream is not None and all(t.is_cuda for t in arrays.values())
         if on_comm:
+            # the side launches read inputs produced on the current stream (and write outputs whose previous user may
+            # still be pending there): order the communication stream behind it even when no exchange was started
+            # in this call (start_exchange records the same dependency; a second record / wait is harmless)
+            self._ev_ready.record(self.torch.cuda.current_stream(self.device))
+            self._comm_stream.wait_event(self._ev_ready)
             for r in side:
                 kernel(**arrays, **kwargs, _range=r, _stream=self._comm_stream.cuda_stream)
             self._ev_halo.record(self._comm_stream)
@@ -796,10 +801,17 @@ class TimeLoop:
     def __init__(self, data_handling, use_cuda_graph=True):
         self.dh = data_handling
         self._pre, self._post, self._steps = [], [], []
+        self._single_step_asts = []       # what one step consists of, in the reference's vocabulary (for TimeloopRun)
         self.time_steps_run = 0
-        self._graph = None
-        self._graph_parity = 0
+        self._graphs = {}                 # buffer roles at capture time -> CUDA graph of two steps
+        self._step_record = None          # what the data handling recorded during one executed step
         self.use_cuda_graph = use_cuda_graph
+
+    max_cached_graphs = 4
+
+    @property
+    def parent(self):                     # the reference's name for the data handling (graph_datahandling.py:155)
+        return self.dh
 
     def add_pre_run_function(self, f):
         self._pre.append(f)
@@ -809,7 +821,8 @@ class TimeLoop:
 
     def add_single_step_function(self, f):
         self._steps.append(f)
-        self._graph = None
+        self._graphs.clear()
+        self._step_record = None
 
     def add_call(self, functor, argument_list=None):
         args = argument_list if argument_list is not None else {}
@@ -818,50 +831,93 @@ class TimeLoop:
         for a in args:
             if isinstance(functor, CompiledKernel):
                 halo = a.pop('halo_fields', ()) if isinstance(a, dict) else ()
+                self._single_step_asts.append(('KernelCall', functor.function_name))
                 self.add_single_step_function(lambda k=functor, kw=a, h=halo: self.dh.run_kernel(k, halo_fields=h, **kw))
             else:
+                self._single_step_asts.append(('Call', getattr(functor, '__name__', type(functor).__name__)))
                 self.add_single_step_function(lambda f=functor, kw=a: f(**kw))
 
+    def swap(self, src, dst, is_gpu=True):
+        """graph_datahandling.py:192-197 appends a ``Swap`` to the step's record; here the step also performs it (the
+        reference only records because its queue is compiled later — this data handling executes)."""
+        src = src if isinstance(src, str) else src.name
+        dst = dst if isinstance(dst, str) else dst.name
+        self._single_step_asts.append(('Swap', src, dst))
+        self.add_single_step_function(lambda a=src, b=dst: self.dh.swap(a, b, is_gpu))
+
     def _one_step(self):
+        n = len(self.dh.call_queue)
         for f in self._steps:
             f()
+        if self._step_record is None:
+            self._step_record = tuple(self.dh.call_queue[n:])
+
+    def _roles(self):
+        """Identity of every registered buffer under its current name: what a captured graph has baked in."""
+        return tuple((n, t.data_ptr(), tuple(t.shape)) for n, t in self.dh.gpu_arrays.items())
+
+    def _capture_two_steps(self):
+        """Two steps as one CUDA graph (a step that swaps buffers is only periodic with period 2).  Capturing executes
+        the steps' host side — the swaps — but no kernel, so the registry is put back afterwards; a step sequence that is
+        not back at the same buffer roles after two steps (a three-buffer rotation) cannot be replayed: None."""
+        torch, dh = self.dh.torch, self.dh
+        before = OrderedDict(dh.gpu_arrays)
+        roles, n_swaps, n_calls = self._roles(), dh._swap_count, len(dh.call_queue)
+        stream = torch.cuda.Stream(dh.device)
+        stream.wait_stream(torch.cuda.current_stream(dh.device))
+        with torch.cuda.stream(stream):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                self._one_step()
+                self._one_step()
+        torch.cuda.current_stream(dh.device).wait_stream(stream)
+        periodic = self._roles() == roles
+        dh.gpu_arrays.clear()
+        dh.gpu_arrays.update(before)
+        dh._swap_count = n_swaps
+        del dh.call_queue[n_calls:]
+        return g if periodic else None
 
     def run(self, time_steps=1):
-        torch = self.dh.torch
-        for f in self._pre:
-            f()
+        """Like graph_datahandling.py:181-190: the calls of the steps are not appended to the data handling's queue one by
+        one; the queue gets ONE ``('TimeloopRun', time_steps, steps)`` entry."""
+        torch, dh = self.dh.torch, self.dh
+        former_queue = dh.call_queue
+        dh.call_queue = []
         swaps_per_step = None
-        graph_ok = (self.use_cuda_graph and self.dh.dec.world_size == 1 and torch.cuda.is_available()
-                    and all(t.is_cuda for t in self.dh.gpu_arrays.values()))
-        if graph_ok and time_steps >= 4:
-            # warm up (NVRTC / module load must not happen during capture), then capture TWO steps: a step that
-            # swaps buffers is only periodic with period 2
-            n0 = self.dh._swap_count
-            self._one_step()
-            self._one_step()
-            swaps_per_step = (self.dh._swap_count - n0) // 2
-            done = 2
-            if self._graph is None:
-                stream = torch.cuda.Stream(self.dh.device)
-                stream.wait_stream(torch.cuda.current_stream(self.dh.device))
-                with torch.cuda.stream(stream):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=stream):
-                        self._one_step()
-                        self._one_step()
-                torch.cuda.current_stream(self.dh.device).wait_stream(stream)
-                self._graph = g
-            while done + 2 <= time_steps:
-                self._graph.replay()
-                done += 2
+        try:
+            for f in self._pre:
+                f()
+            graph_ok = (self.use_cuda_graph and dh.dec.world_size == 1 and torch.cuda.is_available()
+                        and all(t.is_cuda for t in dh.gpu_arrays.values()))
+            done = 0
+            if graph_ok and time_steps >= 4:
+                # warm up (NVRTC / module load must not happen during capture)
+                n0 = dh._swap_count
+                self._one_step()
+                self._one_step()
+                swaps_per_step = (dh._swap_count - n0) // 2
+                done = 2
+                # a graph bakes the buffer pointers in: it is only valid for the roles it was captured with (an odd
+                # number of steps in an earlier run, an external swap or a replaced array all change them)
+                roles = self._roles()
+                if roles not in self._graphs:
+                    if len(self._graphs) >= self.max_cached_graphs:
+                        self._graphs.clear()
+                    self._graphs[roles] = self._capture_two_steps()
+                graph = self._graphs[roles]
+                while graph is not None and done + 2 <= time_steps:
+                    graph.replay()
+                    done += 2
             for _ in range(time_steps - done):
                 self._one_step()
-        else:
-            for _ in range(time_steps):
-                self._one_step()
-        self.time_steps_run += time_steps
-        for f in self._post:
-            f()
+            self.time_steps_run += time_steps
+            for f in self._post:
+                f()
+        finally:
+            recorded = self._step_record if self._step_record is not None else tuple(self._single_step_asts)
+            dh.call_queue = former_queue
+            dh._record(('TimeloopRun', time_steps, recorded))
         return swaps_per_step
 
 

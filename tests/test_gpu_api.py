@@ -247,13 +247,54 @@ def test_timeloop_with_swap_and_cuda_graph_replay():
         torch.cuda.synchronize()
         assert tl.time_steps_run == T
         results.append(dh.owned('u').clone())
-        kinds = [c[0] for c in dh.call_queue]
-        assert kinds.count('KernelCall') >= 2 and 'Swap' in kinds
+        # graph_datahandling.py:181-190: the run is ONE queue entry holding what a step consists of
+        kind, steps, recorded = dh.call_queue[-1]
+        assert kind == 'TimeloopRun' and steps == T and [c[0] for c in recorded] == ['KernelCall', 'Swap']
+        assert not any(c[0] == 'KernelCall' for c in dh.call_queue)
     assert torch.equal(results[0], results[1])
     ref = U0
     for _ in range(T):
         ref = evaluate(op.forward_assignments, dict(u=ref), 'zeros')['out']
     assert np.abs(results[0].cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_timeloop_graph_follows_the_buffer_roles():
+    """a captured graph bakes buffer pointers in.  ``run(5)`` leaves ``u`` / ``out`` swapped after its odd
+    eager tail step, an external ``swap`` or a replaced array changes the roles too — each must re-capture (or reuse the
+    graph captured for exactly those roles), never replay a stale one."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    shape = (64, 128)
+    op = make_config('c2', shape=shape)
+    kern = CompiledKernel(op.forward_ast_gpu)
+    U0 = np.random.default_rng(5).normal(size=shape).astype(np.float32)
+    finals = []
+    for use_graph in (True, False):
+        dh = SlabDataHandling(shape, 0, 1, 0, device='cuda:0')
+        dh.add_arrays('u, out', dtype=np.float32)
+        dh.owned('u').copy_(_t(U0))
+        tl = dh.create_timeloop(use_cuda_graph=use_graph)
+        tl.add_call(kern, {})
+        tl.swap('u', 'out')
+        tl.run(5)
+        tl.run(4)                                  # roles swapped relative to the first capture
+        dh.swap('u', 'out')
+        dh.swap('u', 'out')
+        tl.run(6)
+        fresh = dh.owned('u').clone()              # a replaced array: same values, new pointer
+        dh.gpu_arrays['u'] = fresh
+        tl.run(7)
+        torch.cuda.synchronize()
+        assert tl.time_steps_run == 22
+        if use_graph:
+            assert len(tl._graphs) >= 2 and all(g is not None for g in tl._graphs.values())
+        finals.append(dh.owned('u').clone())
+    assert torch.equal(finals[0], finals[1])
+    ref = U0
+    for _ in range(22):
+        ref = evaluate(op.forward_assignments, dict(u=ref), 'zeros')['out']
+    assert np.abs(finals[0].cpu().numpy() - ref).max() <= 4e-6 * np.abs(ref).max()
 
 
 def test_tensor_field_front_door():
