@@ -14,6 +14,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.no_launch          # the launches happen in the rank processes this test starts
 @pytest.mark.parametrize('name,bh', [('c3', 'zeros'), ('c3', 'none'), ('c4', 'zeros'), ('c2', 'zeros'), ('c5', 'zeros')])
 def test_sharded_equals_unsharded(name, bh):
     n = _ngpu()
