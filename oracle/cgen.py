@@ -23,8 +23,7 @@ import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
-from pystencils_autodiff_b200.assignment import coerce_assignments
-from pystencils_autodiff_b200.field import Field
+from ._model import as_collection, field_dtype, ghost_width, is_access, offsets_of
 
 _BUILD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_build')
 _CTYPES = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
@@ -55,24 +54,24 @@ def generate_c(assignments, boundary_handling=None, function_name='kernel', open
     """Returns ``(c_source, field_names, scalar_names)``; the function signature is
     ``void f(void** fields, const int64_t* shape, const int64_t* strides, const double* scalars)`` with
     ``strides[f*4 + d]`` in elements."""
-    ac = coerce_assignments(assignments)
+    ac = as_collection(assignments)
     mode = _mode(boundary_handling)
-    reads = sorted(set().union(*[a.rhs.atoms(Field.Access) for a in ac.all_assignments]), key=str)
+    reads = ac.reads()
     writes = [a.lhs for a in ac.main_assignments]
-    scalars = sorted([s for s in ac.free_symbols if not isinstance(s, Field.Access)], key=str)
+    scalars = sorted([s for s in ac.free_symbols if not is_access(s)], key=str)
     out_fields = sorted({w.field for w in writes}, key=str)
     in_fields = sorted({r.field for r in reads}, key=str)
     all_fields = out_fields + [f for f in in_fields if f not in out_fields]
     fidx = {f.name: i for i, f in enumerate(all_fields)}
     ndim = all_fields[0].spatial_dimensions
-    gl = 0 if mode == 'zeros' else max([a.required_ghost_layers for a in reads + writes] + [0])
+    gl = 0 if mode == 'zeros' else max([ghost_width(a) for a in reads + writes] + [0])
 
     pr = _Printer()
     lines = ['#include <stdint.h>', '#include <math.h>', '',
              'void %s(void** fields, const int64_t* shape, const int64_t* strides, const double* scalars)' % function_name,
              '{']
     for f in all_fields:
-        ct = _CTYPES[f.dtype.numpy_dtype]
+        ct = _CTYPES[field_dtype(f)]
         const = '' if f in out_fields else 'const '
         lines.append('  %s%s* restrict _data_%s = (%s%s*) fields[%d];' % (const, ct, f.name, const, ct, fidx[f.name]))
     for k in range(ndim):
@@ -84,14 +83,14 @@ def generate_c(assignments, boundary_handling=None, function_name='kernel', open
         lines.append('  const double %s = scalars[%d];' % (s.name, i))
 
     def addr(a):
-        terms = ['_stride_%s_%d*(ctr_%d%+d)' % (a.field.name, k, k, int(o)) for k, o in enumerate(a.offsets)]
+        terms = ['_stride_%s_%d*(ctr_%d%+d)' % (a.field.name, k, k, int(o)) for k, o in enumerate(offsets_of(a))]
         terms += ['_stride_%s_%d*%d' % (a.field.name, ndim + j, int(i)) for j, i in enumerate(a.index)]
         return '_data_%s[%s]' % (a.field.name, ' + '.join(terms))
 
     def read_expr(a):
-        if mode == 'zeros' and any(o != 0 for o in a.offsets):
+        if mode == 'zeros' and any(o != 0 for o in offsets_of(a)):
             conds = []
-            for k, o in enumerate(a.offsets):
+            for k, o in enumerate(offsets_of(a)):
                 if o != 0:
                     conds.append('ctr_%d%+d < 0 || ctr_%d%+d >= _size_%d' % (k, int(o), k, int(o), k))
             return '((%s) ? 0.0 : (double) %s)' % (' || '.join(conds), addr(a))
@@ -112,7 +111,7 @@ def generate_c(assignments, boundary_handling=None, function_name='kernel', open
     for a in ac.subexpressions:
         lines.append(ind + 'const double %s = %s;' % (pr.doprint(a.lhs), pr.doprint(a.rhs.xreplace(local))))
     for a in ac.main_assignments:
-        ct = _CTYPES[a.lhs.field.dtype.numpy_dtype]
+        ct = _CTYPES[field_dtype(a.lhs.field)]
         lines.append(ind + '%s = (%s) (%s);' % (addr(a.lhs), ct, pr.doprint(a.rhs.xreplace(local))))
     for k in reversed(range(ndim)):
         lines.append('  ' * (k + 1) + '}')
@@ -140,7 +139,7 @@ class CompiledCKernel:
         ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         strides = (ctypes.c_int64 * (4 * len(arrs)))()
         for i, a in enumerate(arrs):
-            assert a.dtype == self._fields[self.field_names[i]].dtype.numpy_dtype, self.field_names[i]
+            assert a.dtype == field_dtype(self._fields[self.field_names[i]]), self.field_names[i]
             for d, s in enumerate(a.strides):
                 strides[4 * i + d] = s // a.itemsize
         sc = (ctypes.c_double * max(1, len(self.scalar_names)))(*[float(kwargs[n]) for n in self.scalar_names])
@@ -159,7 +158,7 @@ def _cpu_tag():
 
 
 def compile_c(assignments, boundary_handling=None, function_name='kernel', flavour='fast', openmp=True):
-    ac = coerce_assignments(assignments)
+    ac = as_collection(assignments)
     src, field_names, scalar_names = generate_c(ac, boundary_handling, function_name, openmp)
     flags = FLAGS[flavour]
     key = hashlib.md5((src + ' '.join(flags) + (_cpu_tag() if '-march=native' in flags else '')).encode()).hexdigest()
@@ -172,6 +171,6 @@ def compile_c(assignments, boundary_handling=None, function_name='kernel', flavo
         tmp = so_path + '.tmp%d' % os.getpid()
         subprocess.check_call(['gcc'] + flags + ['-shared', '-o', tmp, c_path, '-lm'])
         os.replace(tmp, so_path)
-    reads = set().union(*[a.rhs.atoms(Field.Access) for a in ac.all_assignments])
+    reads = set(ac.reads())
     fields = {a.field for a in reads} | {a.lhs.field for a in ac.main_assignments}
     return CompiledCKernel(so_path, function_name, field_names, scalar_names, src, fields)

@@ -25,9 +25,8 @@ Semantics restated:
 import numpy as np
 import sympy as sp
 
-from pystencils_autodiff_b200.assignment import coerce_assignments
-from pystencils_autodiff_b200.field import Field
-from pystencils_autodiff_b200.transformations import ConditionalFieldAccess
+from ._model import (as_collection, conditional_accesses_in, field_dtype, ghost_width, index_tail as _index_tail, is_access,
+                     offsets_of, spatial_shape)
 
 __all__ = ['evaluate', 'evaluate_literal', 'evaluate_loops', 'forward_backward']
 
@@ -42,25 +41,11 @@ def _mode(boundary_handling):
 
 
 def _accesses(ac):
-    # every access on a right-hand side, including a ``+=`` form's read of its own output (_autodiff.py:110-113)
-    reads = sorted(set().union(*[a.rhs.atoms(Field.Access) for a in ac.all_assignments]), key=str)
-    writes = [a.lhs for a in ac.main_assignments]
-    return reads, writes
+    return ac.reads(), ac.writes()
 
 
 def _spatial_shape(ac, arrays):
-    reads, writes = _accesses(ac)
-    for a in reads + writes:
-        if a.field.name in arrays:
-            return tuple(arrays[a.field.name].shape[:a.field.spatial_dimensions])
-    for a in reads + writes:
-        if a.field.has_fixed_shape:
-            return tuple(int(s) for s in a.field.spatial_shape)
-    raise ValueError('cannot infer the iteration shape')
-
-
-def _index_tail(a):
-    return tuple(int(i) for i in a.index)
+    return spatial_shape(as_collection(ac), arrays)
 
 
 def evaluate(assignments, arrays, boundary_handling=None, scalars=None, ghost_layers=None,
@@ -69,7 +54,7 @@ def evaluate(assignments, arrays, boundary_handling=None, scalars=None, ghost_la
 
     Returns ``{output field name: ndarray}`` (fresh arrays, zero where the kernel does not write).
     """
-    ac = coerce_assignments(assignments)
+    ac = as_collection(assignments)
     mode = _mode(boundary_handling)
     scalars = dict(scalars or {})
     reads, writes = _accesses(ac)
@@ -80,8 +65,8 @@ def evaluate(assignments, arrays, boundary_handling=None, scalars=None, ghost_la
     elif ghost_layers is not None:
         gl = int(ghost_layers)
     else:
-        gl = max([a.required_ghost_layers for a in reads + writes] + [0])
-    pad = max([a.required_ghost_layers for a in reads] + [0])
+        gl = max([ghost_width(a) for a in reads + writes] + [0])
+    pad = max([ghost_width(a) for a in reads] + [0])
 
     region_lo = [gl] * ndim
     region_hi = [n - gl for n in shape]
@@ -93,10 +78,10 @@ def evaluate(assignments, arrays, boundary_handling=None, scalars=None, ghost_la
         tail = _index_tail(a)
         if mode == 'zeros':
             padded = np.pad(arr, [(pad, pad)] * ndim + [(0, 0)] * (arr.ndim - ndim))
-            sl = tuple(slice(pad + o + l, pad + o + h) for o, l, h in zip(a.offsets, region_lo, region_hi))
+            sl = tuple(slice(pad + o + l, pad + o + h) for o, l, h in zip(offsets_of(a), region_lo, region_hi))
             v = padded[sl]
         else:
-            sl = tuple(slice(o + l, o + h) for o, l, h in zip(a.offsets, region_lo, region_hi))
+            sl = tuple(slice(o + l, o + h) for o, l, h in zip(offsets_of(a), region_lo, region_hi))
             v = arr[sl]
         if tail:
             v = v[(Ellipsis,) + tail]
@@ -104,7 +89,7 @@ def evaluate(assignments, arrays, boundary_handling=None, scalars=None, ghost_la
 
     env = {a: read_view(a) for a in reads}
     for s in ac.free_symbols:
-        if not isinstance(s, Field.Access):
+        if not is_access(s):
             if s.name not in scalars:
                 raise KeyError('missing scalar %s' % s.name)
             env[s] = compute_dtype(scalars[s.name])
@@ -125,11 +110,11 @@ def evaluate(assignments, arrays, boundary_handling=None, scalars=None, ghost_la
         f = a.lhs.field
         if f.name not in out:
             full_shape = shape + tuple(int(s) for s in f.index_shape)
-            out[f.name] = np.zeros(full_shape, dtype=f.dtype.numpy_dtype)
+            out[f.name] = np.zeros(full_shape, dtype=field_dtype(f))
         val = ev(a.rhs)
-        sl = tuple(slice(l + o, h + o) for o, l, h in zip(a.lhs.offsets, region_lo, region_hi))
+        sl = tuple(slice(l + o, h + o) for o, l, h in zip(offsets_of(a.lhs), region_lo, region_hi))
         tail = _index_tail(a.lhs)
-        out[f.name][sl + tail if tail else sl] = val.astype(f.dtype.numpy_dtype)
+        out[f.name][sl + tail if tail else sl] = val.astype(field_dtype(f))
     return out
 
 
@@ -137,7 +122,7 @@ def evaluate_literal(assignments, arrays, scalars=None, compute_dtype=np.float64
     """Evaluate a collection in the reference's *symbolic* ``'zeros'`` form (``ConditionalFieldAccess`` nodes,
     transformations.py:26-30) literally: every cell, index grids, condition → 0.  Independent of the padding trick
     in :func:`evaluate`; used to cross-check it."""
-    ac = coerce_assignments(assignments)
+    ac = as_collection(assignments)
     scalars = dict(scalars or {})
     shape = _spatial_shape(ac, arrays)
     ndim = len(shape)
@@ -146,20 +131,20 @@ def evaluate_literal(assignments, arrays, scalars=None, compute_dtype=np.float64
 
     def access_value(a):
         arr = np.asarray(arrays[a.field.name])
-        idx = tuple(np.clip(grids[k] + int(a.offsets[k]), 0, shape[k] - 1) for k in range(ndim))
+        idx = tuple(np.clip(grids[k] + offsets_of(a)[k], 0, shape[k] - 1) for k in range(ndim))
         v = arr[idx + _index_tail(a)] if a.index else arr[idx]
         return v.astype(compute_dtype)
 
     env = dict(ctr)
     for s in set(ac.free_symbols) | set(_accesses(ac)[0]):
-        if isinstance(s, Field.Access):
+        if is_access(s):
             env[s] = access_value(s)
         elif s not in ctr:
             env[s] = compute_dtype(scalars[s.name])
 
     def ev(expr):
         repl = {}
-        for c in expr.atoms(ConditionalFieldAccess):
+        for c in conditional_accesses_in(expr):
             cond_syms = sorted(c.outofbounds_condition.free_symbols, key=str)
             cond = sp.lambdify(cond_syms, c.outofbounds_condition, modules='numpy')(*[env[s] for s in cond_syms])
             d = sp.Dummy()
@@ -177,9 +162,9 @@ def evaluate_literal(assignments, arrays, scalars=None, compute_dtype=np.float64
     for a in ac.main_assignments:
         f = a.lhs.field
         if f.name not in out:
-            out[f.name] = np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=f.dtype.numpy_dtype)
+            out[f.name] = np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=field_dtype(f))
         tail = _index_tail(a.lhs)
-        out[f.name][(Ellipsis,) + tail if tail else Ellipsis] = ev(a.rhs).astype(f.dtype.numpy_dtype)
+        out[f.name][(Ellipsis,) + tail if tail else Ellipsis] = ev(a.rhs).astype(field_dtype(f))
     return out
 
 
@@ -188,17 +173,17 @@ def evaluate_loops(assignments, arrays, boundary_handling=None, scalars=None):
     generated kernels' per-cell body (SURVEY.md Appendix C sketch)."""
     import itertools
     import math
-    ac = coerce_assignments(assignments)
+    ac = as_collection(assignments)
     mode = _mode(boundary_handling)
     scalars = dict(scalars or {})
     reads, writes = _accesses(ac)
     shape = _spatial_shape(ac, arrays)
     ndim = len(shape)
-    gl = 0 if mode == 'zeros' else max([a.required_ghost_layers for a in reads + writes] + [0])
+    gl = 0 if mode == 'zeros' else max([ghost_width(a) for a in reads + writes] + [0])
     out = {}
     for a in ac.main_assignments:
         f = a.lhs.field
-        out.setdefault(f.name, np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=f.dtype.numpy_dtype))
+        out.setdefault(f.name, np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=field_dtype(f)))
     all_syms = sorted(set(ac.free_symbols) | set(reads), key=str)
     sub_fns = [(a.lhs, sp.lambdify(sorted(a.rhs.free_symbols, key=str), a.rhs, modules='math'),
                 sorted(a.rhs.free_symbols, key=str)) for a in ac.subexpressions]
@@ -207,8 +192,8 @@ def evaluate_loops(assignments, arrays, boundary_handling=None, scalars=None):
     for c in itertools.product(*[range(gl, n - gl) for n in shape]):
         env = {}
         for s in all_syms:
-            if isinstance(s, Field.Access):
-                idx = tuple(ci + o for ci, o in zip(c, s.offsets))
+            if is_access(s):
+                idx = tuple(ci + o for ci, o in zip(c, offsets_of(s)))
                 if all(0 <= i < n for i, n in zip(idx, shape)):
                     env[s] = float(arrays[s.field.name][idx + _index_tail(s)])
                 else:
@@ -219,7 +204,7 @@ def evaluate_loops(assignments, arrays, boundary_handling=None, scalars=None):
         for lhs, fn, syms in sub_fns:
             env[lhs] = _safe(fn, [env[s] for s in syms], math)
         for lhs, fn, syms in main_fns:
-            idx = tuple(ci + o for ci, o in zip(c, lhs.offsets))
+            idx = tuple(ci + o for ci, o in zip(c, offsets_of(lhs)))
             out[lhs.field.name][idx + _index_tail(lhs)] = _safe(fn, [env[s] for s in syms], math)
     return out
 
@@ -251,6 +236,6 @@ def forward_backward(op, inputs, grads, scalars=None, compute_dtype=np.float64):
     for f in op.backward_output_fields:
         if f.name not in env:
             shape = _spatial_shape(op.backward_assignments, env)
-            env[f.name] = np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=f.dtype.numpy_dtype)
+            env[f.name] = np.zeros(shape + tuple(int(s) for s in f.index_shape), dtype=field_dtype(f))
     din = evaluate(op.backward_assignments, env, bh, scalars, compute_dtype=compute_dtype)
     return outs, din
