@@ -60,6 +60,11 @@ class CompiledKernel:
         self.scalars = [s.name for s in ir.scalars]
         self.last_variant = None
         self._torch_dtypes = None
+        # repeated launches (time loops, autograd Functions on the same buffers): everything the checks below derive from
+        # (variant request, range, tensor identity = pointer + shape + strides + dtype) is remembered, so a repeat costs
+        # one dictionary lookup and the C call
+        self._field_names = [f.name for f in self.fields]
+        self._fast = {}
 
     # -- introspection ---------------------------------------------------------------------------------------
     @property
@@ -160,7 +165,23 @@ class CompiledKernel:
                     return 'generic'
         return 'march'
 
+    max_remembered_launches = 64
+
     def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
+        try:
+            key = [_variant, id(_range)]
+            for n in self._field_names:
+                t = kwargs[n]
+                key += (t.data_ptr(), t.shape, t.stride(), t.dtype, t.is_cuda)
+            hit = self._fast.get(tuple(key))
+        except (KeyError, AttributeError, RuntimeError):
+            hit = key = None        # missing / non-tensor argument: the checks below say what is wrong
+        if hit is not None and hit[4] is _range:
+            native, fa, n, dev_index, _, range_ref, self.last_variant, self.last_instance = hit
+            if _stream is None:
+                _stream = _raw_current_stream(dev_index)
+            native.launch_packed(fa, n, [float(kwargs[s]) for s in self.scalars] if self.scalars else (), _stream, range_ref)
+            return None
         import torch
         if self._torch_dtypes is None:
             self._torch_dtypes = {f.name: numpy_dtype_to_torch(f.dtype.numpy_dtype) for f in self.fields}
@@ -232,13 +253,33 @@ class CompiledKernel:
                 st = list(t.stride()[:nd]) + [0] * (3 - nd)
                 st.append(t.stride(nd) if f.index_dimensions else 0)
                 field_args.append((t.data_ptr(), tuple(t.shape[:nd]), st))
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         with torch.cuda.device(dev):
             stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
-            self.native(variant, dev.index if dev.index is not None else torch.cuda.current_device()).launch(
-                field_args, scal, stream, _range)
+            native = self.native(variant, dev_index)
+            native.launch(field_args, scal, stream, _range)
         self.last_variant = 'march' if variant.startswith('march') else variant
         self.last_instance = variant
+        # remember the validated launch (the range dict is held: its id() cannot be reused while the entry lives)
+        if key is not None and (_range is None or '_ctypes' in _range):
+            if len(self._fast) >= self.max_remembered_launches:
+                self._fast.clear()
+            range_ref = None
+            if _range is not None:
+                import ctypes
+                range_ref = ctypes.byref(_range['_ctypes'])
+            self._fast[tuple(key)] = (native, native.pack_fields(field_args), len(field_args), dev_index, _range, range_ref,
+                                      self.last_variant, self.last_instance)
         return None
+
+
+def _raw_current_stream(device_index):
+    """``cudaStream_t`` of torch's current stream as an integer (the private fast accessor when it exists)."""
+    import torch
+    try:
+        return torch._C._cuda_getCurrentRawStream(device_index)
+    except AttributeError:
+        return torch.cuda.current_stream(device_index).cuda_stream
 
 
 _KERNEL_CACHE = {}

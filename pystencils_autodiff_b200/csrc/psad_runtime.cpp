@@ -66,6 +66,8 @@ struct Driver {
   CUresult (*cuCtxGetCurrent)(CUcontext*);
   CUresult (*cuCtxSetCurrent)(CUcontext);
   CUresult (*cuCtxGetDevice)(CUdevice*);
+  CUresult (*cuCtxPushCurrent)(CUcontext);
+  CUresult (*cuCtxPopCurrent)(CUcontext*);
   CUresult (*cuDevicePrimaryCtxRetain)(CUcontext*, CUdevice);
   CUresult (*cuModuleLoadData)(CUmodule*, const void*);
   CUresult (*cuModuleUnload)(CUmodule);
@@ -96,6 +98,7 @@ static void load_driver() {
   bool ok = sym(lib, "cuInit", d.cuInit, e) && sym(lib, "cuDeviceGet", d.cuDeviceGet, e) &&
             sym(lib, "cuDeviceGetAttribute", d.cuDeviceGetAttribute, e) && sym(lib, "cuCtxGetCurrent", d.cuCtxGetCurrent, e) &&
             sym(lib, "cuCtxSetCurrent", d.cuCtxSetCurrent, e) && sym(lib, "cuCtxGetDevice", d.cuCtxGetDevice, e) &&
+            sym(lib, "cuCtxPushCurrent_v2", d.cuCtxPushCurrent, e) && sym(lib, "cuCtxPopCurrent_v2", d.cuCtxPopCurrent, e) &&
             sym(lib, "cuDevicePrimaryCtxRetain", d.cuDevicePrimaryCtxRetain, e) &&
             sym(lib, "cuModuleLoadData", d.cuModuleLoadData, e) && sym(lib, "cuModuleUnload", d.cuModuleUnload, e) &&
             sym(lib, "cuModuleGetFunction", d.cuModuleGetFunction, e) && sym(lib, "cuFuncSetAttribute", d.cuFuncSetAttribute, e) &&
@@ -309,6 +312,27 @@ extern "C" int psad_compile(const char* source, const char* cache_key, const cha
 
 // ---------------------------------------------------------------------------------------------------------------
 // kernel objects
+// One remembered launch: what was passed (the key) and everything derived from it that does not depend on the scalars —
+// the parameter block, the grid and the encoded tensor maps.  A time loop or an autograd Function launches the same
+// kernel on the same few buffers over and over; re-validating the arguments and re-encoding every tensor map
+// (cuTensorMapEncodeTiled) on each launch was most of the host cost of a launch.
+struct LaunchKey {
+  int n_fields;
+  int has_range;
+  psad_field_arg_t fields[PSAD_MAX_FIELDS];
+  psad_range_t range;
+};
+struct alignas(64) TensorMaps { CUtensorMap m[PSAD_MAX_FIELDS]; };
+struct LaunchEntry {
+  LaunchKey key;
+  PsadArgs args;
+  unsigned grid[3];
+  int empty;
+  TensorMaps tm;
+  unsigned long long stamp;
+};
+static const int PSAD_LAUNCH_CACHE = 16;
+
 struct psad_kernel {
   psad_plan_t plan;
   CUmodule module = nullptr;
@@ -317,7 +341,12 @@ struct psad_kernel {
   int sm_count = 0;
   int occupancy = 1;  // resident CTAs per SM for this kernel (march: persistent grid = sm_count * occupancy)
   std::string name;
+  std::mutex cache_mutex;                 // launches of one kernel may come from several threads (autograd workers)
+  std::vector<LaunchEntry*> cache;        // most recently used launches, at most PSAD_LAUNCH_CACHE
+  unsigned long long cache_clock = 0;
+  ~psad_kernel() { for (LaunchEntry* e : cache) delete e; }
 };
+static std::atomic<unsigned long long> g_cache_hits{0}, g_cache_misses{0};
 
 extern "C" int psad_kernel_create(const char* source, const char* kernel_name, const char* cache_key,
                                   const char* const* options, int n_options, const psad_plan_t* plan,
@@ -414,6 +443,14 @@ static int build_args(const psad_plan_t& P, const char* kname, int sm_count, int
       if (A.wr_lo[e] < 0 || A.wr_hi[e] > A.shape[e])
         return fail(PSAD_ERR_INVALID, "%s: write range [%lld, %lld) outside the array extent %lld in dim %d", kname,
                     A.wr_lo[e], A.wr_hi[e], A.shape[e], d);
+      // Evaluated cells read c + offset.  The generic kernel with interior iteration (boundary 0) reads unguarded, so
+      // every evaluated cell must keep `ghost_layers` cells to each array edge; everywhere else out-of-array reads are
+      // zero-filled (TMA boxes of the march kernels) or index-guarded ('zeros'), but the evaluated cell must exist.
+      const long long margin = (P.boundary == 0 && P.kind == PSAD_KIND_GENERIC) ? P.ghost_layers : 0;
+      if (A.it_hi[e] > A.it_lo[e] && (A.it_lo[e] < margin || A.it_hi[e] > A.shape[e] - margin))
+        return fail(PSAD_ERR_INVALID, "%s: iteration range [%lld, %lld) in dim %d must lie inside [%lld, %lld) of the array "
+                    "(extent %lld, %d ghost layers, boundary %s)", kname, A.it_lo[e], A.it_hi[e], d, margin,
+                    A.shape[e] - margin, A.shape[e], P.ghost_layers, P.boundary == 0 ? "none" : "zeros");
     }
   } else if (P.boundary == 0 && P.ghost_layers > 0) {
     for (int d = 0; d < nd; ++d) {
@@ -506,49 +543,113 @@ extern "C" int psad_plan_launch(const psad_plan_t* plan, int sm_count, int ctas_
   return 0;
 }
 
+static int encode_tensor_maps(const psad_plan_t& P, const PsadArgs& A, int n_fields, TensorMaps& TM) {
+  const int nd = P.ndim;
+  int n_tma = 0;
+  // L2 promotion of TMA requests: 0 none, 1 64B, 2 128B, 3 256B (PSAD_L2PROMO overrides for experiments)
+  static const int l2promo = getenv("PSAD_L2PROMO") ? atoi(getenv("PSAD_L2PROMO")) : 3;
+  for (int f = 0; f < n_fields; ++f) {
+    const psad_field_plan_t& fp = P.field[f];
+    if (!fp.tma) continue;
+    unsigned long long gdim[3] = {(unsigned long long)A.shape[2], (unsigned long long)A.shape[1], (unsigned long long)A.shape[0]};
+    unsigned long long gstr[2] = {(unsigned long long)A.stride[f][1] * fp.elem_size, (unsigned long long)A.stride[f][0] * fp.elem_size};
+    unsigned box[3] = {(unsigned)fp.box[0], (unsigned)fp.box[1], (unsigned)(nd == 3 ? fp.box[2] : 1)};
+    unsigned estr[3] = {1, 1, 1};
+    for (int d = 0; d < nd; ++d)
+      if (box[d] < 1 || box[d] > 256) return fail(PSAD_ERR_INVALID, "TMA box dim %d = %u out of range", d, box[d]);
+    CUresult r = g_drv.cuTensorMapEncodeTiled(&TM.m[n_tma], fp.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                              (unsigned)nd, A.ptr[f], gdim, gstr, box, estr,
+                                              /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion*/ l2promo, /*oob fill: zeros*/ 0);
+    if (r != 0) return cu_fail(r, "cuTensorMapEncodeTiled");
+    ++n_tma;
+  }
+  return 0;
+}
+
 extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields,
                                   const double* scalars, int n_scalars, const psad_range_t* range, void* stream) {
   if (!k || !fields) return fail(PSAD_ERR_INVALID, "psad_kernel_launch: null argument");
   const psad_plan_t& P = k->plan;
+  if (n_fields != P.n_fields) return fail(PSAD_ERR_INVALID, "%s: expected %d fields, got %d", k->name.c_str(), P.n_fields, n_fields);
+  if (n_scalars != P.n_scalars) return fail(PSAD_ERR_INVALID, "%s: expected %d scalars, got %d", k->name.c_str(), P.n_scalars, n_scalars);
+  if (n_scalars > 0 && !scalars) return fail(PSAD_ERR_INVALID, "null scalars");
+  static const bool debug = getenv("PSAD_DEBUG") != nullptr;
+  static const bool no_cache = getenv("PSAD_NO_LAUNCH_CACHE") != nullptr;
+
+  // the calling thread needs the kernel's context: none current (an autograd worker) -> make it current; another device's
+  // context current -> push ours for the duration of the launch
+  CUcontext cur = nullptr;
+  CU_CHECK(g_drv.cuCtxGetCurrent(&cur));
+  bool pushed = false;
+  if (cur == nullptr) {
+    CU_CHECK(g_drv.cuCtxSetCurrent(k->ctx));
+  } else if (cur != k->ctx) {
+    CU_CHECK(g_drv.cuCtxPushCurrent(k->ctx));
+    pushed = true;
+  }
+  struct PopGuard { bool on; ~PopGuard() { if (on) { CUcontext c; g_drv.cuCtxPopCurrent(&c); } } } guard{pushed};
+
+  // parameter block + tensor maps: from the launch cache when this (buffers, shapes, strides, range) was seen before
+  LaunchKey key;
+  memset(&key, 0, sizeof(key));
+  key.n_fields = n_fields;
+  memcpy(key.fields, fields, sizeof(psad_field_arg_t) * (size_t)n_fields);
+  if (range) { key.has_range = 1; key.range = *range; }
   PsadArgs A;
+  TensorMaps TM;
   unsigned grid[3];
   int empty = 0;
-  if (int rc = build_args(P, k->name.c_str(), k->sm_count, k->occupancy, fields, n_fields, scalars, n_scalars, range, A, grid, &empty)) return rc;
-  if (empty) return 0;
-  if (int rc = ensure_context(k->ctx)) return rc;
-  const int nd = P.ndim;
-  void* params[2];
-  params[0] = &A;
-  // tensor maps live here for the duration of cuLaunchKernel (parameters are copied at launch)
-  struct alignas(64) { CUtensorMap m[PSAD_MAX_FIELDS]; } TM;
-  if (P.kind == PSAD_KIND_MARCH) {
-    int n_tma = 0;
-    // L2 promotion of TMA requests: 0 none, 1 64B, 2 128B, 3 256B (PSAD_L2PROMO overrides for experiments)
-    static const int l2promo = getenv("PSAD_L2PROMO") ? atoi(getenv("PSAD_L2PROMO")) : 3;
-    for (int f = 0; f < n_fields; ++f) {
-      const psad_field_plan_t& fp = P.field[f];
-      if (!fp.tma) continue;
-      unsigned long long gdim[3] = {(unsigned long long)A.shape[2], (unsigned long long)A.shape[1], (unsigned long long)A.shape[0]};
-      unsigned long long gstr[2] = {(unsigned long long)A.stride[f][1] * fp.elem_size, (unsigned long long)A.stride[f][0] * fp.elem_size};
-      unsigned box[3] = {(unsigned)fp.box[0], (unsigned)fp.box[1], (unsigned)(nd == 3 ? fp.box[2] : 1)};
-      unsigned estr[3] = {1, 1, 1};
-      for (int d = 0; d < nd; ++d)
-        if (box[d] < 1 || box[d] > 256) return fail(PSAD_ERR_INVALID, "TMA box dim %d = %u out of range", d, box[d]);
-      CUresult r = g_drv.cuTensorMapEncodeTiled(&TM.m[n_tma], fp.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
-                                                (unsigned)nd, A.ptr[f], gdim, gstr, box, estr,
-                                                /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion*/ l2promo, /*oob fill: zeros*/ 0);
-      if (r != 0) return cu_fail(r, "cuTensorMapEncodeTiled");
-      ++n_tma;
+  bool hit = false;
+  if (!no_cache) {
+    std::lock_guard<std::mutex> lock(k->cache_mutex);
+    for (LaunchEntry* e : k->cache) {
+      if (memcmp(&e->key, &key, sizeof(key)) == 0) {
+        A = e->args; TM = e->tm; empty = e->empty;
+        grid[0] = e->grid[0]; grid[1] = e->grid[1]; grid[2] = e->grid[2];
+        e->stamp = ++k->cache_clock;
+        hit = true;
+        break;
+      }
     }
-    params[1] = &TM;
   }
-  if (grid[0] == 0) return 0;
-  if (getenv("PSAD_DEBUG"))
-    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d\n", k->name.c_str(), grid[0],
-            P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy);
+  if (hit) {
+    g_cache_hits.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    g_cache_misses.fetch_add(1, std::memory_order_relaxed);
+    if (int rc = build_args(P, k->name.c_str(), k->sm_count, k->occupancy, fields, n_fields, scalars, n_scalars, range, A, grid, &empty)) return rc;
+    if (!empty && P.kind == PSAD_KIND_MARCH)
+      if (int rc = encode_tensor_maps(P, A, n_fields, TM)) return rc;
+    if (!no_cache) {
+      LaunchEntry* e = new LaunchEntry();
+      e->key = key; e->args = A; e->tm = TM; e->empty = empty;
+      e->grid[0] = grid[0]; e->grid[1] = grid[1]; e->grid[2] = grid[2];
+      std::lock_guard<std::mutex> lock(k->cache_mutex);
+      e->stamp = ++k->cache_clock;
+      if ((int)k->cache.size() >= PSAD_LAUNCH_CACHE) {          // evict the least recently used launch
+        size_t victim = 0;
+        for (size_t i = 1; i < k->cache.size(); ++i) if (k->cache[i]->stamp < k->cache[victim]->stamp) victim = i;
+        delete k->cache[victim];
+        k->cache[victim] = e;
+      } else {
+        k->cache.push_back(e);
+      }
+    }
+  }
+  if (empty || grid[0] == 0) return 0;
+  for (int i = 0; i < n_scalars; ++i) A.scalar[i] = scalars[i];      // scalars are not part of the key
+  void* params[2] = {&A, &TM};   // both are copied by cuLaunchKernel
+  if (debug)
+    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d cache=%s\n", k->name.c_str(), grid[0],
+            P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy, hit ? "hit" : "miss");
   CUresult r = g_drv.cuLaunchKernel(k->fn, grid[0], grid[1], grid[2], (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
   if (r != 0) return cu_fail(r, "cuLaunchKernel");
   g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int psad_launch_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  if (hits) *hits = g_cache_hits.load();
+  if (misses) *misses = g_cache_misses.load();
   return 0;
 }
 

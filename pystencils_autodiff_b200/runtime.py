@@ -81,6 +81,8 @@ def build_library(force=False, verbose=False):
 
 def lib():
     global _lib
+    if _lib is not None:             # the common case takes no lock
+        return _lib
     with _lock:
         if _lib is not None:
             return _lib
@@ -106,6 +108,7 @@ def lib():
         L.psad_plan_launch.argtypes = [ctypes.POINTER(Plan), ctypes.c_int, ctypes.c_int, ctypes.POINTER(FieldArg),
                                        ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(Range),
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint)]
+        L.psad_launch_cache_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)] * 2
         L.psad_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
         L.psad_nccl_unique_id.argtypes = [ctypes.c_void_p]
         L.psad_nccl_comm_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
@@ -186,8 +189,9 @@ class NativeKernel:
         return dict(num_regs=vals[0].value, static_smem=vals[1].value, local_bytes=vals[2].value,
                     max_ctas_per_sm=vals[3].value)
 
-    def launch(self, field_args, scalars, stream, rng=None):
-        """field_args: list of ``(ptr, shape, strides)`` in plan order; scalars: list of floats; stream: int handle."""
+    @staticmethod
+    def pack_fields(field_args):
+        """``(ptr, shape, strides)`` triples in plan order -> the ``psad_field_arg_t`` array of a launch."""
         n = len(field_args)
         fa = (FieldArg * n)()
         for i, (ptr, shape, strides) in enumerate(field_args):
@@ -196,6 +200,20 @@ class NativeKernel:
                 fa[i].shape[d] = shape[d] if d < len(shape) else 1
             for d in range(4):
                 fa[i].stride[d] = strides[d] if d < len(strides) else 0
+        return fa
+
+    def launch_packed(self, fa, n, scalars, stream, range_ref):
+        """A launch whose field array (and range) were packed before: the repeated-launch path."""
+        ns = len(scalars)
+        scal = (ctypes.c_double * ns)(*scalars) if ns else self._scal
+        rc = _lib.psad_kernel_launch(self._handle, fa, n, scal, ns, range_ref, stream)
+        if rc:
+            check(rc, 'psad_kernel_launch(%s)' % self.emitted.name)
+
+    def launch(self, field_args, scalars, stream, rng=None):
+        """field_args: list of ``(ptr, shape, strides)`` in plan order; scalars: list of floats; stream: int handle."""
+        n = len(field_args)
+        fa = self.pack_fields(field_args)
         # per-call buffer: launches of one kernel from several threads (autograd workers) must not share it
         scal = (ctypes.c_double * max(1, len(scalars)))(*[float(s) for s in scalars]) if scalars else self._scal
         r = None
@@ -221,6 +239,13 @@ class NativeKernel:
 
 def launch_count():
     return int(lib().psad_launch_count())
+
+
+def launch_cache_stats():
+    """(hits, misses) of the per-kernel launch cache (parameter block + encoded tensor maps) of ``psad_kernel_launch``."""
+    h, m = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib().psad_launch_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    return int(h.value), int(m.value)
 
 
 def device_info():

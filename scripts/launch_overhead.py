@@ -1,27 +1,75 @@
-import os, sys, time
+"""Host cost of the launch path: raw CompiledKernel launches, and Function.apply + backward.
+
+    python scripts/launch_overhead.py            # tiny arrays: host-bound by construction
+"""
+import json
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pystencils_autodiff_b200.configs import make_config
+from pystencils_autodiff_b200 import runtime
 from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+from pystencils_autodiff_b200.configs import make_config
+
+res = {}
+for cached in (True, False):
+    if not cached:
+        os.environ['PSAD_NO_LAUNCH_CACHE'] = '1'       # read once per process by the library: only affects a fresh run
+    op = make_config('c2', shape=(64, 128))
+    k = CompiledKernel(op.forward_ast_gpu)
+    u = torch.randn(64, 128, device='cuda')
+    out = torch.empty_like(u)
+    if not cached:
+        k._fast = None.__class__ and {}
+        k.max_remembered_launches = 0
+    for _ in range(10):
+        k(u=u, out=out)
+    torch.cuda.synchronize()
+    n = 3000
+    t0 = time.perf_counter()
+    for _ in range(n):
+        k(u=u, out=out)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    res['raw_launch_host_us' + ('' if cached else '_python_repack')] = (t1 - t0) / n * 1e6
+    res['raw_launch_incl_drain_us' + ('' if cached else '_python_repack')] = (t2 - t0) / n * 1e6
 op = make_config('c2', shape=(64, 128))
-k = CompiledKernel(op.forward_ast_gpu)
-u = torch.randn(64, 128, device='cuda'); out = torch.empty_like(u)
-for _ in range(10): k(u=u, out=out)
-torch.cuda.synchronize()
-n = 2000
-t0 = time.perf_counter()
-for _ in range(n): k(u=u, out=out)
-t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
-print('host time per launch %.1f us; incl. drain %.1f us' % ((t1 - t0) / n * 1e6, (t2 - t0) / n * 1e6))
 fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+u = torch.randn(64, 128, device='cuda')
+out = torch.empty_like(u)
 ug = u.clone().requires_grad_(True)
 for _ in range(10):
-    (o,) = fn.apply(ug); o.backward(out)
-torch.cuda.synchronize(); t0 = time.perf_counter()
-for _ in range(500):
-    (o,) = fn.apply(ug); o.backward(out)
-torch.cuda.synchronize(); print('Function.apply + backward per step %.1f us' % ((time.perf_counter() - t0) / 500 * 1e6))
-import cProfile, pstats
-pr = cProfile.Profile(); pr.enable()
-for _ in range(500): k(u=u, out=out)
-pr.disable(); pstats.Stats(pr).sort_stats('cumulative').print_stats(14)
+    (o,) = fn.apply(ug)
+    o.backward(out)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(1000):
+    (o,) = fn.apply(ug)
+    o.backward(out)
+    ug.grad = None
+torch.cuda.synchronize()
+res['function_apply_backward_us_per_step'] = (time.perf_counter() - t0) / 1000 * 1e6
+# the same through plain torch ops of comparable launch count (two elementwise kernels): the floor autograd itself sets
+x = u.clone().requires_grad_(True)
+t0 = time.perf_counter()
+for _ in range(1000):
+    o = x * 2.0
+    o.backward(out)
+    x.grad = None
+torch.cuda.synchronize()
+res['torch_mul_backward_us_per_step'] = (time.perf_counter() - t0) / 1000 * 1e6
+res['launch_cache'] = runtime.launch_cache_stats()
+print(json.dumps(res))
+import cProfile
+import pstats
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(300):
+    (o,) = fn.apply(ug)
+    o.backward(out)
+    ug.grad = None
+pr.disable()
+pstats.Stats(pr).sort_stats('tottime').print_stats(18)

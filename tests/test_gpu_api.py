@@ -457,3 +457,58 @@ def test_gradients_are_matched_to_outputs_by_name_not_position():
     torch.autograd.backward((oa, ob), (_t(GA), _t(GB)))
     _, ref = forward_backward(op, dict(x=X), dict(a_out=GA, b_out=GB))
     np.testing.assert_allclose(xt.grad.cpu().numpy(), ref['diffx'], rtol=1e-13, atol=1e-13)
+
+
+def test_repeated_launches_hit_the_launch_cache_and_stay_correct():
+    """psad_kernel_launch remembers the parameter block + encoded tensor maps per (buffers, shapes, strides, range) and
+    CompiledKernel.__call__ the validated argument pack: repeats must hit, give the same bits, follow a changed scalar,
+    and new buffers / views must miss (never reuse another buffer's tensor map)."""
+    import torch
+    from pystencils_autodiff_b200 import runtime
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    import pystencils_autodiff_b200 as ps
+    u, out = ps.fields('u, out: float32[48,128]')
+    a = sp.Symbol('a')
+    op = ps.AutoDiffOp([ps.Assignment(out.center, a * (u[0, 1] + u[0, -1] + u[1, 0] + u[-1, 0]) - u.center)],
+                       boundary_handling='zeros')
+    k = CompiledKernel(op.forward_ast_gpu)
+    rng = np.random.default_rng(0)
+    U = [rng.normal(size=(48, 128)).astype(np.float32) for _ in range(3)]
+    tu = [_t(x) for x in U]
+    to = [torch.empty_like(tu[0]) for _ in range(3)]
+    h0, m0 = runtime.launch_cache_stats()
+    for rep in range(3):
+        for i in range(3):
+            k(u=tu[i], out=to[i], a=0.5 + rep)
+    torch.cuda.synchronize()
+    h1, m1 = runtime.launch_cache_stats()
+    assert m1 - m0 == 3 and h1 - h0 == 6                  # three buffer pairs, each built once
+    for i in range(3):
+        ref = evaluate(op.forward_assignments, dict(u=U[i]), 'zeros', scalars={'a': 2.5})['out']
+        assert np.abs(to[i].cpu().numpy() - ref).max() <= 1e-6 * np.abs(ref).max()
+    # a view with the same pointer but another shape is another launch
+    k2 = CompiledKernel(ps.AutoDiffOp([ps.Assignment(ps.fields('o2: float32[24,128]').center,
+                                                     ps.fields('u2: float32[24,128]')[1, 0])],
+                                      boundary_handling='zeros').forward_ast_gpu)
+    o2 = torch.empty((24, 128), device='cuda')
+    k2(u2=tu[0][:24], o2=o2)
+    k2(u2=tu[0][24:], o2=o2)
+    torch.cuda.synchronize()
+    assert torch.equal(o2[:-1], tu[0][25:]) and not o2[-1].any()
+
+
+def test_iteration_range_outside_the_array_is_rejected():
+    """build_args validated only the write range.  The generic kernel with interior iteration reads unguarded:
+    an iteration range closer than the ghost width to the array edge must be an error, not an out-of-bounds read."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    op = make_config('c2', shape=(20, 30), boundary_handling=None)           # 120-byte rows: generic kernel
+    k = CompiledKernel(op.forward_ast_gpu)
+    u = torch.zeros((20, 30), device='cuda')
+    out = torch.empty_like(u)
+    with pytest.raises(RuntimeError, match='iteration range'):
+        k(u=u, out=out, _range=dict(iter_lo=[0, 1], iter_hi=[20, 29], write_lo=[0, 0], write_hi=[20, 30]))
+    with pytest.raises(RuntimeError, match='iteration range'):
+        k(u=u, out=out, _range=dict(iter_lo=[1, 1], iter_hi=[19, 31], write_lo=[0, 0], write_hi=[20, 30]))
+    k(u=u, out=out, _range=dict(iter_lo=[1, 1], iter_hi=[19, 29], write_lo=[0, 0], write_hi=[20, 30]))
+    torch.cuda.synchronize()
