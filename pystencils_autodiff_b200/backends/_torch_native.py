@@ -273,6 +273,13 @@ class CompiledKernel:
         return None
 
 
+class _ShapeOnly:
+    """Stand-in for a tensor where only ``.shape`` is needed."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
 def _raw_current_stream(device_index):
     """``cudaStream_t`` of torch's current stream as an integer (the private fast accessor when it exists)."""
     import torch
@@ -318,6 +325,7 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
     fwd_read = {f.name for f in forward_ir.fields_read}
     bwd_accessed = {f.name for f in backward_ir.fields_accessed} if backward_ir is not None else set()
     bwd_read = {f.name for f in backward_ir.fields_read} if backward_ir is not None else set()
+    bwd_read_sorted = sorted(bwd_read)           # the order tensors are saved in must not depend on set iteration
     grad_fields = [f for f in bwd_inputs if f not in fwd_inputs and f not in fwd_outputs and f not in bwd_outputs]
     # which forward output each upstream-gradient field belongs to.  The reference binds ``grad_outputs[i]`` to the
     # i-th such field (:99-100), which is only right when the adjoint reads the gradient of EVERY output; here the
@@ -334,19 +342,27 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
         prefix_map[fwd.name if fwd is not None else f.name] = f
     class_kwargs = dict()
 
+    # per output field, once: fixed shape (or None), index shape, torch dtype — Function.apply / backward run per time step
+    # and must not redo numpy dtype-name lookups or shape conversions (8 us each, measured)
+    _alloc_info = {}
+    for _f in list(fwd_outputs) + list(bwd_outputs):
+        _alloc_info[_f.name] = (tuple(int(s_) for s_ in _f.shape) if _f.has_fixed_shape else None,
+                                tuple(int(s_) for s_ in _f.index_shape), _f.spatial_dimensions,
+                                numpy_dtype_to_torch(_f.dtype.numpy_dtype), bool(_f.index_dimensions))
+
     def _alloc(field, like, device, read_too):
-        shape = tuple(int(s) for s in field.shape) if field.has_fixed_shape else \
-            tuple(like.shape[:field.spatial_dimensions]) + tuple(int(s) for s in field.index_shape)
+        fixed, index_shape, nsp, dtype, has_index = _alloc_info[field.name]
+        shape = fixed if fixed is not None else tuple(like.shape[:nsp]) + index_shape
         maker = torch.zeros if read_too else torch.empty
-        dtype = numpy_dtype_to_torch(field.dtype.numpy_dtype)
-        if field.index_dimensions:
+        if has_index:
             # vector outputs are allocated structure-of-arrays (x contiguous) so that they qualify for the fast path;
             # the returned tensor still has the field's logical shape [spatial..., index]
-            nsp = field.spatial_dimensions
             t = maker(tuple(shape[nsp:]) + tuple(shape[:nsp]), dtype=dtype, device=device)
             return t.permute(*range(len(shape) - nsp, len(shape)), *range(len(shape) - nsp))
         return maker(shape, dtype=dtype, device=device)
 
+    _grad_info = {f.name: (tuple(int(s_) for s_ in f.shape) if f.has_fixed_shape else None,
+                           numpy_dtype_to_torch(f.dtype.numpy_dtype)) for f in grad_fields}
     fields_by_name = {f.name: f for f in list(fwd_inputs) + list(fwd_outputs) + list(bwd_inputs) + list(bwd_outputs)}
 
     def _device_layout(t, field=None):
@@ -381,7 +397,7 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
         outputs = OrderedDict((f.name, kwargs[f.name]) for f in fwd_outputs)
         fwd_kernel(**{k: v for k, v in kwargs.items() if k in fwd_accessed or k in fwd_kernel.scalars})
         # keep only what the adjoint kernel reads (tensors through save_for_backward, scalars on ctx)
-        saved_names = [n for n in bwd_read if n in kwargs and isinstance(kwargs[n], torch.Tensor)]
+        saved_names = [n for n in bwd_read_sorted if n in kwargs and isinstance(kwargs[n], torch.Tensor)]
         ctx.saved_names = saved_names
         ctx.save_for_backward(*[kwargs[n] for n in saved_names])
         ctx.saved_scalars = {k: v for k, v in kwargs.items() if not isinstance(v, torch.Tensor)}
@@ -399,15 +415,16 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
             i = grad_index[f.name]
             g = grad_outputs[i] if i < len(grad_outputs) else None
             if g is None:
-                g = torch.zeros(tuple(int(s) for s in f.shape) if f.has_fixed_shape else shape,
-                                dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=device)
+                g = torch.zeros(_grad_info[f.name][0] or shape, dtype=_grad_info[f.name][1], device=device)
             g = _device_layout(g, f) if g.is_cuda else g.contiguous()
             if not g.is_cuda:
                 raise AssertionError('Some of the tensors where on the wrong device. Op was compiled for CUDA: True')
-            if f.has_fixed_shape and tuple(int(s) for s in f.shape) != tuple(g.shape):
+            if _grad_info[f.name][0] is not None and _grad_info[f.name][0] != tuple(g.shape):
                 raise AssertionError('gradient for %s has shape %s, expected %s' % (f.name, tuple(g.shape), f.shape))
             gradients[f.name] = g
-        like = next(iter(gradients.values())) if gradients else next(iter(saved.values()))
+        # shape template for adjoint outputs of fields without a fixed shape: an upstream gradient, else a saved tensor,
+        # else the forward call's first tensor (an adjoint with constant right-hand sides reads neither)
+        like = next(iter(gradients.values())) if gradients else (next(iter(saved.values())) if saved else _ShapeOnly(shape))
         outs = OrderedDict((f.name, _alloc(f, like, device, f.name in bwd_read)) for f in bwd_outputs)
         kw = {**gradients, **saved, **outs}
         kw = {k: v for k, v in kw.items() if k in bwd_accessed}

@@ -75,6 +75,27 @@ template <typename T> PSAD_DEV void psad_lds_vec(const T* p, T* e) {
   typename PsadVec<T>::type v = *reinterpret_cast<const typename PsadVec<T>::type*>(p);
   PsadVec<T>::unpack(v, e);
 }
+// shared -> registers, the two aligned 16-byte vectors of a 32-byte strip (8-byte elements, 4 cells per lane), free of bank
+// conflicts.  A warp-wide LDS.128 is served one quarter warp (8 lanes x 16 bytes = one 128-byte wavefront) at a time; with a
+// lane pitch of 32 bytes the eight lanes of a quarter warp touch only the even 16-byte columns, twice each: every LDS.128 is
+// a 2-way bank conflict (ncu, 27-point fp64 kernel of round 1: 36 % of all shared wavefronts).  Here lanes 0-3 of every
+// quarter warp fetch their first vector while lanes 4-7 fetch their second one, then the other way round: each
+// instruction covers all 32 banks exactly once.  The price is one select per 32-bit register to put the halves back in order.
+// `hi` = (lane >> 2) & 1.
+template <typename T> PSAD_DEV void psad_lds_pair(const T* p, int hi, T* e) {
+  typedef typename PsadVec<T>::type V;
+  constexpr int N = PsadVec<T>::N;
+  const V a = *reinterpret_cast<const V*>(p + (hi ? N : 0));
+  const V b = *reinterpret_cast<const V*>(p + (hi ? 0 : N));
+  T ea[N], eb[N];
+  PsadVec<T>::unpack(a, ea);
+  PsadVec<T>::unpack(b, eb);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    e[i] = hi ? eb[i] : ea[i];
+    e[N + i] = hi ? ea[i] : eb[i];
+  }
+}
 // registers -> shared, one aligned 16-byte vector (STS.128)
 template <typename T> PSAD_DEV void psad_sts_vec(T* p, const T* e) {
   *reinterpret_cast<typename PsadVec<T>::type*>(p) = PsadVec<T>::pack(e);

@@ -168,8 +168,14 @@ class HaloExchanger:
         g, n = dec.g, dec.n_local
         if dec.world_size == 1 or g == 0:
             return
-        lo_send, lo_recv = tensor[g:2 * g], tensor[0:g]
-        hi_send, hi_recv = tensor[n:n + g], tensor[n + g:n + 2 * g]
+        self.exchange_planes(tensor[g:2 * g], tensor[0:g], tensor[n:n + g], tensor[n + g:n + 2 * g], stream)
+
+    def exchange_planes(self, lo_send, lo_recv, hi_send, hi_recv, stream=None):
+        """The exchange on explicitly given (contiguous, equally sized) blocks: ``lo_send`` goes to the lower neighbour,
+        whose ``hi_send`` arrives in ``lo_recv``; likewise upwards.  Blocks towards a missing neighbour are ignored."""
+        dec = self.dec
+        if dec.world_size == 1:
+            return
         if self.backend == 'nccl':
             nbytes = lo_send.numel() * lo_send.element_size()
             runtime.check(runtime.lib().psad_halo_exchange(
@@ -961,7 +967,6 @@ class SlabStencilOp:
         self.fwd_scalars = {s_: scalars[s_] for s_ in self.fwd.scalars}
         self.bwd_scalars = {s_: scalars[s_] for s_ in self.bwd.scalars}
         self._fn = None
-        self._pinned = None
 
     def randomize(self, generator):
         """Synthetic inputs: forward inputs ~ U(0.1, 1), upstream gradients ~ N(0, 1)."""
@@ -983,118 +988,79 @@ class SlabStencilOp:
         return {'forward': self.fwd.last_variant, 'adjoint': self.bwd.last_variant}
 
     # -- end-to-end with host buffers ----------------------------------------------------------------------------
-    def end_to_end(self, steps, barrier):
-        """Same metric through the public operator API with HOST (pinned) buffers: every step copies the forward
-        inputs and the upstream gradients host->device, runs forward + adjoint, and copies the outputs and the
-        input gradients device->host.  world_size == 1: ``Function.apply`` + ``torch.autograd.backward``;
-        world_size > 1: the slab operator (same kernels + halo exchange)."""
+    def end_to_end(self, steps, barrier, copy_baseline=True):
+        """Same metric through the public operator for HOST buffers (``HostStreamedOp``): every step uploads the forward
+        inputs and the upstream gradients of this rank's slab from pinned host memory in chunks of planes, runs forward +
+        adjoint per chunk and downloads the outputs and the input gradients — upload, kernels and download of consecutive
+        chunks overlap on three streams, every rank streams its own slab (one pinned buffer per field), and the planes
+        next to a neighbouring rank are exchanged GPU to GPU.  ``copy_baseline``: also time the bare copies of the same
+        bytes (H2D on one stream, D2H on another) — the ceiling the host memory / PCIe fabric sets for this step."""
         torch = self.torch
-        op = self.op
-        in_fields = list(op.forward_input_fields)
-        out_fields = list(op.forward_output_fields)
-        dt = {f.name: self.dh.gpu_arrays[f.name].dtype for f in in_fields + out_fields}
-        esize = {n: torch.empty((), dtype=d).element_size() for n, d in dt.items()}
-        cells = int(np.prod(self.local_shape))
-        # world > 1: two pinned staging buffers (one per direction), reused for every field: synthetic data, honest byte counts
-        big = max(esize.values()) * cells
-        if self._pinned is None and self.world > 1:
-            self._pinned = (torch.empty(big, dtype=torch.uint8, pin_memory=True),
-                            torch.empty(big, dtype=torch.uint8, pin_memory=True))
-            self._pinned[0].random_(0, 64)
-        h_in, h_out = self._pinned if self._pinned is not None else (None, None)
+        if self._fn is None:
+            self._fn = HostStreamedOp(self.op, self.local_shape, self.device, rank=self.rank, world_size=self.world,
+                                      exchanger=self.dh.exchanger if self.world > 1 else None,
+                                      kernels=(self.fwd, self.bwd))
+            self._host = {n: torch.empty(self.local_shape, dtype=self.dh.gpu_arrays[n].dtype, pin_memory=True)
+                          for n in self._fn.fields}
+            for n in self._fn.input_names:
+                self._host[n].copy_(self.dh.owned(n))
+        streamed = self._fn
+        h_in = {n: self._host[n] for n in streamed.input_names}
+        h_out = {n: self._host[n] for n in streamed.output_names}
 
-        def host_view(buf, name):
-            return buf[:esize[name] * cells].view(dt[name]).view(self.local_shape)
+        def step():
+            streamed(h_in, h_out, **self.scalars)
 
-        h2d = sum(esize[f.name] * cells for f in in_fields) + sum(esize[f.name] * cells for f in out_fields)
-        d2h = h2d
-        if self.world == 1:
-            # host-resident fields streamed through the GPU in chunks of planes (HostStreamedOp): the public call for
-            # host buffers; H2D, kernels and D2H of consecutive chunks overlap on three streams
-            if self._fn is None:
-                self._fn = HostStreamedOp(op, self.local_shape, self.device)
-                fields = self._fn.fields
-                self._host = {n: torch.empty(self.local_shape, dtype=self.dh.gpu_arrays[n].dtype, pin_memory=True)
-                              for n in fields}
-                for n in self._fn.input_names:
-                    self._host[n].copy_(self.dh.owned(n))
-            streamed = self._fn
-            h_in = {n: self._host[n] for n in streamed.input_names}
-            h_out = {n: self._host[n] for n in streamed.output_names}
+        def timed(fn, n):
+            fn()
+            barrier()
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            for _ in range(n):
+                fn()
+            end.record()
+            barrier()
+            return start.elapsed_time(end) / n
 
-            def step():
-                streamed(h_in, h_out, **self.scalars)
-        else:
-            grad_names = [f.name for f in op.backward_input_fields if f not in op.forward_input_fields]
-            dnames = [f.name for f in op.backward_output_fields]
+        result = dict(ms_per_step=timed(step, steps), h2d=streamed.h2d_bytes, d2h=streamed.d2h_bytes,
+                      chunks=streamed.n_chunks, chunk_planes=streamed.chunk)
+        # the streamed results against the resident kernels on the same inputs (outside the timed region): a few planes of
+        # every output — first and last plane of the slab (next to the neighbouring ranks when N > 1) and the planes
+        # around two chunk boundaries — bit for bit
+        self.forward()
+        self.backward()
+        torch.cuda.synchronize() if torch.cuda.is_available() else None
+        st = streamed.starts
+        n0 = self.local_shape[0]
+        planes = sorted({0, n0 - 1} | {p for b_ in (st[1:2] + st[-1:]) for p in (b_ - 1, b_) if 0 <= p < n0})
+        result['checked_planes'] = planes
+        result['matches_resident'] = all(bool(torch.equal(self._host[n][p].to(self.device), self.dh.owned(n)[p]))
+                                         for n in streamed.output_names for p in planes)
+        if copy_baseline:
+            if getattr(self, '_copy_streams', None) is None:
+                self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+            s_up, s_dn = self._copy_streams
+            dev_in = [self.dh.owned(n) for n in streamed.input_names]
+            dev_out = [self.dh.owned(n) for n in streamed.output_names]
 
-            # Three streams, so that PCIe runs in both directions at once: the upstream gradients are uploaded while the
-            # forward kernel runs and its outputs are downloaded; the input gradients follow the adjoint kernel.
-            #   upload:   H2D(inputs) ........ H2D(upstream gradients)
-            #   compute:  ........... forward ......................... adjoint
-            #   download: ................... D2H(outputs) ..................... D2H(input gradients)
-            if getattr(self, '_e2e_streams', None) is None:
-                self._e2e_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
-                self._e2e_events = [torch.cuda.Event() for _ in range(5)]
-            s_up, s_dn = self._e2e_streams
-            ev_in, ev_grad, ev_fwd, ev_bwd, ev_done = self._e2e_events
-
-            def step():
+            def copies():
                 cur = torch.cuda.current_stream(self.device)
-                s_up.wait_stream(cur)            # the previous step's kernels have read their inputs
+                s_up.wait_stream(cur)
+                s_dn.wait_stream(cur)
                 with torch.cuda.stream(s_up):
-                    for f in in_fields:
-                        self.dh.owned(f.name).copy_(host_view(h_in, f.name), non_blocking=True)
-                    ev_in.record(s_up)
-                    for n, f in zip(grad_names, out_fields):
-                        self.dh.owned(n).copy_(host_view(h_in, f.name), non_blocking=True)
-                    ev_grad.record(s_up)
-                cur.wait_event(ev_in)
-                self.forward()
-                ev_fwd.record(cur)
-                cur.wait_event(ev_grad)
-                self.backward()
-                ev_bwd.record(cur)
+                    for n, d in zip(streamed.input_names, dev_in):
+                        d.copy_(self._host[n], non_blocking=True)
                 with torch.cuda.stream(s_dn):
-                    s_dn.wait_event(ev_fwd)
-                    for f in out_fields:
-                        host_view(h_out, f.name).copy_(self.dh.owned(f.name), non_blocking=True)
-                    s_dn.wait_event(ev_bwd)
-                    for n, f in zip(dnames, in_fields):
-                        host_view(h_out, f.name).copy_(self.dh.owned(n), non_blocking=True)
-                    ev_done.record(s_dn)
-                cur.wait_event(ev_done)          # the step ends (and is timed) when its results are in host memory
-
-        step()
-        barrier()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for _ in range(steps):
-            step()
-        end.record()
-        barrier()
-        result = dict(ms_per_step=start.elapsed_time(end) / steps, h2d=h2d, d2h=d2h)
-        if self.world == 1:
-            result['h2d'], result['d2h'] = self._fn.h2d_bytes, self._fn.d2h_bytes
-            # the streamed results against the resident kernels on the same inputs (outside the timed region): a few
-            # planes of every output — the first and last plane and the planes around two chunk boundaries — bit for bit
-            self.forward()
-            self.backward()
-            torch.cuda.synchronize()
-            st = self._fn.starts
-            planes = sorted({0, self.local_shape[0] - 1} | {p for b in (st[1:2] + st[-1:]) for p in (b - 1, b)
-                                                            if 0 <= p < self.local_shape[0]})
-            result['checked_planes'] = planes
-            result['matches_resident'] = all(
-                bool(torch.equal(self._host[n][p].to(self.device), self.dh.owned(n)[p]))
-                for n in self._fn.output_names for p in planes)
-        else:
-            # the staging buffer is shared by all downloads: what it holds now is the last one — the gradient of the last
-            # forward input — which must equal the device array it came from
-            last_field, last_grad = in_fields[-1], dnames[-1] if len(dnames) >= len(in_fields) else None
-            if last_grad is not None:
-                result['matches_resident'] = bool(torch.equal(host_view(h_out, last_field.name).to(self.device),
-                                                              self.dh.owned(last_grad)))
+                    for n, d in zip(streamed.output_names, dev_out):
+                        self._host[n].copy_(d, non_blocking=True)
+                cur.wait_stream(s_up)
+                cur.wait_stream(s_dn)
+            saved = [d.clone() for d in dev_in]       # the uploads overwrite the resident inputs: put them back afterwards
+            try:
+                result['copy_only_ms'] = timed(copies, max(1, steps))
+            finally:
+                for d, s_ in zip(dev_in, saved):
+                    d.copy_(s_)
         return result
 
 
@@ -1111,14 +1077,24 @@ class HostStreamedOp:
     logic as ``SlabDecomposition``.
     """
 
-    def __init__(self, op, shape, device=None, chunk_planes=None, stages=3, tuning=None, ramp=True):
+    def __init__(self, op, shape, device=None, chunk_planes=None, stages=3, tuning=None, ramp=True, rank=0, world_size=1,
+                 exchanger=None, kernels=None):
+        """``rank`` / ``world_size`` / ``exchanger`` (a ``HaloExchanger`` of a decomposition with the same ranks): ``shape``
+        is then THIS RANK'S slab of a field split along dim 0, each rank streams its own slab from its own host memory,
+        and the ``g`` planes next to a neighbouring rank are uploaded first and exchanged GPU to GPU (one small grouped
+        send / receive per input field per call), so a chunk at a slab border finds its ghost planes on the device."""
         import torch
         self.torch = torch
         self.op = op
         self.shape = tuple(int(s) for s in shape)
+        self.rank, self.world = int(rank), int(world_size)
+        self.exchanger = exchanger
+        if self.world > 1 and exchanger is None:
+            raise ValueError('HostStreamedOp on %d ranks needs a HaloExchanger' % self.world)
+        self.global_shape = (self.shape[0] * self.world,) + self.shape[1:]
         self.device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
-        self.fwd = CompiledKernel(op.forward_ast_gpu, tuning)
-        self.bwd = CompiledKernel(op.backward_ast_gpu, tuning)
+        self.fwd, self.bwd = kernels if kernels is not None else (CompiledKernel(op.forward_ast_gpu, tuning),
+                                                                    CompiledKernel(op.backward_ast_gpu, tuning))
         self.g = max(max(ir.max_halo[0]) for ir in (op.forward_ast_gpu, op.backward_ast_gpu))
         plane_bytes = int(np.prod(self.shape[1:])) * max(f.dtype.itemsize for f in op.forward_fields)
         if chunk_planes is None:
@@ -1142,12 +1118,16 @@ class HostStreamedOp:
         buf_shape = (self.chunk + 2 * self.g,) + self.shape[1:]
         self.buffers = [{n: torch.empty(buf_shape, dtype=numpy_dtype_to_torch(f.dtype.numpy_dtype), device=self.device)
                          for n, f in fields.items()} for _ in range(self.stages)]
+        # [planes received from below | first g planes | last g planes | planes received from above] per input field
+        self.edges = ({n: torch.zeros((4 * self.g,) + self.shape[1:], dtype=self.buffers[0][n].dtype, device=self.device)
+                       for n in self.input_names} if (self.world > 1 and self.g > 0) else None)
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(self.stages)]
         self.ev_cmp = [torch.cuda.Event() for _ in range(self.stages)]
         self.ev_out = [torch.cuda.Event() for _ in range(self.stages)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._range_cache = {}
 
     @staticmethod
     def _chunk_sizes(n0, chunk, smallest):
@@ -1162,8 +1142,15 @@ class HostStreamedOp:
         return [q, h] + [base + (1 if i < rem else 0) for i in range(n_mid)] + [h, q]
 
     def _ranges(self, kernel, z0, n_k):
+        key = (id(kernel), z0, n_k)      # one dict per (kernel, chunk), reused every call: the launch path keys on it
+        if key not in self._range_cache:
+            self._range_cache[key] = self._make_range(kernel, z0, n_k)
+        return self._range_cache[key]
+
+    def _make_range(self, kernel, z0, n_k):
         ir = kernel.ir   # the chunk's ghost planes are filled from the host array, so one launch covers it
-        return slab_ranges(self.shape, z0, n_k, self.g, False, False, ir.boundary, ir.ghost_layers, ir.ndim)[0]
+        return slab_ranges(self.global_shape, self.rank * self.shape[0] + z0, n_k, self.g, False, False, ir.boundary,
+                           ir.ghost_layers, ir.ndim)[0]
 
     def __call__(self, host_in, host_out, **scalars):
         """``host_in``: name -> pinned CPU tensor for every input field (forward inputs and ``diff<out>`` gradients);
@@ -1181,6 +1168,20 @@ class HostStreamedOp:
         for s_ in (self.s_in, self.s_cmp, self.s_out):
             s_.wait_event(start)
         self.h2d_bytes = self.d2h_bytes = 0
+        has_lo, has_hi = self.rank > 0, self.rank < self.world - 1
+        if self.edges is not None:
+            # the planes the neighbouring ranks need go up first and are exchanged GPU to GPU on the upload stream; they
+            # cross PCIe a second time with their chunk (2 g planes per field: 0.4 % of a 1024-plane slab)
+            with torch.cuda.stream(self.s_in):
+                for n in self.input_names:
+                    e = self.edges[n]
+                    e[g:2 * g].copy_(host_in[n][:g], non_blocking=True)
+                    e[2 * g:3 * g].copy_(host_in[n][N0 - g:N0], non_blocking=True)
+                    self.h2d_bytes += 2 * g * host_in[n][0].numel() * host_in[n].element_size()
+                    if self.exchanger.backend == 'nccl':
+                        self.exchanger.exchange_planes(e[g:2 * g], e[:g], e[2 * g:3 * g], e[3 * g:], self.s_in.cuda_stream)
+                    else:
+                        self.exchanger.exchange_planes(e[g:2 * g], e[:g], e[2 * g:3 * g], e[3 * g:])
         for k in range(self.n_chunks):
             st = k % self.stages
             buf = self.buffers[st]
@@ -1197,7 +1198,10 @@ class HostStreamedOp:
                     dst = buf[n]
                     off = lo - (z0 - g)
                     if off > 0:
-                        dst[:off].zero_()                       # planes below the domain: the 'zeros' boundary
+                        if has_lo:
+                            dst[:off].copy_(self.edges[n][g - off:g], non_blocking=True)     # the lower rank's last planes
+                        else:
+                            dst[:off].zero_()                   # planes below the domain: the 'zeros' boundary
                     up_lo = lo
                     if prev is not None:
                         n_prev = self.sizes[k - 1]
@@ -1207,7 +1211,11 @@ class HostStreamedOp:
                         dst[up_lo - (z0 - g):off + (hi - lo)].copy_(host_in[n][up_lo:hi], non_blocking=True)
                         self.h2d_bytes += (hi - up_lo) * host_in[n][0].numel() * host_in[n].element_size()
                     if off + (hi - lo) < n_k + 2 * g:
-                        dst[off + (hi - lo):n_k + 2 * g].zero_()
+                        if has_hi:
+                            m = n_k + 2 * g - (off + (hi - lo))
+                            dst[off + (hi - lo):n_k + 2 * g].copy_(self.edges[n][3 * g:3 * g + m], non_blocking=True)
+                        else:
+                            dst[off + (hi - lo):n_k + 2 * g].zero_()
                 self.ev_in[st].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self.ev_in[st])

@@ -28,7 +28,7 @@ from .ir import StencilKernelIR
 from .linopt import plan_linear
 
 KERNEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'kernels')
-EMITTER_VERSION = '18'
+EMITTER_VERSION = '19'
 
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
@@ -348,6 +348,8 @@ class MarchTuning:
     store_mode: int = 1    # global store cache policy: 0 default, 1 streaming (.cs, default), 2 write-through
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes; scalar LDS halos only win for narrow fp64 strips)
+    lds_pair: Optional[bool] = None  # 8-byte fields, 4-cell strips: fetch a lane's two 16-byte vectors in an order that
+    #                                  depends on the lane, so that no LDS.128 has a bank conflict (psad_lds_pair); default on
 
 
 def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
@@ -583,6 +585,8 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     def elem(f, j, row, c):
         return '%s[%d]' % (arr(f, j, row), c + geo[f.name]['hx'][0])
 
+    lds_pair = (t.lds_pair if t.lds_pair is not None else True) and any(
+        geo[f.name]['nv'] == 2 and geo[f.name]['es'] == 8 for f in tma_fields)
     # ---- source -------------------------------------------------------------------------------------------------
     jrel = min([j for j in range(D + 1) if any(fresh[f.name][j] for f in tma_fields)] or [D])
     # ring = planes still read from shared memory (D - jrel + 1) + `lookahead` planes in flight ahead of them
@@ -663,6 +667,8 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
         L.append('{')
         for i, s_ in enumerate(scalars):
             L.append('  const CT %s = (CT)A.scalar[%d];' % (_c_ident(s_), i))
+        if lds_pair:
+            L.append('  const int lane_hi = (lane >> 2) & 1;')
         for j in range(D + 1):
             if any(fresh[f.name][j] for f in tma_fields):
                 back = D - j
@@ -683,7 +689,12 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
                     rp = 'p%d_%d_%d' % (g['ti'], j, row + g['hy'][0])
                     L.append('  const %s* %s = reinterpret_cast<const %s*>(st%d + %d) + (wy * %d + %d) * %d + %d + lane * %d;'
                              % (g['T'], rp, g['T'], j, g['off'], RY, row + g['hy'][0], g['boxw'], g['padl'], SX))
-                    for u in sorted(x for x in fr if x[0] == 'U' and x[1] == row):
+                    own = sorted(x for x in fr if x[0] == 'U' and x[1] == row)
+                    if lds_pair and g['nv'] == 2 and g['es'] == 8 and [u[2] for u in own] == [0, 1]:
+                        # both vectors of the 32-byte strip: lane-ordered pair of loads, no bank conflicts
+                        L.append('  psad_lds_pair<%s>(%s, lane_hi, &%s);' % (g['T'], rp, elem(f, j, row, 0)))
+                        own = []
+                    for u in own:
                         L.append('  psad_lds_vec<%s>(%s + %d, &%s);' % (g['T'], rp, u[2] * g['vec'], elem(f, j, row, u[2] * g['vec'])))
                     for u in sorted(x for x in fr if x[0] == 'H' and x[1] == row):
                         c = u[2]

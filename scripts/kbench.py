@@ -29,7 +29,7 @@ def main():
     for kv in os.environ.get('PSAD_TUNE', '').split(','):
         if kv:
             k, v = kv.split('=')
-            tun[k] = bool(int(v)) if k in ("carry", "shuffle", "plane_sums", "arrival", "linopt", "cross_cse") else int(v)
+            tun[k] = bool(int(v)) if k in ("carry", "shuffle", "plane_sums", "arrival", "linopt", "cross_cse", "lds_pair", "exchange") else int(v)
     tuning = MarchTuning(**tun) if tun else None
     extra = {'fast_math': True} if os.environ.get('PSAD_FAST_MATH') else {}
     if os.environ.get('PSAD_ADJOINT_MODE'):          # 'exact': the true transpose for non-linear stencils (C5)

@@ -22,7 +22,13 @@ def main():
     name, iters = sys.argv[1], int(sys.argv[2])
     shape = CONFIG_SHAPES[name]['shape']
     op = make_config(name, shape=shape, boundary_handling='zeros')
-    k = CompiledKernel(op.forward_ast_gpu)
+    tun = {}
+    for kv in os.environ.get('PSAD_TUNE', '').split(','):
+        if kv:
+            a, b = kv.split('=')
+            tun[a] = bool(int(b)) if a in ('carry', 'shuffle', 'plane_sums', 'arrival', 'linopt', 'cross_cse', 'lds_pair') else int(b)
+    from pystencils_autodiff_b200.emit import MarchTuning
+    k = CompiledKernel(op.forward_ast_gpu, MarchTuning(**tun) if tun else None)
     dt = numpy_dtype_to_torch(k.fields[0].dtype.numpy_dtype)
     arrs = {f.name: torch.rand(shape, dtype=dt, device='cuda') for f in k.fields}
     for _ in range(3):

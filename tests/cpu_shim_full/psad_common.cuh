@@ -132,6 +132,8 @@ template <typename T> static inline T psad_from_left(T v) { return psad_emu_shif
 template <typename T> static inline T psad_from_right(T v) { return psad_emu_shift(v, +1); }
 
 template <typename T> static inline void psad_lds_vec(const T* p, T* e) { std::memcpy(e, p, 16); }
+// the device version orders its two 16-byte loads by lane to avoid bank conflicts; the values are the same 32 bytes
+template <typename T> static inline void psad_lds_pair(const T* p, int hi, T* e) { (void)hi; std::memcpy(e, p, 32); }
 template <typename T> static inline void psad_stg_vec(T* p, const T* e) { std::memcpy(p, e, 16); }
 template <typename T> static inline void psad_sts_vec(T* p, const T* e) { std::memcpy(p, e, 16); }
 

@@ -512,3 +512,18 @@ def test_iteration_range_outside_the_array_is_rejected():
         k(u=u, out=out, _range=dict(iter_lo=[1, 1], iter_hi=[19, 31], write_lo=[0, 0], write_hi=[20, 30]))
     k(u=u, out=out, _range=dict(iter_lo=[1, 1], iter_hi=[19, 29], write_lo=[0, 0], write_hi=[20, 30]))
     torch.cuda.synchronize()
+
+
+def test_backward_that_reads_nothing_still_allocates_its_outputs():
+    """a user-supplied adjoint with constant right-hand sides reads neither an upstream gradient nor a saved
+    tensor; the shape template then comes from the forward call (used to raise a bare StopIteration)."""
+    import torch
+    from pystencils_autodiff_b200._adjoint_field import AdjointField
+    u, out = ps.fields('u, out: float32[2D]')
+    op = ps.AutoDiffOp([ps.Assignment(out.center, 2 * u[0, 1])],
+                       backward_assignments=[ps.Assignment(AdjointField(u).center, sp.Float(3.0))], boundary_handling='zeros')
+    fn = op.create_tensorflow_op(backend='torch_native', use_cuda=True)
+    x = torch.ones((8, 16), device='cuda', requires_grad=True)
+    (y,) = fn.apply(x)
+    y.sum().backward()
+    assert x.grad.shape == (8, 16) and float(x.grad.min()) == 3.0 and float(x.grad.max()) == 3.0

@@ -492,12 +492,21 @@ def _e2e_worker(rank, world, port, q):
         with fake_cuda():
             slab = SlabStencilOp(op, local, rank, world, device='cpu', backend='torch')
             slab.fwd, slab.bwd = ReplayKernel(op.forward_ast_gpu), ReplayKernel(op.backward_ast_gpu)
+            g0 = torch.Generator().manual_seed(5 + rank)
+            slab.randomize(g0)
             r = slab.end_to_end(2, dist.barrier)
-        cells = int(np.prod(local))
-        assert r['ms_per_step'] > 0 and r['h2d'] == 2 * 4 * cells and r['d2h'] == 2 * 4 * cells
-        assert r['matches_resident'] is True
-        # what the last step left on the "device": forward and adjoint of the uploaded (synthetic) host data
-        got = {n: slab.dh.gather_array(n) for n in ('u', 'out', 'diffout', 'diffu')}
+            plane = int(np.prod(local[1:])) * 4
+            cells = int(np.prod(local))
+            # every input plane once, plus the g = 1 planes next to each side uploaded ahead for the neighbour exchange
+            assert r['ms_per_step'] > 0 and r['h2d'] == 2 * 4 * cells + 2 * 2 * plane and r['d2h'] == 2 * 4 * cells
+            assert r['matches_resident'] is True and r['copy_only_ms'] > 0
+            assert 0 in r['checked_planes'] and local[0] - 1 in r['checked_planes']
+            # the host arrays the streamed operator filled, gathered over the ranks
+            got = {}
+            for n in ('u', 'out', 'diffout', 'diffu'):
+                parts = [torch.empty(local, dtype=torch.float32) for _ in range(world)]
+                dist.all_gather(parts, slab._host[n].contiguous())
+                got[n] = torch.cat(parts, 0).numpy()
         op_g = configs.heat3d_op(shape=gshape, boundary_handling='zeros')
         ref_out = evaluate(op_g.forward_assignments, {'u': got['u'].astype(np.float64)}, 'zeros')['out']
         ref_du = evaluate(op_g.backward_assignments, {'diffout': got['diffout'].astype(np.float64)}, 'zeros')['diffu']
@@ -509,9 +518,10 @@ def _e2e_worker(rank, world, port, q):
 
 
 def test_end_to_end_leg_with_host_buffers_two_ranks():
-    """``SlabStencilOp.end_to_end`` at N > 1 (bench.py's ``e2e`` leg: upload / compute / download streams) executed on CPU
-    tensors with stand-in streams and events (tests/fake_cuda.py) and replayed kernels, two gloo ranks."""
-    world = 2
+    """``SlabStencilOp.end_to_end`` at N > 1 (bench.py's ``e2e`` leg: every rank streams its slab from host memory in chunks,
+    the planes next to a neighbouring rank exchanged between the "devices") executed on CPU tensors with stand-in streams
+    and events (tests/fake_cuda.py) and replayed kernels, three gloo ranks (a middle rank has neighbours on both sides)."""
+    world = 3
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     procs = [ctx.Process(target=_e2e_worker, args=(r, world, 29891, q)) for r in range(world)]
