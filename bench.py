@@ -54,17 +54,52 @@ def parse_args():
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+
+    NVML — the library behind nvidia-smi — polled from a thread without sleeping (a C2 timed region is 4 ms long: the
+    ``nvidia-smi -lms`` subprocess of round 1 delivered no sample at all inside it); falls back to that subprocess when the
+    NVML binding is missing.  Samples are stamped on arrival and ``stop(t0, t1)`` keeps the ones inside the region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         self.index = index
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, power_w, reasons)
+        self.max_mhz = None
         self.proc = None
         self.thread = None
+        self.running = False
+        self.source = None
 
     def start(self):
+        self.running = True
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[self.index]) if visible and visible.split(',')[self.index].strip().isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [('hw_slowdown', pynvml.nvmlClocksEventReasonHwSlowdown),
+                    ('hw_thermal_slowdown', pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                    ('sw_thermal_slowdown', pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                    ('sw_power_cap', pynvml.nvmlClocksEventReasonSwPowerCap)]
+
+            def poll():
+                while self.running:
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        break
+                    self.samples.append((time.perf_counter(), mhz, watts, [n for n, b in bits if mask & b]))
+            self.source = 'nvml'
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '20'],
@@ -72,41 +107,49 @@ class ClockSampler:
         except OSError:
             self.proc = None
             return
+        self.source = 'nvidia-smi -lms 20'
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
         def pump():
             for line in self.proc.stdout:
-                self.lines.append(line.strip())
+                parts = [p.strip() for p in line.split(',')]
+                if len(parts) < 7:
+                    continue
+                try:
+                    self.max_mhz = float(parts[1])
+                    self.samples.append((time.perf_counter(), float(parts[0]), float(parts[2]),
+                                         [n for n, v in zip(names, parts[3:7]) if v.lower().startswith('active')]))
+                except ValueError:
+                    continue
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], None, set(), []
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(',')]
-            if len(parts) < 7:
-                continue
+    def stop(self, t0=None, t1=None):
+        self.running = False
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nme, val in zip(names, parts[3:7]):
-                if val.lower().startswith('active'):
-                    reasons.add(nme)
-        ordered = sorted(sm)
-        # the median over the samples under load (the upper half: the sampler also sees the idle edges)
-        load = ordered[len(ordered) // 2:] if ordered else []
-        return {'sm_mhz': load[len(load) // 2] if load else None, 'sm_max_mhz': mx, 'sm_min_mhz': ordered[0] if ordered else None,
-                'power_w_max': max(power) if power else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if self.source is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML binding and no nvidia-smi'], 'samples': 0}
+        inside = [s_ for s_ in self.samples if (t0 is None or s_[0] >= t0) and (t1 is None or s_[0] <= t1)]
+        note = None
+        if not inside and self.samples:            # region shorter than the sampling period: the samples nearest to it
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            inside = sorted(self.samples, key=lambda s_: abs(s_[0] - mid))[:3]
+            note = 'no sample inside the region: nearest samples used'
+        sm = sorted(s_[1] for s_ in inside)
+        reasons = sorted({r for s_ in inside for r in s_[3]})
+        out = {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'sm_min_mhz': sm[0] if sm else None,
+               'power_w_max': max((s_[2] for s_ in inside), default=None), 'reasons': reasons, 'samples': len(inside),
+               'source': self.source}
+        if note:
+            out['note'] = note
+        return out
 
 
 def measured_peaks():
@@ -278,7 +321,7 @@ def measure_resident(env, wl, shape, steps, warmup, cooldown_s=0.0):
     warmup = max(3, warmup)
     # per-kernel durations: CUDA events around the forward and the adjoint launch on every `stride`-th timed step (an
     # event between two 90 us kernels costs a few us of GPU idle time, so not on every step)
-    stride = 1 if steps < 40 else 8
+    stride = 1 if steps < 8 else (4 if steps < 40 else 8)
 
     def timed_region():
         if cooldown_s:
@@ -290,7 +333,6 @@ def measure_resident(env, wl, shape, steps, warmup, cooldown_s=0.0):
         clocks = ClockSampler(env.local_rank)
         if env.rank == 0:
             clocks.start()
-            time.sleep(0.1)
         evs = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, steps, stride)}
         env.barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,7 +343,8 @@ def measure_resident(env, wl, shape, steps, warmup, cooldown_s=0.0):
         host_ms_ = (time.perf_counter() - t_host0) * 1e3 / steps   # CPU time spent issuing one step
         end.record()
         env.barrier()
-        clk_ = clocks.stop() if env.rank == 0 else None
+        t_host1 = time.perf_counter()
+        clk_ = clocks.stop(t_host0, t_host1) if env.rank == 0 else None
         return (start.elapsed_time(end), sum(e[0].elapsed_time(e[1]) for e in evs.values()) / len(evs),
                 sum(e[1].elapsed_time(e[2]) for e in evs.values()) / len(evs), host_ms_, clk_,
                 runtime.launch_count() - n0, len(evs))

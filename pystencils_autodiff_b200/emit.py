@@ -349,7 +349,9 @@ class MarchTuning:
     shuffle: Optional[bool] = None   # x-halo elements from neighbouring lanes instead of shared memory
     #                                  (default: yes; scalar LDS halos only win for narrow fp64 strips)
     lds_pair: Optional[bool] = None  # 8-byte fields, 4-cell strips: fetch a lane's two 16-byte vectors in an order that
-    #                                  depends on the lane, so that no LDS.128 has a bank conflict (psad_lds_pair); default on
+    #                                  depends on the lane, so that no LDS.128 has a bank conflict (psad_lds_pair).  Default
+    #                                  OFF: measured on B200 (profiles/r2_c4_bank_conflicts.md) the 40 extra selects per
+    #                                  step cost more than the conflicts (27-point fp64: 1.13 -> 1.30 ms at full clocks)
 
 
 def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
@@ -585,7 +587,7 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     def elem(f, j, row, c):
         return '%s[%d]' % (arr(f, j, row), c + geo[f.name]['hx'][0])
 
-    lds_pair = (t.lds_pair if t.lds_pair is not None else True) and any(
+    lds_pair = bool(t.lds_pair) and any(
         geo[f.name]['nv'] == 2 and geo[f.name]['es'] == 8 for f in tma_fields)
     # ---- source -------------------------------------------------------------------------------------------------
     jrel = min([j for j in range(D + 1) if any(fresh[f.name][j] for f in tma_fields)] or [D])

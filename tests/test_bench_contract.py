@@ -32,6 +32,7 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 
 @pytest.mark.gpu
+@pytest.mark.no_launch          # the launches happen in the bench.py process this test starts
 def test_gpu_arm_line_small():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '3', '--warmup', '3',
                           '--workload', 'c3', '--shape', '128', '128', '256', '--e2e-steps', '1', '--no-cpu-baseline'],
