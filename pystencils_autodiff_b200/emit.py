@@ -33,7 +33,7 @@ EMITTER_VERSION = '19'
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
 # chains stay as they are
-FAST_MATH_OPTIONS = ['-ftz=true', '-prec-div=false', '-prec-sqrt=false']
+FAST_MATH_OPTIONS = ['-ftz=true', '-prec-div=false', '-prec-sqrt=false', '-DPSAD_RSQRT_APPROX=1']
 
 
 @dataclass
@@ -45,7 +45,8 @@ class EmittedKernel:
     fields: List[Field]            # plan order: outputs then inputs
     scalars: List[str]
     plan: Dict = dc_field(default_factory=dict)
-    options: List[str] = dc_field(default_factory=lambda: ['-fmad=false'])
+    # PSAD_NVRTC_EXTRA: additional compiler options for experiments (part of the cache key like every option)
+    options: List[str] = dc_field(default_factory=lambda: ['-fmad=false'] + os.environ.get('PSAD_NVRTC_EXTRA', '').split())
 
     @property
     def cache_key(self):
