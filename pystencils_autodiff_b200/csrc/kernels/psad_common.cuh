@@ -118,15 +118,17 @@ template <typename T> PSAD_DEV void psad_stg_vec(T* p, const T* e) {
 #endif
 }
 
-// ---- reciprocal square root.  float: the hardware approximation (rsqrt.approx.ftz.f32, max relative error 2^-22.4;
-// subnormal arguments are treated as zero) followed by ONE Newton-Raphson step, y <- y + y/2 * (1 - x y^2), evaluated with two
-// FMAs: the result is within 1 ulp, the accuracy class of an IEEE 1/sqrt(x) pair, for 4 extra FP32 instructions and without
-// the subnormal pre-scaling branches of CUDA's rsqrtf().  PSAD_RSQRT_APPROX (AutoDiffOp(..., fast_math=True)) keeps the raw
-// approximation.  double: CUDA's rsqrt() (1 ulp).
+// ---- reciprocal square root.  float: the hardware approximation (rsqrt.approx.ftz.f32, max relative error 2^-22.4 — the
+// accuracy class of CUDA's rsqrtf(), without its subnormal pre-scaling branches; subnormal arguments are treated as zero).
+// -DPSAD_RSQRT_NEWTON=1 adds one Newton-Raphson step, y <- y + y/2 * (1 - x y^2) (two FMAs, result within 1 ulp).  Measured
+// on B200 for the TV-denoising gradient (scripts/c5_accuracy.py, profiles/r2_c5_accuracy.md): the error against the fp64
+// oracle does not change (adjoint 2.0e-7 .. 4.2e-7 norm-wise either way: it is set by the other ~60 fp32 operations per
+// cell), while the issue-bound adjoint kernel gets 15 % slower (0.72 -> 0.83 ms) — so it is not the default.
+// double: CUDA's rsqrt() (1 ulp).
 PSAD_DEV float psad_rsqrt(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-#ifndef PSAD_RSQRT_APPROX
+#ifdef PSAD_RSQRT_NEWTON
   const float e = __fmaf_rn(-x * r, r, 1.0f);          // 1 - x y^2
   r = __fmaf_rn(0.5f * r, e, r);
 #endif

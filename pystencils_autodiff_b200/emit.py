@@ -33,7 +33,7 @@ EMITTER_VERSION = '19'
 _CT = {np.dtype(np.float32): 'float', np.dtype(np.float64): 'double'}
 # AutoDiffOp(..., fast_math=True): denormals flushed, approximate reciprocal / square root (2 ulp); the explicit FMA
 # chains stay as they are
-FAST_MATH_OPTIONS = ['-ftz=true', '-prec-div=false', '-prec-sqrt=false', '-DPSAD_RSQRT_APPROX=1']
+FAST_MATH_OPTIONS = ['-ftz=true', '-prec-div=false', '-prec-sqrt=false']
 
 
 @dataclass

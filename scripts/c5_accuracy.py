@@ -1,5 +1,5 @@
 """C5 (TV-denoising gradient) accuracy and speed by arithmetic mode, against the fp64 oracle:
-fp32 compute with the Newton-refined reciprocal root (default), with the raw rsqrt.approx (PSAD_NVRTC_EXTRA=-DPSAD_RSQRT_APPROX=1),
+fp32 compute with the raw rsqrt.approx (default), with a Newton-refined reciprocal root (PSAD_NVRTC_EXTRA=-DPSAD_RSQRT_NEWTON=1),
 and data_type='double' (pystencils' default promotion: fp32 fields, fp64 arithmetic).
 
     python scripts/c5_accuracy.py

@@ -527,3 +527,27 @@ def test_backward_that_reads_nothing_still_allocates_its_outputs():
     (y,) = fn.apply(x)
     y.sum().backward()
     assert x.grad.shape == (8, 16) and float(x.grad.min()) == 3.0 and float(x.grad.max()) == 3.0
+
+
+@pytest.mark.parametrize('name', ['c2', 'c3', 'c4', 'c5'])
+def test_full_size_outputs_match_the_c_oracle_on_sampled_blocks(name):
+    """At the BASELINE.json sizes: blocks of planes (first, middle, last; whole images for C5) of what the forward and the
+    adjoint kernel produced, recomputed by the C restatement of the pystencils CPU loop nest (oracle/cgen.py, 'strict': double
+    precision, no contraction) from the same inputs plus their halo planes.  North-star tolerances: 1e-6 (fp32), 1e-12
+    (fp64), norm-wise.  (The same check runs inside bench.py's line as ``parity``.)"""
+    import types
+    import torch
+    import bench
+    from pystencils_autodiff_b200.configs import CONFIG_SHAPES
+    from pystencils_autodiff_b200.datahandling import SlabStencilOp
+    shape = tuple(CONFIG_SHAPES[name]['shape'])
+    op = make_config(name, shape=shape, boundary_handling='zeros')
+    slab = SlabStencilOp(op, local_shape=shape, rank=0, world_size=1, device=torch.device('cuda', 0))
+    g = torch.Generator(device='cuda')
+    g.manual_seed(77)
+    slab.randomize(g)
+    res = bench.oracle_parity(types.SimpleNamespace(torch=torch), name, op, slab)
+    assert slab.fwd.last_variant == 'march' and slab.bwd.last_variant == 'march'
+    assert res['ok'] and res['max_rel_err'] <= res['tolerance'], res
+    assert res['max_rel_err'] > 0 or name == 'c4'          # an fp32 kernel that matches a double oracle exactly compared nothing
+    assert len(res['blocks_dim0']) == 6

@@ -59,7 +59,7 @@ CASES = [
 def test_forward_backward_matches_oracle(name, shape, dtype, rng, bh):
     op = make_config(name, shape=shape, dtype=dtype, boundary_handling=bh)
     res, fn = run_op(op, shape, rng[0], rng[1], seed=1)
-    tol = TOL[dtype] * (50 if name == 'c5' else 1)  # TV: sqrt/div chains, norm-wise 5e-5 in fp32 arithmetic
+    tol = TOL[dtype]      # north_star: 1e-6 (fp32) / 1e-12 (fp64), the TV gradient's sqrt / division chains included
     for k, v in res.items():
         assert v <= tol, (name, shape, bh, k, v, fn.forward_kernel.last_variant, fn.backward_kernel.last_variant)
 
@@ -69,7 +69,7 @@ def test_forward_backward_matches_oracle(name, shape, dtype, rng, bh):
 def test_generic_variant_matches_oracle(name, shape, dtype, rng, bh):
     op = make_config(name, shape=shape, dtype=dtype, boundary_handling=bh)
     res, fn = run_op(op, shape, rng[0], rng[1], seed=2, variant='generic')
-    tol = TOL[dtype] * (50 if name == 'c5' else 1)
+    tol = TOL[dtype]
     for k, v in res.items():
         assert v <= tol, (name, shape, bh, k, v)
 
