@@ -729,13 +729,23 @@ extern "C" int psad_halo_exchange(void* comm, const void* lo_send, void* lo_recv
   NCCL_CHECK(g_nccl.ncclGroupStart());
   int rc = 0;
   // ncclInt8 == ncclChar == 0: counts are bytes
-  if (lo_rank >= 0) {
+  if (lo_rank >= 0 && lo_rank == hi_rank) {
+    // two ranks on a periodic domain: both neighbours are the same peer.  Sends and receives between one pair of ranks
+    // match in issue order, so the receives are posted in the order the peer sends: its first planes (our upper ghost
+    // planes), then its last planes (our lower ghost planes).
     if (!rc) rc = g_nccl.ncclSend(lo_send, bytes, 0, lo_rank, c, s);
-    if (!rc) rc = g_nccl.ncclRecv(lo_recv, bytes, 0, lo_rank, c, s);
-  }
-  if (hi_rank >= 0) {
     if (!rc) rc = g_nccl.ncclSend(hi_send, bytes, 0, hi_rank, c, s);
     if (!rc) rc = g_nccl.ncclRecv(hi_recv, bytes, 0, hi_rank, c, s);
+    if (!rc) rc = g_nccl.ncclRecv(lo_recv, bytes, 0, lo_rank, c, s);
+  } else {
+    if (lo_rank >= 0) {
+      if (!rc) rc = g_nccl.ncclSend(lo_send, bytes, 0, lo_rank, c, s);
+      if (!rc) rc = g_nccl.ncclRecv(lo_recv, bytes, 0, lo_rank, c, s);
+    }
+    if (hi_rank >= 0) {
+      if (!rc) rc = g_nccl.ncclSend(hi_send, bytes, 0, hi_rank, c, s);
+      if (!rc) rc = g_nccl.ncclRecv(hi_recv, bytes, 0, hi_rank, c, s);
+    }
   }
   int rc2 = g_nccl.ncclGroupEnd();
   if (rc) return fail(PSAD_ERR_NCCL, "ncclSend/ncclRecv failed: %s", g_nccl.ncclGetErrorString(rc));

@@ -36,9 +36,12 @@ __all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataH
 class SlabDecomposition:
     """Pure index logic of the 1-D decomposition along dim 0."""
 
-    def __init__(self, global_shape, rank, world_size, ghost_layers):
+    def __init__(self, global_shape, rank, world_size, ghost_layers, periodic=False):
+        """``periodic``: the domain wraps around along dim 0 — the first and the last rank are neighbours (one rank: its own
+        neighbour), the ghost planes at the global border receive the planes of the opposite end instead of staying zero."""
         self.global_shape = tuple(int(s) for s in global_shape)
         self.rank, self.world_size, self.g = int(rank), int(world_size), int(ghost_layers)
+        self.periodic = bool(periodic)
         n0 = self.global_shape[0]
         base, rem = divmod(n0, world_size)
         self.counts = [base + (1 if r < rem else 0) for r in range(world_size)]
@@ -50,10 +53,14 @@ class SlabDecomposition:
 
     @property
     def lo_rank(self):
+        if self.periodic and self.world_size > 1:
+            return (self.rank - 1) % self.world_size
         return self.rank - 1 if self.rank > 0 else -1
 
     @property
     def hi_rank(self):
+        if self.periodic and self.world_size > 1:
+            return (self.rank + 1) % self.world_size
         return self.rank + 1 if self.rank < self.world_size - 1 else -1
 
     @property
@@ -72,10 +79,10 @@ class SlabDecomposition:
         ``steps`` > 1: ranges of a kernel that applies the stencil ``steps`` times per launch (``halo``: its reach along
         dim 0 per step)."""
         return slab_ranges(self.global_shape, self.start, self.n_local, self.g, self.lo_rank >= 0, self.hi_rank >= 0,
-                           boundary, ghost_width_of_kernel, ndim, steps, halo)
+                           boundary, ghost_width_of_kernel, ndim, steps, halo, periodic=self.periodic)
 
 
-def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndim, steps=1, halo=None):
+def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndim, steps=1, halo=None, periodic=False):
     """Launch ranges for the slab owning global planes ``[start, start+n)``, stored with ``g`` ghost planes.
 
     Returns ``(interior, lo, hi)``: the planes that do not depend on the ghost planes of a neighbour, and the planes
@@ -106,6 +113,9 @@ def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndi
         dom_lo, dom_hi = margin, global_shape[0] - margin
     else:
         dom_lo, dom_hi = 0, global_shape[0]
+    if periodic:
+        # no global border along dim 0: every plane the local array holds (ghost planes included) belongs to the domain
+        dom_lo, dom_hi = start - g, start + n + g
     if fused:
         # global plane p lives at local index p - start + g
         it_lo[0] = max(dom_lo, start - g) - start + g
@@ -184,12 +194,21 @@ class HaloExchanger:
         else:
             import torch.distributed as dist
             ops = []
-            if dec.lo_rank >= 0:
-                ops.append(dist.P2POp(dist.isend, lo_send.contiguous(), dec.lo_rank, self.group))
-                ops.append(dist.P2POp(dist.irecv, lo_recv, dec.lo_rank, self.group))
-            if dec.hi_rank >= 0:
-                ops.append(dist.P2POp(dist.isend, hi_send.contiguous(), dec.hi_rank, self.group))
-                ops.append(dist.P2POp(dist.irecv, hi_recv, dec.hi_rank, self.group))
+            if dec.lo_rank >= 0 and dec.lo_rank == dec.hi_rank:
+                # two ranks on a periodic domain: both neighbours are the same peer.  Messages between one pair of ranks
+                # match in order, so the receives are posted in the order the peer sends: its first planes (our upper
+                # ghost planes) first, its last planes (our lower ghost planes) second
+                ops = [dist.P2POp(dist.isend, lo_send.contiguous(), dec.lo_rank, self.group),
+                       dist.P2POp(dist.isend, hi_send.contiguous(), dec.hi_rank, self.group),
+                       dist.P2POp(dist.irecv, hi_recv, dec.hi_rank, self.group),
+                       dist.P2POp(dist.irecv, lo_recv, dec.lo_rank, self.group)]
+            else:
+                if dec.lo_rank >= 0:
+                    ops.append(dist.P2POp(dist.isend, lo_send.contiguous(), dec.lo_rank, self.group))
+                    ops.append(dist.P2POp(dist.irecv, lo_recv, dec.lo_rank, self.group))
+                if dec.hi_rank >= 0:
+                    ops.append(dist.P2POp(dist.isend, hi_send.contiguous(), dec.hi_rank, self.group))
+                    ops.append(dist.P2POp(dist.irecv, hi_recv, dec.hi_rank, self.group))
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
@@ -206,10 +225,13 @@ class SlabDataHandling:
     what was executed with the reference's event names (``KernelCall``, ``Communication``, ``Swap``)."""
 
     def __init__(self, domain_size, rank=0, world_size=1, default_ghost_layers=1, device=None, backend='nccl',
-                 group=None):
+                 group=None, periodic=False):
+        """``periodic``: the domain is periodic along dim 0 (the decomposed axis): ghost-plane synchronisation wraps around
+        — what pystencils' serial data handling does inside one array for the reference (graph_datahandling.py:305-316 →
+        ``SerialDataHandling.synchronization_function``).  The other axes keep the kernels' own boundary treatment."""
         import torch
         self.torch = torch
-        self.dec = SlabDecomposition(domain_size, rank, world_size, default_ghost_layers)
+        self.dec = SlabDecomposition(domain_size, rank, world_size, default_ghost_layers, periodic)
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
         self.device = torch.device(device)
@@ -399,7 +421,14 @@ class SlabDataHandling:
     def start_exchange(self, name):
         """Asynchronous: exchange on the communication stream, ordered after everything already queued on the
         current stream."""
-        if self.dec.world_size == 1 or self.dec.g == 0 or name in self._replicated:
+        if self.dec.g == 0 or name in self._replicated:
+            return
+        if self.dec.world_size == 1:
+            if self.dec.periodic:
+                # one rank on a periodic domain is its own neighbour: two device copies on the current stream
+                t, g, n = self.gpu_arrays[name], self.dec.g, self.dec.n_local
+                t[:g].copy_(t[n:n + g])
+                t[n + g:].copy_(t[g:2 * g])
             return
         t = self.gpu_arrays[name]
         if t.is_cuda:
@@ -790,14 +819,18 @@ class GraphDataHandling(SlabDataHandling):
     """``SlabDataHandling`` behind the reference's constructor (graph_datahandling.py:196-200 /
     framework_integration/datahandling.py:176-183: ``(domain_size, default_ghost_layers, default_layout, periodicity,
     default_target)``).  Rank and world size come from ``torch.distributed`` when a process group is initialised, so the
-    same script runs on one GPU or slab-decomposed under torchrun.  ``periodicity`` is not supported (the global boundary
-    is 'zeros' or interior iteration), layouts other than 'numpy' (C order) neither; ``default_target`` must be 'gpu'."""
+    same script runs on one GPU or slab-decomposed under torchrun.  ``periodicity``: ``False``, or periodic along dim 0 only
+    (``(True, False, ...)``: the decomposed axis, where ghost planes exist; arrays carry no ghost cells along the other axes,
+    so periodicity there raises); layouts other than 'numpy' (C order) raise; ``default_target`` must be 'gpu'."""
 
     def __init__(self, domain_size, default_ghost_layers=0, default_layout='numpy', periodicity=False,
                  default_target='gpu', device=None, backend=None):
         import torch.distributed as dist
-        if periodicity not in (False, None) and any(periodicity if hasattr(periodicity, '__iter__') else [periodicity]):
-            raise NotImplementedError('periodic domains are not supported: the global boundary is zeros / interior iteration')
+        nd = len(domain_size)
+        per = tuple(bool(p) for p in periodicity) if hasattr(periodicity, '__iter__') else (bool(periodicity),) * nd
+        if any(per[1:]):
+            raise NotImplementedError('periodicity is supported along dim 0 only (the decomposed axis, where ghost planes '
+                                      'exist): pass periodicity=(True,%s)' % (' False,' * (nd - 1)))
         if default_layout not in ('numpy', 'c', 'C'):
             raise NotImplementedError("only the 'numpy' (C order) layout is supported")
         if default_target not in ('gpu', None):
@@ -805,7 +838,7 @@ class GraphDataHandling(SlabDataHandling):
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
         if backend is None:
             backend = 'nccl' if (world == 1 or dist.get_backend() == 'nccl') else 'torch'
-        super().__init__(domain_size, rank, world, default_ghost_layers, device, backend)
+        super().__init__(domain_size, rank, world, default_ghost_layers, device, backend, periodic=per[0])
         self.default_target = 'gpu'
 
 

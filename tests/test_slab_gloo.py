@@ -609,3 +609,89 @@ def test_computation_graph_of_a_recorded_time_loop(tmp_path):
     assert len(merged.computation_nodes) == len(g.computation_nodes)
     with pytest.raises(KeyError):
         ComputationGraph([('KernelCall', 'unknown_kernel')])
+
+
+def _periodic_reference(assigns, key, src_name, glob, g):
+    """Global field periodic along dim 0, 'zeros' along the other axes: evaluate on the field wrapped by ``g`` planes."""
+    from oracle import evaluate
+    wrapped = np.concatenate([glob[-g:], glob, glob[:g]], axis=0)
+    return evaluate(assigns, {src_name: wrapped}, 'zeros')[key][g:-g]
+
+
+def _periodic_check(dh, op_g, gshape, glob_u, glob_go, bh):
+    from oracle import evaluate
+    from pystencils_autodiff_b200.configs import make_config
+    g = dh.dec.g
+    sl = slice(dh.dec.start, dh.dec.start + dh.dec.n_local)
+    dh.owned('u').copy_(torch.from_numpy(glob_u[sl]))
+    dh.owned('diffout').copy_(torch.from_numpy(glob_go[sl]))
+    dh.synchronization_function(['u', 'diffout'])()
+    name = op_g.op_name
+    op_l = {'heat3d': 'c3', 'stencil27': 'c4'}[name]
+    op_l = make_config(op_l, shape=dh.dec.local_shape, dtype='float64', boundary_handling='zeros')
+    res = {}
+    for key, asg_l, asg_g, src, glob in (('out', op_l.forward_assignments, op_g.forward_assignments, 'u', glob_u),
+                                         ('diffu', op_l.backward_assignments, op_g.backward_assignments, 'diffout', glob_go)):
+        local = evaluate(asg_l, {src: dh.gpu_arrays[src].numpy()}, 'zeros')[key][dh.dec.owned]
+        ref = _periodic_reference(asg_g, key, src, glob, g)[sl]
+        res[key] = float(np.abs(local - ref).max())
+    # launch ranges: every rank has neighbours on both sides (or is its own), nothing is clipped along dim 0
+    ir = op_l.forward_ast_gpu
+    cover = np.zeros(dh.dec.local_shape[0], dtype=int)
+    for r in dh.dec.ranges('none' if bh is None else 'zeros', 1, ir.ndim):
+        if r is not None:
+            cover[r['write_lo'][0]:r['write_hi'][0]] += 1
+            assert r['iter_lo'][0] >= g and r['iter_hi'][0] <= g + dh.dec.n_local
+            assert r['iter_lo'][0] == r['write_lo'][0] and r['iter_hi'][0] == r['write_hi'][0]
+    assert list(cover[dh.dec.owned]) == [1] * dh.dec.n_local
+    return res
+
+
+def _periodic_worker(rank, world, port, name, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from pystencils_autodiff_b200.configs import make_config
+        from pystencils_autodiff_b200.datahandling import SlabDataHandling
+        gshape = (12, 5, 6)
+        op_g = make_config(name, shape=(gshape[0] + 2,) + gshape[1:], dtype='float64', boundary_handling='zeros')
+        dh = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch', periodic=True)
+        assert dh.dec.lo_rank == (rank - 1) % world and dh.dec.hi_rank == (rank + 1) % world
+        dh.add_array('u', dtype=np.float64)
+        dh.add_array('diffout', dtype=np.float64)
+        rng = np.random.default_rng(8)
+        q.put((rank, _periodic_check(dh, op_g, gshape, rng.normal(size=gshape), rng.normal(size=gshape), 'zeros')))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('name,world', [('c3', 2), ('c4', 3)])
+def test_periodic_synchronisation_wraps_around(name, world):
+    """graph_datahandling.py:305-316 -> pystencils' periodic ghost-layer copy: with ``periodic=True`` the first and last rank
+    exchange planes (two ranks: both neighbours are the same peer, the receives are ordered accordingly)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_periodic_worker, args=(r, world, 29871 + world, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for rank, res in _collect(procs, q, world):
+        assert res['out'] < 1e-13 and res['diffu'] < 1e-13, (rank, res)
+
+
+def test_periodic_single_rank_is_its_own_neighbour():
+    from pystencils_autodiff_b200.configs import make_config
+    from pystencils_autodiff_b200.datahandling import GraphDataHandling, SlabDataHandling
+    gshape = (7, 5, 6)
+    op_g = make_config('c3', shape=(gshape[0] + 2,) + gshape[1:], dtype='float64', boundary_handling='zeros')
+    dh = SlabDataHandling(gshape, 0, 1, 1, device='cpu', backend='torch', periodic=True)
+    dh.add_array('u', dtype=np.float64)
+    dh.add_array('diffout', dtype=np.float64)
+    rng = np.random.default_rng(2)
+    res = _periodic_check(dh, op_g, gshape, rng.normal(size=gshape), rng.normal(size=gshape), 'zeros')
+    assert res['out'] < 1e-13 and res['diffu'] < 1e-13
+    # the reference's constructor: periodic along the decomposed axis is accepted, other axes are refused with a reason
+    assert GraphDataHandling((8, 8), 1, periodicity=(True, False), device='cpu').dec.periodic
+    with pytest.raises(NotImplementedError, match='dim 0 only'):
+        GraphDataHandling((8, 8), 1, periodicity=True, device='cpu')
