@@ -451,8 +451,8 @@ class SlabDataHandling:
             return
         self.torch.cuda.current_stream(self.device).wait_event(self._ev_halo)
 
-    def create_timeloop(self, use_cuda_graph=True):
-        return TimeLoop(self, use_cuda_graph)
+    def create_timeloop(self, use_cuda_graph=True, concurrent=True):
+        return TimeLoop(self, use_cuda_graph, concurrent)
 
     # -- kernels ---------------------------------------------------------------------------------------------------
     def run_kernel(self, kernel, halo_fields=(), fused_steps=1, **kwargs):
@@ -852,10 +852,20 @@ class TimeLoop:
     ``add_post_run_function``, ``add_single_step_function``, ``add_call``, ``run``).  On one GPU the body of a time step
     (kernel launches and swaps) is captured once into a **CUDA graph** and replayed, which removes the per-launch host
     latency for small fields; with more than one rank (halo exchange inside the step) the calls are issued eagerly.
+
+    **Scheduling from the dependency graph** (f-3, the reference's ``ComputationGraph`` over a call queue,
+    computationgraph.py:17-163): when every part of the step was added through ``add_call(kernel, ...)`` / ``swap`` the
+    loop knows what each call reads and writes, derives the levels of mutually independent calls
+    (``computationgraph.ComputationGraph.levels``) and — on one rank — issues the calls of one level on different streams,
+    forked from and joined back into the current stream with events.  Inside the captured CUDA graph those become parallel
+    branches.  ``levels()`` shows the schedule; ``concurrent=False`` turns it off.
     """
 
-    def __init__(self, data_handling, use_cuda_graph=True):
+    def __init__(self, data_handling, use_cuda_graph=True, concurrent=True):
         self.dh = data_handling
+        self.concurrent = concurrent
+        self._entries = []                # structured step parts: ('kernel', kernel, kwargs, halo) | ('swap', a, b) | None
+        self._side_streams = []
         self._pre, self._post, self._steps = [], [], []
         self._single_step_asts = []       # what one step consists of, in the reference's vocabulary (for TimeloopRun)
         self.time_steps_run = 0
@@ -875,10 +885,12 @@ class TimeLoop:
     def add_post_run_function(self, f):
         self._post.append(f)
 
-    def add_single_step_function(self, f):
+    def add_single_step_function(self, f, _entry=None):
         self._steps.append(f)
+        self._entries.append(_entry)      # None: an opaque function — the step is then issued in program order
         self._graphs.clear()
         self._step_record = None
+        self._levels = None
 
     def add_call(self, functor, argument_list=None):
         args = argument_list if argument_list is not None else {}
@@ -888,7 +900,8 @@ class TimeLoop:
             if isinstance(functor, CompiledKernel):
                 halo = a.pop('halo_fields', ()) if isinstance(a, dict) else ()
                 self._single_step_asts.append(('KernelCall', functor.function_name))
-                self.add_single_step_function(lambda k=functor, kw=a, h=halo: self.dh.run_kernel(k, halo_fields=h, **kw))
+                self.add_single_step_function(lambda k=functor, kw=a, h=halo: self.dh.run_kernel(k, halo_fields=h, **kw),
+                                              _entry=('kernel', functor))
             else:
                 self._single_step_asts.append(('Call', getattr(functor, '__name__', type(functor).__name__)))
                 self.add_single_step_function(lambda f=functor, kw=a: f(**kw))
@@ -899,12 +912,58 @@ class TimeLoop:
         src = src if isinstance(src, str) else src.name
         dst = dst if isinstance(dst, str) else dst.name
         self._single_step_asts.append(('Swap', src, dst))
-        self.add_single_step_function(lambda a=src, b=dst: self.dh.swap(a, b, is_gpu))
+        self.add_single_step_function(lambda a=src, b=dst: self.dh.swap(a, b, is_gpu), _entry=('swap', src, dst))
+
+    _levels = None
+
+    def levels(self):
+        """The step as levels of mutually independent parts (lists of indices into the step's parts, in order), from the
+        array versions each part reads and writes; None when the step contains an opaque function."""
+        if self._levels is None:
+            if not self._entries or any(e is None for e in self._entries):
+                return None
+            from .computationgraph import ComputationGraph
+            queue, io = [], {}
+            for e in self._entries:
+                if e[0] == 'kernel':
+                    k = e[1]
+                    io[k.function_name] = ([f.name for f in k.ir.input_fields], [f.name for f in k.ir.output_fields])
+                    queue.append(('KernelCall', k.function_name))
+                else:
+                    queue.append(('Swap', e[1], e[2]))
+            graph = ComputationGraph(queue, io)
+            self._levels = [[n.index for n in level] for level in graph.levels()]
+        return self._levels
 
     def _one_step(self):
         n = len(self.dh.call_queue)
-        for f in self._steps:
-            f()
+        levels = self.levels() if (self.concurrent and self.dh.dec.world_size == 1) else None
+        torch = self.dh.torch
+        if levels is None or all(len(lv) == 1 for lv in levels) or not torch.cuda.is_available() \
+                or not all(t.is_cuda for t in self.dh.gpu_arrays.values()):
+            for f in self._steps:
+                f()
+        else:
+            cur = torch.cuda.current_stream(self.dh.device)
+            for lv in levels:
+                kernels = [i for i in lv if self._entries[i][0] == 'kernel']
+                if len(kernels) > 1:
+                    while len(self._side_streams) < len(kernels) - 1:
+                        self._side_streams.append(torch.cuda.Stream(self.dh.device))
+                    fork = torch.cuda.Event()
+                    fork.record(cur)
+                    self._steps[kernels[0]]()
+                    for s_, i in zip(self._side_streams, kernels[1:]):
+                        s_.wait_event(fork)
+                        with torch.cuda.stream(s_):
+                            self._steps[i]()
+                        cur.wait_stream(s_)
+                else:
+                    for i in kernels:
+                        self._steps[i]()
+                for i in lv:                       # swaps are host-side role changes: in order, after the level's launches
+                    if self._entries[i][0] != 'kernel':
+                        self._steps[i]()
         if self._step_record is None:
             self._step_record = tuple(self.dh.call_queue[n:])
 

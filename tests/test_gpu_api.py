@@ -551,3 +551,46 @@ def test_full_size_outputs_match_the_c_oracle_on_sampled_blocks(name):
     assert res['ok'] and res['max_rel_err'] <= res['tolerance'], res
     assert res['max_rel_err'] > 0 or name == 'c4'          # an fp32 kernel that matches a double oracle exactly compared nothing
     assert len(res['blocks_dim0']) == 6
+
+
+def test_timeloop_schedules_independent_calls_from_the_dependency_graph():
+    """f-3: the step's parts are grouped into levels of mutually independent calls (ComputationGraph.levels over what each
+    kernel reads / writes); the calls of a level go to different streams (parallel branches of the captured CUDA graph).
+    Forward and adjoint of one step are independent, the two swaps follow; a third kernel reading the adjoint's output
+    must wait for it.  Same bits as issuing everything in program order."""
+    import torch
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    shape = (64, 128)
+    op = make_config('c2', shape=shape)
+    fk, bk = CompiledKernel(op.forward_ast_gpu), CompiledKernel(op.backward_ast_gpu)
+    w, diffu = ps.fields('w, diffu: float32[64,128]')
+    third = CompiledKernel(ps.AutoDiffOp([ps.Assignment(w.center, 2 * diffu[0, 1] - diffu[1, 0])],
+                                         boundary_handling='zeros').forward_ast_gpu)
+    rng = np.random.default_rng(12)
+    U0, G0 = rng.normal(size=shape).astype(np.float32), rng.normal(size=shape).astype(np.float32)
+    finals = []
+    for concurrent in (True, False):
+        dh = SlabDataHandling(shape, 0, 1, 0, device='cuda:0')
+        dh.add_arrays('u, out, diffout, diffu, w', dtype=np.float32)
+        dh.owned('u').copy_(_t(U0))
+        dh.owned('diffout').copy_(_t(G0))
+        tl = dh.create_timeloop(use_cuda_graph=True, concurrent=concurrent)
+        tl.add_call(fk, {})
+        tl.add_call(bk, {})
+        tl.add_call(third, {})
+        tl.swap('u', 'out')
+        assert tl.levels() == [[0, 1], [2, 3]]       # forward | adjoint, then the kernel reading diffu and the swap
+        tl.run(9)
+        torch.cuda.synchronize()
+        finals.append({n: dh.owned(n).clone() for n in ('u', 'diffu', 'w')})
+    for n in finals[0]:
+        assert torch.equal(finals[0][n], finals[1][n]), n
+    ref = evaluate(third.ir.assignments if hasattr(third.ir, 'assignments') else
+                   [ps.Assignment(w.center, 2 * diffu[0, 1] - diffu[1, 0])], dict(diffu=finals[0]['diffu'].cpu().numpy()), 'zeros')['w']
+    assert np.abs(finals[0]['w'].cpu().numpy() - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+    # an opaque step function makes the step unschedulable: program order
+    tl2 = dh.create_timeloop()
+    tl2.add_call(fk, {})
+    tl2.add_single_step_function(lambda: None)
+    assert tl2.levels() is None
