@@ -12,7 +12,7 @@ for w in c4 c2 c5; do
   PSAD_MARCH_ONLY=1 ncu --set full --clock-control none --import-source on -k regex:forward_gpu_march -c 1 -o gpurun_out/r2_${w}_fwd $K > gpurun_out/r2_ncu_full_$w.log 2>&1; echo "ncu full $w fwd rc=$?"
 done
 PSAD_MARCH_ONLY=1 ncu --set full --clock-control none --import-source on -k regex:tvgrad_backward_gpu_march -c 1 -o gpurun_out/r2_c5_bwd python scripts/kbench.py c5 > gpurun_out/r2_ncu_full_c5b.log 2>&1; echo "ncu full c5 bwd rc=$?"
+# compute-sanitizer is closed on this pool (rc 86, "runs under it have left GPUs needing a reset"): the small-launch script
+# below still runs plain; the race evidence for the row-exchange kernel is the CPU replay with concurrent warps
+# (tests/test_march_replay.py::test_replay_detects_a_missing_consumer_barrier)
 python scripts/sanitize_small.py > gpurun_out/r2_sanitize_plain.log 2>&1; echo "sanitize plain rc=$?"
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool python scripts/sanitize_small.py > gpurun_out/r2_sanitize_$tool.log 2>&1; echo "$tool rc=$?"; tail -3 gpurun_out/r2_sanitize_$tool.log
-done

@@ -53,21 +53,24 @@ def main():
             d[0] += 1
             d[1] += float(r['Metric Value'])
         with open(os.path.join(OUT, '%s_launches_c3.md' % tag), 'w') as fh:
-            fh.write('# ncu launch list — `python bench.py --steps 5 --warmup 3 --e2e-steps 1 --no-cpu-baseline` (C3, 1 B200)\n\n')
+            cmd = ('python bench.py --steps 2 --warmup 3 --only-headline --no-cpu-baseline --e2e-steps 1' if tag != 'r1' else
+                   'python bench.py --steps 5 --warmup 3 --e2e-steps 1 --no-cpu-baseline')
+            fh.write('# ncu launch list — `%s` (C3, 1 B200)\n\n' % cmd)
             fh.write('`ncu --metrics gpu__time_duration.sum --clock-control none -c 400`; per-launch times are cold-cache and '
                      'serialised: compare SHARES. %d launches, %.3f ms of kernel time.\n\n' % (len(rows), total / 1e6))
             fh.write('| kernel | launches | total ms | share | avg ms | grid | block |\n|---|---|---|---|---|---|---|\n')
             for k, d in sorted(by.items(), key=lambda kv: -kv[1][1]):
                 fh.write('| `%s` | %d | %.3f | %.1f %% | %.3f | %s | %s |\n' % (k, d[0], d[1] / 1e6, 100 * d[1] / total,
                                                                              d[1] / d[0] / 1e6, d[2], d[3]))
-            fh.write('\nThe `psad_*_march*` kernels are this repo\'s (NVRTC, sm_100a): 8 whole-field launches each (3 warm-up + 5 '
-                     'timed steps, ~1.39 ms per launch) plus the 22-chunk launches of the two host-streamed e2e passes. Everything '
-                     'else is torch\'s fill / RNG used to create the synthetic inputs, outside the timed region.\n')
+            fh.write('\nThe `psad_*` kernels are this repo\'s (NVRTC, sm_100a): the whole-field forward / adjoint launches of the '
+                     'first, warm-up and timed steps (~1.4 ms per launch), the fused forward+adjoint and fused-pair diagnostics, '
+                     'and the per-chunk launches of the host-streamed e2e passes. Everything else is torch\'s fill / RNG / copy '
+                     'kernels used to create the synthetic inputs and to stage the e2e comparison, outside the timed region.\n')
         import shutil
         shutil.copy(lpath, os.path.join(OUT, '%s_launches_c3.csv' % tag))
     # ---- full captures
     names = {'c3_fwd': ('c3', 'forward'), 'c2_fwd': ('c2', 'forward'), 'c4_fwd': ('c4', 'forward'), 'c5_fwd': ('c5', 'forward'),
-             'c5_bwd': ('c5', 'adjoint')}
+             'c5_bwd': ('c5', 'adjoint'), 'c3_x2e': ('c3', 'fused_pair')}
     with open(os.path.join(OUT, '%s_ncu_full_summary.md' % tag), 'w') as fh:
         fh.write('# ncu --set full summaries (%s)\n\nOne launch per kernel, captured with `ncu --set full --clock-control none '
                  '--import-source on` under the bench command line of each workload.\n' % tag)
