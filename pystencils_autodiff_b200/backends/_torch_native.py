@@ -100,9 +100,9 @@ class CompiledKernel:
     def run_steps(self, src, steps, out=None, fuse=None, **scalars):
         """``S^steps(src)``: the stencil applied ``steps`` times, ping-ponging between ``out`` and one scratch tensor;
         ``src`` is not modified.  ``fuse``: run pairs of steps as one launch (one read and one write of the field per
-        pair instead of two).  Default: where that is a measured win — 4-byte fields (7-point fp32 at 1024^3: 1.61x);
-        for fp64 the rows recomputed by the fused kernel cost as much FP64 issue as the saved traffic (27-point fp64 at
-        768^3: 1.00x), so those stay on single-step launches unless asked."""
+        pair instead of two).  Default: wherever a fused pair can be built (one-field stencils on dense aligned rows, 3-D
+        or 2-D with the 'zeros' boundary) — measured wins on B200: 7-point fp32 at 1024^3 1.62x, 5-point fp32 at 8192^2
+        1.39x, 27-point fp64 at 768^3 1.11x (two CTAs per SM, rows exchanged through shared memory)."""
         import torch
         if len(self.ir.input_fields) != 1 or len(self.ir.output_fields) != 1:
             raise ValueError('%s: run_steps needs a kernel with one input and one output field' % self.function_name)
@@ -113,9 +113,9 @@ class CompiledKernel:
         if fuse and not can_pair:
             raise ValueError('%s: steps cannot be fused: %s' % (self.function_name, self.fused_steps_reason() or
                                                                 'tensor layout needs the generic kernel'))
-        # measured wins only: 3-D fields of 4-byte elements (2-D pairs work — lifted to one-plane 3-D fields — but have
-        # not been timed yet, so they need an explicit fuse=True)
-        pair = can_pair and ((src.element_size() == 4 and self.ir.ndim == 3) if fuse is None else bool(fuse))
+        # pairs wherever they can be built: every measured case wins (round 2, scripts/steps_bench.py: 7-point fp32 1024^3
+        # 1.62x, 5-point fp32 8192^2 — lifted to a one-plane 3-D field — 1.39x, 27-point fp64 768^3 1.11x)
+        pair = can_pair if fuse is None else bool(fuse)
         launches = [2] * (steps // 2) + [1] * (steps % 2) if pair else [1] * steps
         out = torch.empty_like(src) if out is None else out
         if out.data_ptr() == src.data_ptr():

@@ -91,9 +91,15 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     #   rows exchanged through shared memory, 44x128 tiles, 4 x 4 cells per thread, 11+1 warps, 168 registers: 1.73 ms
     #   same with 30x128 tiles, 2 x 4 cells, 15+1 warps, 109 registers: 1.79 ms
     #   rows recomputed, 30x128 tiles, 2 x 4 cells, 15+1 warps, 128 registers: 1.99 ms
-    # 27-point fp64 at 768^3, two launches = 2.26 ms: recomputed rows 22x64 / 2 x 2 cells / 11+1 warps 2.29 ms,
-    # exchanged rows 28x64 / 4 x 2 cells 2.37 ms — no gain either way, fp64 pairs are not fused by default (run_steps).
-    want_exchange = (es == 4) if t.exchange is None else bool(t.exchange)
+    # 27-point fp64 at 768^3, two launches = 2.31 ms (round 2, scripts/steps_bench.py): recomputed rows 22x64 / 2 x 2 cells /
+    # 11+1 warps 2.28 ms; exchanged rows 28x64 / 4 x 2 cells, one CTA per SM 2.37 ms; exchanged rows with TWO CTAs per SM
+    # (while one waits at its per-plane barrier the other computes) 18x64 tiles / 2 x 2 cells / 9+1 warps / 96 registers:
+    # 2.09 ms = 1.11x — the fp64 default; 14x64: 2.12 ms, three CTAs of 10x64: 2.64 ms.
+    want_exchange = True if t.exchange is None else bool(t.exchange)
+    fp64_default = es == 8 and want_exchange and not (t.ry or t.ty or t.sx or t.min_ctas)
+    if fp64_default:
+        import dataclasses
+        t = dataclasses.replace(t, ry=2, ty=18, sx=2, min_ctas=2)
     SX = t.sx or (4 if es == 4 else 2)
     if (SX * es) % 16:
         raise ValueError('sx*itemsize must be a multiple of 16 bytes')

@@ -58,6 +58,13 @@ def report(ek, label, cells_per_step, cells):
     mix = collections.Counter(op.split('.')[0] for _, op, _ in rows)
     print('%s  %s' % (label, ' '.join(re.findall(r'REG:\d+|STACK:\d+|SHARED:\d+', res))))
     print('  whole kernel: %d instructions  %s' % (len(rows), dict(mix.most_common(12))))
+    ops = collections.Counter(op for _, op, _ in rows)
+    tma = sum(v for k, v in ops.items() if k.startswith('UTMALDG'))
+    syncs = sum(v for k, v in ops.items() if k.startswith('SYNCS'))
+    local = sum(v for k, v in ops.items() if k.split('.')[0] in ('STL', 'LDL'))
+    vec = {k: v for k, v in ops.items() if k.startswith(('LDS.128', 'STG.E.EF.128', 'STG.E.128', 'STS.128', 'LDG'))}
+    print('  Blackwell markers: UTMALDG (TMA tensor loads) %d, SYNCS (mbarrier) %d, local-memory LDL/STL %d; vector memory ops %s'
+          % (tma, syncs, local, vec))
     loop = hottest_loop(rows)
     if loop:
         body = [r for r in rows if loop[0] <= r[0] <= loop[1]]
