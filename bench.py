@@ -654,9 +654,9 @@ def extra_legs(env, wl, op, slab, args, with_fused=True):
             tmp.copy_(keep)
             steps_info = {'two_launches_ms': t_two, 'one_fused_launch_ms': t_x2, 'speedup': t_two / t_x2,
                           'gcell_steps_per_s': 2 * src.numel() / (t_x2 * 1e-3) / 1e9,
-                          'used_by_default': bool(src.element_size() == 4),
-                          'note': 'out = S(S(u)) with one read and one write of the field; run_steps() / '
-                                  'create_unrolled_torch_op() fuse pairs only where this is a win (4-byte fields)'}
+                          'used_by_default': True,
+                          'note': 'out = S(S(u)) with one read and one write of the field; the default of run_steps() / '
+                                  'create_unrolled_torch_op() wherever a pair can be built'}
     except Exception as exc:   # a diagnostic beside the headline must never take the line down
         steps_info = {'error': '%s: %s' % (type(exc).__name__, exc)}
     out['fused_steps'] = steps_info
@@ -699,6 +699,16 @@ def main_ours(args):
     # ---- end to end through the public API with HOST buffers (copies inside the timed region) -------------------
     e2e_error = None
     try:
+        # every rank pins one host buffer per field: refuse (and say so) rather than drive the box out of memory
+        need = sum(t.numel() * t.element_size() for t in slab.dh.gpu_arrays.values()) * env.world
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        if avail is not None and need > 0.6 * avail:
+            raise MemoryError('the e2e leg pins %.0f GB of host memory over %d ranks, %.0f GB are available'
+                              % (need / 1e9, env.world, avail / 1e9))
         e2e = slab.end_to_end(args.e2e_steps, env.barrier)
     except Exception as exc:   # e.g. not enough pinnable host memory: keep the line, say what happened
         e2e_error = '%s: %s' % (type(exc).__name__, exc)
