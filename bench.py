@@ -54,6 +54,7 @@ def parse_args():
                     help='strong scaling: the workload shape is the GLOBAL field, split along dim 0 over the ranks '
                          '(default: weak scaling, every rank owns the full workload shape)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (diagnostic runs)')
     ap.add_argument('--only-headline', action='store_true', help='skip the extra N = 1 legs (workloads, function path, parity)')
     ap.add_argument('--cpu-shape', type=int, nargs='*', default=None, help='CPU arm: sample shape (default: the full workload)')
     return ap.parse_args()
@@ -81,6 +82,8 @@ class ClockSampler:
     def start(self):
         self.running = True
         try:
+            if os.environ.get('PSAD_BENCH_NO_NVML'):
+                raise ImportError('NVML polling disabled')
             import pynvml
             pynvml.nvmlInit()
             visible = os.environ.get('CUDA_VISIBLE_DEVICES')
@@ -699,6 +702,8 @@ def main_ours(args):
     # ---- end to end through the public API with HOST buffers (copies inside the timed region) -------------------
     e2e_error = None
     try:
+        if args.no_e2e:
+            raise RuntimeError('skipped (--no-e2e)')
         # every rank pins one host buffer per field: refuse (and say so) rather than drive the box out of memory
         need = sum(t.numel() * t.element_size() for t in slab.dh.gpu_arrays.values()) * env.world
         try:

@@ -33,6 +33,10 @@ __all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataH
            'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
 
 
+import os as _os
+_ALWAYS_ORDER_SIDE_LAUNCHES = bool(_os.environ.get('PSAD_ALWAYS_ORDER_SIDE'))     # diagnostic switch (scripts/r2_ab_multi.sh)
+
+
 class SlabDecomposition:
     """Pure index logic of the 1-D decomposition along dim 0."""
 
@@ -422,14 +426,14 @@ class SlabDataHandling:
         """Asynchronous: exchange on the communication stream, ordered after everything already queued on the
         current stream."""
         if self.dec.g == 0 or name in self._replicated:
-            return
+            return False
         if self.dec.world_size == 1:
             if self.dec.periodic:
                 # one rank on a periodic domain is its own neighbour: two device copies on the current stream
                 t, g, n = self.gpu_arrays[name], self.dec.g, self.dec.n_local
                 t[:g].copy_(t[n:n + g])
                 t[n + g:].copy_(t[g:2 * g])
-            return
+            return False
         t = self.gpu_arrays[name]
         if t.is_cuda:
             comm = self._streams()
@@ -442,8 +446,9 @@ class SlabDataHandling:
                 with self.torch.cuda.stream(comm):
                     self.exchanger.exchange(t)
             self._ev_halo.record(comm)
-        else:
-            self.exchanger.exchange(t)
+            return True
+        self.exchanger.exchange(t)
+        return False
 
     def finish_exchange(self):
         """Make the current stream wait for the halos (device-side dependency only, no host sync)."""
@@ -513,16 +518,16 @@ class SlabDataHandling:
         interior, lo, hi = self._range_cache[key][1]
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
-        for n in halo_fields:
-            self.start_exchange(n)
+        ordered = [self.start_exchange(n) for n in halo_fields]      # True where the comm stream was ordered behind `cur`
         side = [r for r in (lo, hi) if r is not None]
         on_comm = bool(side) and self._comm_stream is not None and all(t.is_cuda for t in arrays.values())
         if on_comm:
             # the side launches read inputs produced on the current stream (and write outputs whose previous user may
             # still be pending there): order the communication stream behind it even when no exchange was started
             # in this call (start_exchange records the same dependency; a second record / wait is harmless)
-            self._ev_ready.record(self.torch.cuda.current_stream(self.device))
-            self._comm_stream.wait_event(self._ev_ready)
+            if not any(ordered) or _ALWAYS_ORDER_SIDE_LAUNCHES:
+                self._ev_ready.record(self.torch.cuda.current_stream(self.device))
+                self._comm_stream.wait_event(self._ev_ready)
             for r in side:
                 kernel(**arrays, **kwargs, _range=r, _stream=self._comm_stream.cuda_stream)
             self._ev_halo.record(self._comm_stream)
