@@ -73,9 +73,18 @@ class CompiledKernel:
 
     @property
     def variants(self):
-        return sorted(v for v in self._emitted if v != 'march_nomask')
+        return sorted(v for v in self._emitted if v in ('march', 'generic', 'march_x2'))
 
     def emitted(self, variant):
+        if variant in ('march_peer', 'march_nomask_peer') and variant not in self._emitted:
+            if 'march' not in self._emitted or self._components:
+                raise ValueError('%s: peer halos need the march kernel (%s)' % (self.function_name, self._march_reason))
+            self._emitted[variant] = emit_march(self._scalar_ir, self.tuning, masked=(variant == 'march_peer'), peer=True)
+        if variant == 'march_x2_peer' and variant not in self._emitted:
+            reason = self.fused_steps_reason() or ('needs 3-D fields' if self.ir.ndim != 3 else None)
+            if reason:
+                raise ValueError('%s: two fused steps per launch are not available: %s' % (self.function_name, reason))
+            self._emitted[variant] = emit_march_chain(self.ir, self.tuning_x2, peer=True)
         if variant == 'march_x2' and variant not in self._emitted:
             reason = self.fused_steps_reason()
             if reason:
@@ -167,20 +176,23 @@ class CompiledKernel:
 
     max_remembered_launches = 64
 
-    def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
+    def __call__(self, *, _range=None, _variant=None, _stream=None, _peer=None, **kwargs):
+        """``_peer``: a ``runtime.Peer`` struct (neighbouring GPUs' arrays per field in plan order, completion counters,
+        ``expect`` set by the caller) — the launch then uses the peer-halo instance of the march kernel."""
         try:
-            key = [_variant, id(_range)]
+            key = [_variant, id(_range), id(_peer)]
             for n in self._field_names:
                 t = kwargs[n]
                 key += (t.data_ptr(), t.shape, t.stride(), t.dtype, t.is_cuda)
             hit = self._fast.get(tuple(key))
         except (KeyError, AttributeError, RuntimeError):
             hit = key = None        # missing / non-tensor argument: the checks below say what is wrong
-        if hit is not None and hit[4] is _range:
-            native, fa, n, dev_index, _, range_ref, self.last_variant, self.last_instance = hit
+        if hit is not None and hit[4] is _range and hit[8] is _peer:
+            native, fa, n, dev_index, _, range_ref, self.last_variant, self.last_instance, _ = hit
             if _stream is None:
                 _stream = _raw_current_stream(dev_index)
-            native.launch_packed(fa, n, [float(kwargs[s]) for s in self.scalars] if self.scalars else (), _stream, range_ref)
+            native.launch_packed(fa, n, [float(kwargs[s]) for s in self.scalars] if self.scalars else (), _stream, range_ref,
+                                 _peer)
             return None
         import torch
         if self._torch_dtypes is None:
@@ -234,6 +246,12 @@ class CompiledKernel:
                 same = self.ir.boundary == 'zeros' or self.ir.ghost_layers == 0
             if same:
                 variant = 'march_nomask'
+        if _peer is not None:
+            if not variant.startswith('march') or nd != 3:
+                raise ValueError('%s: peer halos need the 3-D march kernel (this launch selected %r)'
+                                 % (self.function_name, variant))
+            variant += '_peer'
+            self.emitted(variant)
         field_args = []
         if variant == 'march_x2' and nd == 2:
             # lifted kernel (lift_to_3d): the 2-D tensors are passed as one-plane 3-D fields
@@ -257,7 +275,14 @@ class CompiledKernel:
         with torch.cuda.device(dev):
             stream = _stream if _stream is not None else torch.cuda.current_stream(dev).cuda_stream
             native = self.native(variant, dev_index)
-            native.launch(field_args, scal, stream, _range)
+            if _peer is None:
+                native.launch(field_args, scal, stream, _range)
+            else:
+                if _range is not None and '_ctypes' not in _range:
+                    native.launch_range_struct(_range)
+                import ctypes as _ct
+                native.launch_packed(native.pack_fields(field_args), len(field_args), scal, stream,
+                                     None if _range is None else _ct.byref(_range['_ctypes']), _peer)
         self.last_variant = 'march' if variant.startswith('march') else variant
         self.last_instance = variant
         # remember the validated launch (the range dict is held: its id() cannot be reused while the entry lives)
@@ -269,7 +294,7 @@ class CompiledKernel:
                 import ctypes
                 range_ref = ctypes.byref(_range['_ctypes'])
             self._fast[tuple(key)] = (native, native.pack_fields(field_args), len(field_args), dev_index, _range, range_ref,
-                                      self.last_variant, self.last_instance)
+                                      self.last_variant, self.last_instance, _peer)
         return None
 
 

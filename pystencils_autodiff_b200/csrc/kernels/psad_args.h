@@ -17,6 +17,15 @@ struct PsadArgs {
   double scalar[PSAD_MAX_SCALARS];         // free scalar symbols, sorted by name
   long long n_items;                       // march: number of work items
   int tiles_x, tiles_y, n_chunks, chunk;   // march: work decomposition
+  // Peer halos (kernels built with PSAD_PEER, 3-D): the ghost planes [0, peer_lo_end) and [peer_hi_begin, Z) are not read
+  // from this array but from the NEIGHBOURING GPU's array through a second / third tensor map — plane p of the lower
+  // ghost block is the lower neighbour's plane p + peer_lo_shift, of the upper block the upper neighbour's p - peer_hi_shift.
+  // Before its first such load a CTA waits until the neighbour's "launches completed" counter has reached peer_expect.
+  const unsigned* peer_flag_lo;            // NULL: no lower neighbour (global border: the local ghost planes, zeros)
+  const unsigned* peer_flag_hi;
+  unsigned* peer_error;                    // set to 1 by a CTA that gave up waiting (timeout), never cleared by kernels
+  unsigned peer_expect;
+  int peer_lo_end, peer_hi_begin, peer_lo_shift, peer_hi_shift;
 };
 
 // 128-byte opaque CUtensorMap image (cuTensorMapEncodeTiled output), 64-byte aligned as the driver requires.

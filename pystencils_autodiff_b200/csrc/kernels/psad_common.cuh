@@ -38,6 +38,25 @@ PSAD_DEV void psad_mbar_wait(psad_u32 bar, psad_u32 parity) {
       : "memory");
 }
 
+// ---- cross-GPU handshake for peer halos: wait until a counter in a NEIGHBOURING GPU's memory (mapped through CUDA IPC,
+// read over NVLink) has reached `expect`.  Acquire at system scope orders the peer data written before the counter; the
+// proxy fence orders the TMA (async proxy) loads that follow behind this generic-proxy load.  Bounded: after ~2 s the CTA
+// raises *error and carries on (wrong halo values, but no hung GPU).
+PSAD_DEV void psad_wait_peer(const unsigned* flag, unsigned expect, unsigned* error) {
+  unsigned v;
+  unsigned long long t0 = 0, t1;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - expect) >= 0) break;
+    if ((spins & 1023u) == 1023u) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > 2000000000ull) { if (error) atomicExch(error, 1u); break; }
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 // ---- TMA tile loads (global -> shared, completion on an mbarrier; out-of-bounds elements are zero-filled) ---
 PSAD_DEV void psad_tma_load_2d(psad_u32 smem_dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1) {
   asm volatile(

@@ -21,8 +21,12 @@
 #ifndef PSAD_MARCH_CUH
 #define PSAD_MARCH_CUH
 
+#ifndef PSAD_PEER
+#define PSAD_PEER 0     // 1: ghost planes along z come from the neighbouring GPUs' arrays (peer memory over NVLink)
+#endif
+
 struct PsadTmaps {
-  PsadTensorMap m[cfg::NTMA];
+  PsadTensorMap m[cfg::NTMA * (PSAD_PEER ? 3 : 1)];   // [this GPU's arrays | lower neighbour's | upper neighbour's]
 };
 
 #include "psad_item.cuh"
@@ -58,22 +62,37 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
     // ================= producer warp =================
     if (lane == 0) {
 #pragma unroll
-      for (int f = 0; f < cfg::NTMA; ++f) psad_tma_prefetch_desc(&TM.m[f]);
+      for (int f = 0; f < cfg::NTMA * (PSAD_PEER ? 3 : 1); ++f) psad_tma_prefetch_desc(&TM.m[f]);
       int slot = 0;
       psad_u32 parity = 1;  // the first pass over the ring does not wait (barrier phase -1 counts as complete)
+#if PSAD_PEER
+      bool lo_ready = (A.peer_flag_lo == nullptr), hi_ready = (A.peer_flag_hi == nullptr);
+#endif
 #pragma unroll 1
       for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const PsadItem it = psad_decode_item(A, item);
 #pragma unroll 1
         for (int p = it.p_first; p <= it.p_last; ++p) {
+          int tm0 = 0, pz = p;   // which set of tensor maps, and the plane in that array
+#if PSAD_PEER
+          if (p < A.peer_lo_end && A.peer_flag_lo != nullptr) {
+            if (!lo_ready) { psad_wait_peer(A.peer_flag_lo, A.peer_expect, A.peer_error); lo_ready = true; }
+            tm0 = cfg::NTMA;
+            pz = p + A.peer_lo_shift;
+          } else if (p >= A.peer_hi_begin && A.peer_flag_hi != nullptr) {
+            if (!hi_ready) { psad_wait_peer(A.peer_flag_hi, A.peer_expect, A.peer_error); hi_ready = true; }
+            tm0 = 2 * cfg::NTMA;
+            pz = p - A.peer_hi_shift;
+          }
+#endif
           psad_mbar_wait(empty_s + 8 * slot, parity);
           psad_mbar_arrive_expect_tx(full_s + 8 * slot, cfg::TX_BYTES);
           const psad_u32 base = ring_s + slot * cfg::STAGE_BYTES;
 #pragma unroll
           for (int f = 0; f < cfg::NTMA; ++f) {
             if (cfg::NDIM == 3) {
-              psad_tma_load_3d(base + cfg::F_OFF[f], &TM.m[f], full_s + 8 * slot, it.x0 + cfg::F_ORGX[f],
-                               it.y0 + cfg::F_ORGY[f], p);
+              psad_tma_load_3d(base + cfg::F_OFF[f], &TM.m[tm0 + f], full_s + 8 * slot, it.x0 + cfg::F_ORGX[f],
+                               it.y0 + cfg::F_ORGY[f], pz);
             } else {
               psad_tma_load_2d(base + cfg::F_OFF[f], &TM.m[f], full_s + 8 * slot, it.x0 + cfg::F_ORGX[f],
                                p * cfg::TY + cfg::F_ORGY[f]);

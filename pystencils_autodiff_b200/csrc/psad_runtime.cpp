@@ -51,6 +51,8 @@ typedef struct CUfunc_st* CUfunction;
 typedef struct CUstream_st* CUstream;
 typedef unsigned long long CUdeviceptr;
 struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
+struct CUipcMemHandle { char reserved[64]; };
+enum { CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS = 1 };
 
 enum { CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT = 16, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR = 75,
        CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR = 76, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN = 97 };
@@ -80,6 +82,12 @@ struct Driver {
   CUresult (*cuGetErrorString)(CUresult, const char**);
   CUresult (*cuTensorMapEncodeTiled)(CUtensorMap*, int, unsigned, void*, const unsigned long long*,
                                      const unsigned long long*, const unsigned*, const unsigned*, int, int, int, int);
+  // optional (peer halos): resolved separately so that an old driver still loads the library
+  CUresult (*cuIpcGetMemHandle)(CUipcMemHandle*, CUdeviceptr) = nullptr;
+  CUresult (*cuIpcOpenMemHandle)(CUdeviceptr*, CUipcMemHandle, unsigned) = nullptr;     // the handle travels by value
+  CUresult (*cuIpcCloseMemHandle)(CUdeviceptr) = nullptr;
+  CUresult (*cuMemGetAddressRange)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
+  CUresult (*cuMemsetD32Async)(CUdeviceptr, unsigned, size_t, CUstream) = nullptr;
 };
 static Driver g_drv;
 static std::once_flag g_drv_once;
@@ -107,6 +115,14 @@ static void load_driver() {
             sym(lib, "cuLaunchKernel", d.cuLaunchKernel, e) && sym(lib, "cuGetErrorString", d.cuGetErrorString, e) &&
             sym(lib, "cuTensorMapEncodeTiled", d.cuTensorMapEncodeTiled, e);
   if (!ok) { g_drv_err = e; return; }
+  {
+    std::string ignore;   // optional: peer halos
+    sym(lib, "cuIpcGetMemHandle", d.cuIpcGetMemHandle, ignore);
+    sym(lib, "cuIpcOpenMemHandle_v2", d.cuIpcOpenMemHandle, ignore);
+    sym(lib, "cuIpcCloseMemHandle", d.cuIpcCloseMemHandle, ignore);
+    sym(lib, "cuMemGetAddressRange_v2", d.cuMemGetAddressRange, ignore);
+    sym(lib, "cuMemsetD32Async", d.cuMemsetD32Async, ignore);
+  }
   CUresult r = d.cuInit(0);
   if (r != 0) { g_drv_err = "cuInit failed with code " + std::to_string(r); return; }
   g_drv = d;
@@ -319,10 +335,12 @@ extern "C" int psad_compile(const char* source, const char* cache_key, const cha
 struct LaunchKey {
   int n_fields;
   int has_range;
+  int has_peer;
   psad_field_arg_t fields[PSAD_MAX_FIELDS];
   psad_range_t range;
+  psad_peer_t peer;      // with expect zeroed: like the scalars it changes from launch to launch
 };
-struct alignas(64) TensorMaps { CUtensorMap m[PSAD_MAX_FIELDS]; };
+struct alignas(64) TensorMaps { CUtensorMap m[3 * PSAD_MAX_FIELDS]; };   // peer kernels: [local | lower | upper neighbour]
 struct LaunchEntry {
   LaunchKey key;
   PsadArgs args;
@@ -543,36 +561,74 @@ extern "C" int psad_plan_launch(const psad_plan_t* plan, int sm_count, int ctas_
   return 0;
 }
 
-static int encode_tensor_maps(const psad_plan_t& P, const PsadArgs& A, int n_fields, TensorMaps& TM) {
+static int encode_one_map(const psad_plan_t& P, const psad_field_plan_t& fp, void* base, const unsigned long long gdim[3],
+                          const unsigned long long gstr[2], CUtensorMap* out) {
   const int nd = P.ndim;
-  int n_tma = 0;
   // L2 promotion of TMA requests: 0 none, 1 64B, 2 128B, 3 256B (PSAD_L2PROMO overrides for experiments)
   static const int l2promo = getenv("PSAD_L2PROMO") ? atoi(getenv("PSAD_L2PROMO")) : 3;
+  unsigned box[3] = {(unsigned)fp.box[0], (unsigned)fp.box[1], (unsigned)(nd == 3 ? fp.box[2] : 1)};
+  unsigned estr[3] = {1, 1, 1};
+  for (int d = 0; d < nd; ++d)
+    if (box[d] < 1 || box[d] > 256) return fail(PSAD_ERR_INVALID, "TMA box dim %d = %u out of range", d, box[d]);
+  CUresult r = g_drv.cuTensorMapEncodeTiled(out, fp.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                            (unsigned)nd, base, gdim, gstr, box, estr,
+                                            /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion*/ l2promo, /*oob fill: zeros*/ 0);
+  if (r != 0) return cu_fail(r, "cuTensorMapEncodeTiled");
+  return 0;
+}
+
+static int encode_tensor_maps(const psad_plan_t& P, const PsadArgs& A, int n_fields, const psad_peer_t* peer, TensorMaps& TM) {
+  int n_tma_total = 0;
+  for (int f = 0; f < n_fields; ++f) n_tma_total += P.field[f].tma ? 1 : 0;
+  int n_tma = 0;
   for (int f = 0; f < n_fields; ++f) {
     const psad_field_plan_t& fp = P.field[f];
     if (!fp.tma) continue;
     unsigned long long gdim[3] = {(unsigned long long)A.shape[2], (unsigned long long)A.shape[1], (unsigned long long)A.shape[0]};
     unsigned long long gstr[2] = {(unsigned long long)A.stride[f][1] * fp.elem_size, (unsigned long long)A.stride[f][0] * fp.elem_size};
-    unsigned box[3] = {(unsigned)fp.box[0], (unsigned)fp.box[1], (unsigned)(nd == 3 ? fp.box[2] : 1)};
-    unsigned estr[3] = {1, 1, 1};
-    for (int d = 0; d < nd; ++d)
-      if (box[d] < 1 || box[d] > 256) return fail(PSAD_ERR_INVALID, "TMA box dim %d = %u out of range", d, box[d]);
-    CUresult r = g_drv.cuTensorMapEncodeTiled(&TM.m[n_tma], fp.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
-                                              (unsigned)nd, A.ptr[f], gdim, gstr, box, estr,
-                                              /*interleave none*/ 0, /*swizzle none*/ 0, /*L2 promotion*/ l2promo, /*oob fill: zeros*/ 0);
-    if (r != 0) return cu_fail(r, "cuTensorMapEncodeTiled");
+    if (int rc = encode_one_map(P, fp, A.ptr[f], gdim, gstr, &TM.m[n_tma])) return rc;
+    if (peer) {
+      // the neighbours' arrays have this array's row / plane pitch and their own number of planes; a missing neighbour
+      // gets a copy of the local map (never used: the kernel takes that branch only with a non-null flag)
+      const void* nb[2] = {peer->flag_lo ? peer->lo_ptr[f] : nullptr, peer->flag_hi ? peer->hi_ptr[f] : nullptr};
+      const long long planes[2] = {peer->lo_planes, peer->hi_planes};
+      for (int s = 0; s < 2; ++s) {
+        CUtensorMap* dst = &TM.m[(s + 1) * n_tma_total + n_tma];
+        if (!nb[s]) { *dst = TM.m[n_tma]; continue; }
+        if (((uintptr_t)nb[s]) % 16 != 0) return fail(PSAD_ERR_INVALID, "peer array of field %d is not 16-byte aligned", f);
+        unsigned long long pdim[3] = {gdim[0], gdim[1], (unsigned long long)planes[s]};
+        if (int rc = encode_one_map(P, fp, const_cast<void*>(nb[s]), pdim, gstr, dst)) return rc;
+      }
+    }
     ++n_tma;
   }
   return 0;
 }
 
-extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields,
-                                  const double* scalars, int n_scalars, const psad_range_t* range, void* stream) {
+static int launch_impl(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields, const double* scalars, int n_scalars,
+                       const psad_range_t* range, const psad_peer_t* peer, void* stream) {
   if (!k || !fields) return fail(PSAD_ERR_INVALID, "psad_kernel_launch: null argument");
   const psad_plan_t& P = k->plan;
   if (n_fields != P.n_fields) return fail(PSAD_ERR_INVALID, "%s: expected %d fields, got %d", k->name.c_str(), P.n_fields, n_fields);
   if (n_scalars != P.n_scalars) return fail(PSAD_ERR_INVALID, "%s: expected %d scalars, got %d", k->name.c_str(), P.n_scalars, n_scalars);
   if (n_scalars > 0 && !scalars) return fail(PSAD_ERR_INVALID, "null scalars");
+  const bool peer_kernel = P.reserved[2] == 1;
+  if (peer_kernel != (peer != nullptr))
+    return fail(PSAD_ERR_INVALID, "%s: %s", k->name.c_str(), peer_kernel ? "a peer-halo kernel needs psad_kernel_launch_peer"
+                                                                         : "not a peer-halo kernel (plan.reserved[2] != 1)");
+  if (peer) {
+    if (P.kind != PSAD_KIND_MARCH || P.ndim != 3) return fail(PSAD_ERR_INVALID, "%s: peer halos need a 3-D march kernel", k->name.c_str());
+    if (peer->ghost_planes < 1) return fail(PSAD_ERR_INVALID, "%s: peer halos need at least one ghost plane", k->name.c_str());
+    for (int s = 0; s < 2; ++s) {
+      const void* flag = s ? peer->flag_hi : peer->flag_lo;
+      if (!flag) continue;
+      if ((s ? peer->hi_planes : peer->lo_planes) < 2 * peer->ghost_planes + 1)
+        return fail(PSAD_ERR_INVALID, "%s: the %s neighbour's array has too few planes", k->name.c_str(), s ? "upper" : "lower");
+      for (int f = 0; f < n_fields; ++f)
+        if (P.field[f].tma && !(s ? peer->hi_ptr[f] : peer->lo_ptr[f]))
+          return fail(PSAD_ERR_INVALID, "%s: field %d has no %s-neighbour array", k->name.c_str(), f, s ? "upper" : "lower");
+    }
+  }
   static const bool debug = getenv("PSAD_DEBUG") != nullptr;
   static const bool no_cache = getenv("PSAD_NO_LAUNCH_CACHE") != nullptr;
 
@@ -589,12 +645,13 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   }
   struct PopGuard { bool on; ~PopGuard() { if (on) { CUcontext c; g_drv.cuCtxPopCurrent(&c); } } } guard{pushed};
 
-  // parameter block + tensor maps: from the launch cache when this (buffers, shapes, strides, range) was seen before
+  // parameter block + tensor maps: from the launch cache when this (buffers, shapes, strides, range, peers) was seen before
   LaunchKey key;
   memset(&key, 0, sizeof(key));
   key.n_fields = n_fields;
   memcpy(key.fields, fields, sizeof(psad_field_arg_t) * (size_t)n_fields);
   if (range) { key.has_range = 1; key.range = *range; }
+  if (peer) { key.has_peer = 1; key.peer = *peer; key.peer.expect = 0; }
   PsadArgs A;
   TensorMaps TM;
   unsigned grid[3];
@@ -617,8 +674,18 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   } else {
     g_cache_misses.fetch_add(1, std::memory_order_relaxed);
     if (int rc = build_args(P, k->name.c_str(), k->sm_count, k->occupancy, fields, n_fields, scalars, n_scalars, range, A, grid, &empty)) return rc;
+    if (peer) {
+      const int g = peer->ghost_planes;
+      A.peer_flag_lo = static_cast<const unsigned*>(peer->flag_lo);
+      A.peer_flag_hi = static_cast<const unsigned*>(peer->flag_hi);
+      A.peer_error = static_cast<unsigned*>(peer->error_flag);
+      A.peer_lo_end = g;
+      A.peer_hi_begin = (int)A.shape[0] - g;
+      A.peer_lo_shift = (int)peer->lo_planes - 2 * g;     // ghost plane p of the lower block = the neighbour's plane p + n_lo
+      A.peer_hi_shift = (int)A.shape[0] - 2 * g;          // ghost plane p of the upper block = the neighbour's plane p - n
+    }
     if (!empty && P.kind == PSAD_KIND_MARCH)
-      if (int rc = encode_tensor_maps(P, A, n_fields, TM)) return rc;
+      if (int rc = encode_tensor_maps(P, A, n_fields, peer, TM)) return rc;
     if (!no_cache) {
       LaunchEntry* e = new LaunchEntry();
       e->key = key; e->args = A; e->tm = TM; e->empty = empty;
@@ -637,13 +704,98 @@ extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* field
   }
   if (empty || grid[0] == 0) return 0;
   for (int i = 0; i < n_scalars; ++i) A.scalar[i] = scalars[i];      // scalars are not part of the key
-  void* params[2] = {&A, &TM};   // both are copied by cuLaunchKernel
+  if (peer) A.peer_expect = peer->expect;                           // nor is the launch counter
+  void* params[2] = {&A, &TM};   // both are copied by cuLaunchKernel (the kernel declares as many maps as it uses)
   if (debug)
-    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d cache=%s\n", k->name.c_str(), grid[0],
-            P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy, hit ? "hit" : "miss");
+    fprintf(stderr, "[psad] %s grid=%u threads=%d smem=%d items=%lld tiles=%dx%d chunks=%d chunk=%d occ=%d cache=%s%s\n", k->name.c_str(), grid[0],
+            P.threads, P.smem_bytes, A.n_items, A.tiles_x, A.tiles_y, A.n_chunks, A.chunk, k->occupancy, hit ? "hit" : "miss",
+            peer ? " peer" : "");
   CUresult r = g_drv.cuLaunchKernel(k->fn, grid[0], grid[1], grid[2], (unsigned)P.threads, 1, 1, (unsigned)P.smem_bytes, (CUstream)stream, params, nullptr);
   if (r != 0) return cu_fail(r, "cuLaunchKernel");
   g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int psad_kernel_launch(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields,
+                                  const double* scalars, int n_scalars, const psad_range_t* range, void* stream) {
+  return launch_impl(k, fields, n_fields, scalars, n_scalars, range, nullptr, stream);
+}
+
+extern "C" int psad_kernel_launch_peer(psad_kernel_t k, const psad_field_arg_t* fields, int n_fields, const double* scalars,
+                                       int n_scalars, const psad_range_t* range, const psad_peer_t* peer, void* stream) {
+  if (!peer) return fail(PSAD_ERR_INVALID, "psad_kernel_launch_peer: null peer description");
+  return launch_impl(k, fields, n_fields, scalars, n_scalars, range, peer, stream);
+}
+
+// ---- CUDA IPC plumbing for peer halos ---------------------------------------------------------------------------
+struct IpcMapping { CUipcMemHandle handle; CUdeviceptr base; int refs; };
+static std::mutex g_ipc_mutex;
+static std::vector<IpcMapping> g_ipc;
+
+static int need_ipc() {
+  if (int rc = need_driver()) return rc;
+  if (!g_drv.cuIpcGetMemHandle || !g_drv.cuIpcOpenMemHandle || !g_drv.cuIpcCloseMemHandle || !g_drv.cuMemGetAddressRange)
+    return fail(PSAD_ERR_NO_DRIVER, "this driver lacks the CUDA IPC entry points needed for peer halos");
+  return ensure_context();
+}
+
+extern "C" int psad_ipc_export(const void* ptr, void* handle_64, uint64_t* offset) {
+  if (!ptr || !handle_64 || !offset) return fail(PSAD_ERR_INVALID, "psad_ipc_export: null argument");
+  if (int rc = need_ipc()) return rc;
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CU_CHECK(g_drv.cuMemGetAddressRange(&base, &size, (CUdeviceptr)(uintptr_t)ptr));
+  CUipcMemHandle h;
+  CUresult r = g_drv.cuIpcGetMemHandle(&h, base);
+  if (r != 0) return cu_fail(r, "cuIpcGetMemHandle (allocations of an expandable-segments / VMM allocator cannot be exported)");
+  memcpy(handle_64, &h, sizeof(h));
+  *offset = (uint64_t)((CUdeviceptr)(uintptr_t)ptr - base);
+  return 0;
+}
+
+extern "C" int psad_ipc_open(const void* handle_64, uint64_t offset, void** ptr_out) {
+  if (!handle_64 || !ptr_out) return fail(PSAD_ERR_INVALID, "psad_ipc_open: null argument");
+  if (int rc = need_ipc()) return rc;
+  CUipcMemHandle h;
+  memcpy(&h, handle_64, sizeof(h));
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  for (IpcMapping& m : g_ipc) {
+    if (memcmp(&m.handle, &h, sizeof(h)) == 0) {           // an allocation can be opened only once per process
+      ++m.refs;
+      *ptr_out = (void*)(uintptr_t)(m.base + offset);
+      return 0;
+    }
+  }
+  CUdeviceptr base = 0;
+  CUresult r = g_drv.cuIpcOpenMemHandle(&base, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+  if (r != 0) return cu_fail(r, "cuIpcOpenMemHandle");
+  g_ipc.push_back(IpcMapping{h, base, 1});
+  *ptr_out = (void*)(uintptr_t)(base + offset);
+  return 0;
+}
+
+extern "C" int psad_ipc_close(void* ptr) {
+  if (!ptr) return 0;
+  if (int rc = need_ipc()) return rc;
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  // the mapping with the largest base not above ptr
+  int best = -1;
+  for (size_t i = 0; i < g_ipc.size(); ++i)
+    if (g_ipc[i].base <= (CUdeviceptr)(uintptr_t)ptr && (best < 0 || g_ipc[i].base > g_ipc[best].base)) best = (int)i;
+  if (best < 0) return fail(PSAD_ERR_INVALID, "psad_ipc_close: not a pointer returned by psad_ipc_open");
+  if (--g_ipc[best].refs == 0) {
+    CUresult r = g_drv.cuIpcCloseMemHandle(g_ipc[best].base);
+    g_ipc.erase(g_ipc.begin() + best);
+    if (r != 0) return cu_fail(r, "cuIpcCloseMemHandle");
+  }
+  return 0;
+}
+
+extern "C" int psad_stream_write_u32(void* dst, uint32_t value, void* stream) {
+  if (!dst) return fail(PSAD_ERR_INVALID, "psad_stream_write_u32: null pointer");
+  if (int rc = need_driver()) return rc;
+  if (!g_drv.cuMemsetD32Async) return fail(PSAD_ERR_NO_DRIVER, "cuMemsetD32Async is not available");
+  CU_CHECK(g_drv.cuMemsetD32Async((CUdeviceptr)(uintptr_t)dst, value, 1, (CUstream)stream));
   return 0;
 }
 

@@ -222,6 +222,127 @@ class HaloExchanger:
             self._comm = None
 
 
+class _PeerHalo:
+    """Ghost planes read from the neighbouring GPUs' memory by the stencil kernel itself (``SlabDataHandling(peer_halo=True)``).
+
+    The NCCL path runs, per kernel, an exchange of the boundary planes into the local ghost planes, one launch for the
+    interior planes and one per side for the planes that had to wait.  Here every registered array is exported through CUDA
+    IPC to the neighbouring ranks of the node, and ONE launch covers the whole slab: the kernel's producer warp stages
+    the ghost planes by TMA straight from the neighbour's array over NVLink (``psad_kernel_launch_peer``, ``PSAD_PEER``
+    in psad_march.cuh) — the halo transfer is part of the kernel's own pipeline, plane by plane, and nothing is copied
+    twice.  Ordering between GPUs is a counter per rank in device memory: after its launch number k a rank stores k
+    (stream order); launch k on a neighbour waits inside the kernel — only in the CTAs that touch ghost planes, and only
+    before their first such load — until it reads k - 1 there.  That one condition covers both hazards (the neighbour has
+    produced what is read, and has finished reading what is about to be overwritten) as long as all ranks issue the same
+    sequence of launches, which an SPMD program does.  Anything that changes an array outside that sequence (``fill``,
+    ``to_gpu``, writes through ``owned()``) must be followed by ``fence()`` — ``fill`` / ``to_gpu`` do it themselves.
+    """
+
+    def __init__(self, data_handling):
+        import torch
+        self.dh = data_handling
+        self.torch = torch
+        dec = data_handling.dec
+        self.lo_rank, self.hi_rank = dec.lo_rank, dec.hi_rank
+        self.seq = 0
+        self.dirty = True                # arrays were written outside the launch sequence: fence before the next launch
+        self.buffers = {}                # data_ptr of a registered array -> (lower neighbour's ptr, planes, upper ptr, planes)
+        self.structs = {}
+        self._keep = []
+        self._ranges = {}
+        # [0]: this rank's "launches completed" counter, [1]: error flag (a kernel gave up waiting for a neighbour)
+        self.flags = torch.zeros(2, dtype=torch.int32, device=data_handling.device)
+        (self.flag_lo, _), (self.flag_hi, _) = self._exchange(self.flags, 1)
+
+    def _exchange(self, tensor, planes):
+        """Collective: export ``tensor``, return ``((lower ptr, planes), (upper ptr, planes))`` of the neighbours' tensors
+        registered in the same call (None where there is no neighbour)."""
+        import torch.distributed as dist
+        handle, offset = runtime.ipc_export(tensor.data_ptr())
+        mine = (handle, offset, int(planes))
+        everyone = [None] * self.dh.dec.world_size
+        dist.all_gather_object(everyone, mine, group=self.dh.exchanger.group)
+        out = []
+        for r in (self.lo_rank, self.hi_rank):
+            if r < 0:
+                out.append((None, 0))
+            else:
+                h, off, pl = everyone[r]
+                out.append((runtime.ipc_open(h, off), pl))
+        self._keep.append(tensor)        # exported memory must stay alive while a neighbour maps it
+        return out
+
+    def register(self, tensor):
+        (lo, lo_planes), (hi, hi_planes) = self._exchange(tensor, tensor.shape[0])
+        self.buffers[tensor.data_ptr()] = (lo, lo_planes, hi, hi_planes)
+
+    def applies(self, kernel, arrays, fused_steps):
+        if kernel.ir.ndim != 3 or 'march' not in kernel._emitted or kernel._components:
+            return False
+        if any(t.data_ptr() not in self.buffers for t in arrays.values()):
+            return False                 # an array that was not registered here (e.g. replaced by the user)
+        return kernel._select_variant([arrays[f.name] for f in kernel.fields]) == 'march'
+
+    def fence(self):
+        """Every rank has finished everything it has launched: after this, arrays may be changed outside the launch
+        sequence, and what was changed is visible to the neighbours' next launches."""
+        import torch.distributed as dist
+        self.torch.cuda.synchronize(self.dh.device)
+        dist.barrier(group=self.dh.exchanger.group)
+        self.dirty = False
+
+    def errors(self):
+        """1 if a kernel of this rank gave up waiting for a neighbour (host synchronisation)."""
+        return int(self.flags[1].item())
+
+    def count_foreign_launch(self):
+        self.seq += 1
+        cur = self.torch.cuda.current_stream(self.dh.device).cuda_stream
+        runtime.stream_write_u32(self.flags.data_ptr(), self.seq, cur)
+
+    def run(self, kernel, arrays, fused_steps, kwargs):
+        dh, dec = self.dh, self.dh.dec
+        ir = kernel.ir
+        if self.dirty:
+            self.fence()
+        key = (id(kernel), fused_steps)
+        if key not in self._ranges:
+            halo = max(ir.halo(ir.input_fields[0].name)[0]) if fused_steps > 1 else None
+            if fused_steps > 1:
+                reason = kernel.fused_steps_reason()
+                if reason:
+                    raise ValueError('%s: steps cannot be fused: %s' % (kernel.function_name, reason))
+                if dec.g < fused_steps * halo:
+                    raise ValueError('%d fused steps of a stencil reaching %d plane(s) need %d ghost planes, the slab stores %d'
+                                     % (fused_steps, halo, fused_steps * halo, dec.g))
+            # ONE launch for all owned planes: nothing waits for an exchange
+            whole = slab_ranges(dec.global_shape, dec.start, dec.n_local, dec.g, False, False, ir.boundary, ir.ghost_layers,
+                                ir.ndim, fused_steps, halo, periodic=dec.periodic)[0]
+            self._ranges[key] = (kernel, whole)
+        whole = self._ranges[key][1]
+        tensors = [arrays[f.name] for f in kernel.fields]
+        skey = (id(kernel),) + tuple(t.data_ptr() for t in tensors)
+        peer = self.structs.get(skey)
+        if peer is None:
+            peer = runtime.Peer()
+            for i, t in enumerate(tensors):
+                lo, lo_planes, hi, hi_planes = self.buffers[t.data_ptr()]
+                peer.lo_ptr[i], peer.hi_ptr[i] = lo, hi
+                peer.lo_planes, peer.hi_planes = lo_planes or 0, hi_planes or 0
+            peer.flag_lo, peer.flag_hi = self.flag_lo, self.flag_hi
+            peer.error_flag = self.flags.data_ptr() + 4
+            peer.ghost_planes = dec.g
+            if len(self.structs) > 256:
+                self.structs.clear()
+            self.structs[skey] = peer
+        self.seq += 1
+        peer.expect = self.seq - 1
+        if fused_steps > 1:
+            kwargs = dict(kwargs, _variant='march_x2')
+        kernel(**arrays, **kwargs, _range=whole, _peer=peer)
+        runtime.stream_write_u32(self.flags.data_ptr(), self.seq, self.torch.cuda.current_stream(dh.device).cuda_stream)
+
+
 class SlabDataHandling:
     """Array registry with the reference's data-handling vocabulary (``add_array``, ``fields``, ``run_kernel``,
     ``synchronization_function``, ``swap``, ``fill``, ``gather_array``; graph_datahandling.py:202-327,
@@ -229,7 +350,7 @@ class SlabDataHandling:
     what was executed with the reference's event names (``KernelCall``, ``Communication``, ``Swap``)."""
 
     def __init__(self, domain_size, rank=0, world_size=1, default_ghost_layers=1, device=None, backend='nccl',
-                 group=None, periodic=False):
+                 group=None, periodic=False, peer_halo=False):
         """``periodic``: the domain is periodic along dim 0 (the decomposed axis): ghost-plane synchronisation wraps around
         — what pystencils' serial data handling does inside one array for the reference (graph_datahandling.py:305-316 →
         ``SerialDataHandling.synchronization_function``).  The other axes keep the kernels' own boundary treatment."""
@@ -251,6 +372,9 @@ class SlabDataHandling:
         self._comm_stream = None
         self._ev_ready = None
         self._ev_halo = None
+        # peer halos: the stencil kernels read their ghost planes from the neighbouring GPUs' arrays (CUDA IPC mappings,
+        # NVLink) instead of having them exchanged first — see _PeerHalo
+        self.peer = _PeerHalo(self) if (peer_halo and self.dec.world_size > 1 and self.dec.g > 0) else None
 
     max_recorded_calls = 1 << 16      # the reference records without bound; a long-running time loop must not leak
 
@@ -282,6 +406,8 @@ class SlabDataHandling:
         else:
             shape = self.dec.local_shape
         arr = self.torch.zeros(shape + tail, dtype=numpy_dtype_to_torch(dtype), device=self.device)
+        if self.peer is not None and name not in self._replicated:
+            self.peer.register(arr)              # collective: every rank adds its arrays in the same order
         self.gpu_arrays[name] = arr
         self.fields[name] = Field.create_fixed_size(name, shape + tail, index_dimensions=len(tail), dtype=dtype)
         return self.fields[name]
@@ -302,7 +428,11 @@ class SlabDataHandling:
 
     def fill(self, array_name, val, **_):
         self._record(('Fill', array_name))        # graph_datahandling.py:324-327 records 'Fill <name>'
+        if self.peer is not None:
+            self.peer.fence()                     # the neighbours may still be reading this array's boundary planes
         self.owned(array_name)[...] = val
+        if self.peer is not None:
+            self.peer.dirty = True
 
     def require_autograd(self, bool_val, *names):
         """framework_integration/datahandling.py:190-200 (which sets an attribute torch never reads — ``require_autograd``
@@ -368,7 +498,11 @@ class SlabDataHandling:
         self._record(('DataTransfer', name, 'HOST_TO_DEVICE'))
         if name not in self.cpu_arrays:
             raise KeyError('no host copy of %r: call to_cpu(%r) first or fill cpu_arrays[%r]' % (name, name, name))
+        if self.peer is not None:
+            self.peer.fence()
         self.gpu_arrays[name].copy_(self.cpu_arrays[name])
+        if self.peer is not None:
+            self.peer.dirty = True
 
     def all_to_cpu(self):
         for n in self.gpu_arrays:
@@ -502,6 +636,8 @@ class SlabDataHandling:
                 kwargs = dict(kwargs, _variant='march_x2')
             return kernel(**arrays, **kwargs)          # whole arrays, every rank, no exchange
         ir = kernel.ir
+        if self.peer is not None and self.peer.applies(kernel, arrays, fused_steps):
+            return self.peer.run(kernel, arrays, fused_steps, kwargs)
         key = (id(kernel), fused_steps)
         if key not in self._range_cache:
             if fused_steps > 1:
@@ -539,6 +675,8 @@ class SlabDataHandling:
                 kernel(**arrays, **kwargs, _range=r)
         elif side or halo_fields:
             self.finish_exchange()
+        if self.peer is not None:
+            self.peer.count_foreign_launch()      # launches outside the peer protocol still advance the counters
 
     def run_steps(self, kernel, steps, fuse=None, **scalars):
         """``steps`` applications of a one-input / one-output stencil kernel as the reference's time loop runs them
@@ -1047,7 +1185,8 @@ class SlabStencilOp:
     ``local_shape`` is the owned (ghost-free) shape per rank; the global field is ``world_size`` such slabs stacked
     along dim 0."""
 
-    def __init__(self, op, local_shape, rank=0, world_size=1, device=None, backend='nccl', tuning=None, scalars=None):
+    def __init__(self, op, local_shape, rank=0, world_size=1, device=None, backend='nccl', tuning=None, scalars=None,
+                 peer_halo=False):
         import torch
         self.torch = torch
         self.op = op
@@ -1061,7 +1200,7 @@ class SlabStencilOp:
             for ir in (op.forward_ast_gpu, op.backward_ast_gpu):
                 g = max(g, max(ir.max_halo[0]))
         global_shape = (local_shape[0] * world_size,) + tuple(local_shape[1:])
-        self.dh = SlabDataHandling(global_shape, rank, world_size, g, device, backend)
+        self.dh = SlabDataHandling(global_shape, rank, world_size, g, device, backend, peer_halo=peer_halo)
         self.exchange_kind = ('ncclSend/ncclRecv via psad_halo_exchange on a comm stream, overlapped with interior planes'
                               if backend == 'nccl' else 'torch.distributed P2P')
         self.local_shape = tuple(local_shape)
@@ -1091,6 +1230,8 @@ class SlabStencilOp:
             if f not in self.op.forward_input_fields:
                 self.dh.owned(f.name).copy_(self.torch.randn(self.local_shape, generator=generator, device=self.device,
                                                              dtype=self.dh.gpu_arrays[f.name].dtype))
+        if self.dh.peer is not None:
+            self.dh.peer.dirty = True         # written outside the launch sequence: fence before the next launch
 
     def forward(self):
         self.dh.run_kernel(self.fwd, halo_fields=self.fwd_halo, **self.fwd_scalars)

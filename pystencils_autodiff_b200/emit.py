@@ -375,9 +375,12 @@ def march_ineligible_reason(ir: StencilKernelIR) -> Optional[str]:
     return None
 
 
-def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True) -> EmittedKernel:
+def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True, peer: bool = False) -> EmittedKernel:
     """Emit the march variant; when the default tile does not fit (several wide-halo fp64 fields), fall back to
-    shallower prefetch and then to smaller tiles — unless the caller pinned those parameters."""
+    shallower prefetch and then to smaller tiles — unless the caller pinned those parameters.
+
+    ``peer``: the peer-halo instance (3-D only) — ghost planes along dim 0 are staged by TMA straight from the neighbouring
+    GPUs' arrays (``psad_kernel_launch_peer``, ``PSAD_PEER`` in psad_march.cuh); the per-step body is the same."""
     import dataclasses
     t = tuning or MarchTuning()
     candidates = [t]
@@ -389,7 +392,7 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked
     last = None
     for cand in candidates:
         try:
-            return _emit_march(ir, cand, masked)
+            return _emit_march(ir, cand, masked, peer)
         except ValueError as e:
             last = e
             if 'shared memory' not in str(e) and 'threads' not in str(e):
@@ -397,17 +400,19 @@ def emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked
     raise last
 
 
-def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True) -> EmittedKernel:
+def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, masked: bool = True, peer: bool = False) -> EmittedKernel:
     reason = march_ineligible_reason(ir)
     if reason:
         raise ValueError('march variant not applicable: ' + reason)
+    if peer and ir.ndim != 3:
+        raise ValueError('march variant not applicable: peer halos need 3-D fields')
     t = tuning or MarchTuning()
     if t.shuffle is None:
         import dataclasses
         t = dataclasses.replace(t, shuffle=True)
     # masked=False: every written cell is inside the iteration range ('zeros' boundary, or a launch range whose
     # iteration and write parts coincide) -> no per-cell select, no mask bookkeeping
-    name = _kernel_name(ir, 'march' if masked else 'march_nomask')
+    name = _kernel_name(ir, ('march' if masked else 'march_nomask') + ('_peer' if peer else ''))
     CT = _CT[ir.compute_dtype]
     pr = _CudaPrinter(ir.compute_dtype)
     fields = ir.all_fields
@@ -864,6 +869,8 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
     L.append('}')
     L.append('')
     L.append('#define PSAD_KERNEL_NAME %s' % name)
+    if peer:
+        L.append('#define PSAD_PEER 1')
     L.append('#include "psad_march.cuh"')
     L.append('')
 
@@ -875,7 +882,7 @@ def _emit_march(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, maske
 
     plan = dict(kind=1, ndim=nd, n_fields=len(fields), n_scalars=len(scalars), threads=THREADS + 32, smem_bytes=smem_bytes,
                 tile_x=TX, tile_y=TY, chunk=t.chunk, ctas_per_sm=t.ctas_per_sm, warmup=D, boundary=1 if ir.boundary == 'zeros' else 0,
-                ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
+                ghost_layers=ir.ghost_layers, peer=int(peer), fields=[fplan(f) for f in fields])
     ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
     ek.masked = masked
     if ir.fast_math:

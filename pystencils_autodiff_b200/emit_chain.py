@@ -68,7 +68,7 @@ def _planewise(rhs):
     return None
 
 
-def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) -> EmittedKernel:
+def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None, peer: bool = False) -> EmittedKernel:
     """Kernel computing ``out = S(S(u))`` for the single-step IR ``out = S(u)`` (fields: out, u)."""
     reason = chain_ineligible_reason(ir)
     if reason:
@@ -128,7 +128,7 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     # `exchange` — written to a shared buffer by their owners and read back after one consumer barrier (input box with
     # one y radius; the tile's outermost rows have no owner, so tiles then overlap along y as well)
     exchange = want_exchange and D1 > 0 and HYL + HYH > 0      # needs >= 2 window phases; pointless without a y halo
-    name = _kernel_name(ir, 'march_x2e' if exchange else 'march_x2')
+    name = _kernel_name(ir, ('march_x2e' if exchange else 'march_x2') + ('_peer' if peer else ''))
     U_L, U_H = (HYL, HYH) if exchange else (2 * HYL, 2 * HYH)      # input rows above / below the thread's own rows
     TYS = TY - HYL - HYH if exchange else TY
     YORG = -HYL if exchange else 0
@@ -427,6 +427,8 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
     L.append('}')
     L.append('')
     L.append('#define PSAD_KERNEL_NAME %s' % name)
+    if peer:
+        L.append('#define PSAD_PEER 1      // ghost planes from the neighbouring GPUs\' arrays (psad_kernel_launch_peer)')
     L.append('#include "psad_march.cuh"')
     L.append('')
 
@@ -437,7 +439,8 @@ def emit_march_chain(ir: StencilKernelIR, tuning: Optional[MarchTuning] = None) 
 
     plan = dict(kind=1, ndim=3, n_fields=len(fields), n_scalars=len(scalars), threads=THREADS + 32, smem_bytes=smem_bytes,
                 tile_x=TXS, tile_y=TYS, chunk=t.chunk, ctas_per_sm=t.ctas_per_sm, warmup=2 * D1, fused_steps=2,
-                boundary=1 if ir.boundary == 'zeros' else 0, ghost_layers=ir.ghost_layers, fields=[fplan(f) for f in fields])
+                boundary=1 if ir.boundary == 'zeros' else 0, ghost_layers=ir.ghost_layers, peer=int(peer),
+                fields=[fplan(f) for f in fields])
     ek = EmittedKernel(name, 'march', '\n'.join(L), ir, fields, scalars, plan)
     ek.masked = True
     if ir.fast_math:

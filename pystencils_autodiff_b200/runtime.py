@@ -56,6 +56,14 @@ class FieldArg(ctypes.Structure):
     _fields_ = [('ptr', ctypes.c_void_p), ('shape', ctypes.c_int64 * 3), ('stride', ctypes.c_int64 * 4)]
 
 
+class Peer(ctypes.Structure):
+    """``psad_peer_t``: the neighbouring GPUs' arrays and completion counters of a peer-halo launch."""
+    _fields_ = [('lo_ptr', ctypes.c_void_p * PSAD_MAX_FIELDS), ('hi_ptr', ctypes.c_void_p * PSAD_MAX_FIELDS),
+                ('lo_planes', ctypes.c_int64), ('hi_planes', ctypes.c_int64), ('flag_lo', ctypes.c_void_p),
+                ('flag_hi', ctypes.c_void_p), ('error_flag', ctypes.c_void_p), ('expect', ctypes.c_uint32),
+                ('ghost_planes', ctypes.c_int32)]
+
+
 class Range(ctypes.Structure):
     _fields_ = [('iter_lo', ctypes.c_int64 * 3), ('iter_hi', ctypes.c_int64 * 3),
                 ('write_lo', ctypes.c_int64 * 3), ('write_hi', ctypes.c_int64 * 3)]
@@ -108,6 +116,13 @@ def lib():
         L.psad_plan_launch.argtypes = [ctypes.POINTER(Plan), ctypes.c_int, ctypes.c_int, ctypes.POINTER(FieldArg),
                                        ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(Range),
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint)]
+        L.psad_kernel_launch_peer.argtypes = [ctypes.c_void_p, ctypes.POINTER(FieldArg), ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(Range),
+                                              ctypes.POINTER(Peer), ctypes.c_void_p]
+        L.psad_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.psad_ipc_open.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
+        L.psad_ipc_close.argtypes = [ctypes.c_void_p]
+        L.psad_stream_write_u32.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.psad_launch_cache_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)] * 2
         L.psad_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
         L.psad_nccl_unique_id.argtypes = [ctypes.c_void_p]
@@ -136,6 +151,7 @@ def make_plan(p):
         setattr(plan, k, int(p[k]))
     plan.reserved[0] = int(p.get('warmup', 0))
     plan.reserved[1] = int(p.get('fused_steps', 1))
+    plan.reserved[2] = int(p.get('peer', 0))
     for i, f in enumerate(p['fields']):
         fp = plan.field[i]
         for k in ('elem_size', 'is_input', 'is_output', 'index_size', 'tma'):
@@ -202,13 +218,29 @@ class NativeKernel:
                 fa[i].stride[d] = strides[d] if d < len(strides) else 0
         return fa
 
-    def launch_packed(self, fa, n, scalars, stream, range_ref):
-        """A launch whose field array (and range) were packed before: the repeated-launch path."""
+    def launch_packed(self, fa, n, scalars, stream, range_ref, peer=None):
+        """A launch whose field array (and range) were packed before: the repeated-launch path.  ``peer``: a ``Peer``
+        struct for peer-halo kernels (its ``expect`` set by the caller)."""
         ns = len(scalars)
         scal = (ctypes.c_double * ns)(*scalars) if ns else self._scal
-        rc = _lib.psad_kernel_launch(self._handle, fa, n, scal, ns, range_ref, stream)
+        if peer is None:
+            rc = _lib.psad_kernel_launch(self._handle, fa, n, scal, ns, range_ref, stream)
+        else:
+            rc = _lib.psad_kernel_launch_peer(self._handle, fa, n, scal, ns, range_ref, ctypes.byref(peer), stream)
         if rc:
             check(rc, 'psad_kernel_launch(%s)' % self.emitted.name)
+
+    @staticmethod
+    def launch_range_struct(rng):
+        """The ``psad_range_t`` of a range dict, built once and kept in the dict (launch ranges are reused every step)."""
+        r = rng.get('_ctypes')
+        if r is None:
+            r = Range()
+            for d in range(len(rng['iter_lo'])):
+                r.iter_lo[d], r.iter_hi[d] = rng['iter_lo'][d], rng['iter_hi'][d]
+                r.write_lo[d], r.write_hi[d] = rng['write_lo'][d], rng['write_hi'][d]
+            rng['_ctypes'] = r
+        return r
 
     def launch(self, field_args, scalars, stream, rng=None):
         """field_args: list of ``(ptr, shape, strides)`` in plan order; scalars: list of floats; stream: int handle."""
@@ -235,6 +267,32 @@ class NativeKernel:
                 lib().psad_kernel_destroy(self._handle)
         except Exception:
             pass
+
+
+def ipc_export(ptr):
+    """``(handle bytes, offset)`` of a device pointer for another process of this node (``psad_ipc_export``)."""
+    handle = (ctypes.c_ubyte * 64)()
+    off = ctypes.c_uint64(0)
+    check(lib().psad_ipc_export(ctypes.c_void_p(ptr), handle, ctypes.byref(off)), 'psad_ipc_export')
+    return bytes(handle), int(off.value)
+
+
+def ipc_open(handle, offset):
+    """Device pointer (int) in THIS process of memory another process exported with :func:`ipc_export`."""
+    buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    out = ctypes.c_void_p()
+    check(lib().psad_ipc_open(buf, ctypes.c_uint64(offset), ctypes.byref(out)), 'psad_ipc_open')
+    return int(out.value)
+
+
+def ipc_close(ptr):
+    check(lib().psad_ipc_close(ctypes.c_void_p(ptr)), 'psad_ipc_close')
+
+
+def stream_write_u32(ptr, value, stream):
+    rc = lib().psad_stream_write_u32(ctypes.c_void_p(ptr), ctypes.c_uint32(value & 0xffffffff), ctypes.c_void_p(stream))
+    if rc:
+        check(rc, 'psad_stream_write_u32')
 
 
 def launch_count():

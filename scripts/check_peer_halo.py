@@ -1,0 +1,118 @@
+"""Peer halos (``SlabDataHandling(peer_halo=True)``: ghost planes read by the kernel from the neighbouring GPUs' arrays over
+NVLink, one launch per kernel, no exchange) against the unsharded kernels and against the NCCL path (run under torchrun).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        scripts/check_peer_halo.py [c3|c4] [zeros|none] [steps] [--time]
+Correctness: a time loop of ``steps`` steps (single steps, then fused pairs) on small slabs, every rank compares its planes
+with the unsharded run on its own GPU — bit for bit; many more steps than ranks, so a missed wait shows up as a difference.
+``--time``: the full-size workload, ms per step for NCCL exchange vs peer halos (forward+adjoint pair and the time loop).
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+from pystencils_autodiff_b200.configs import CONFIG_SHAPES, make_config
+from pystencils_autodiff_b200.datahandling import SlabDataHandling, SlabStencilOp
+
+SHAPES = {'c3': (24, 40, 256), 'c4': (16, 24, 128)}
+
+
+def correctness(name, bh, steps, rank, world, dev):
+    local = SHAPES[name]
+    gshape = (local[0] * world,) + local[1:]
+    op_g = make_config(name, shape=gshape, boundary_handling=bh)
+    ir_g = op_g.forward_ast_gpu
+    halo = max(ir_g.halo(ir_g.input_fields[0].name)[0])
+    dtype = ir_g.input_fields[0].dtype.numpy_dtype
+    g = torch.Generator(device='cpu')
+    g.manual_seed(7)
+    glob = torch.randn(gshape, generator=g, dtype=torch.float64).to(getattr(torch, str(dtype))).to(dev)
+    sl = slice(rank * local[0], (rank + 1) * local[0])
+    kg = CompiledKernel(ir_g)
+    ok = True
+    for fuse in (False, True):
+        dh = SlabDataHandling(gshape, rank, world, 2 * halo, dev, peer_halo=True)
+        dh.add_arrays('u, out', dtype=dtype)
+        op_l = make_config(name, shape=dh.dec.local_shape, boundary_handling=bh)
+        kl = CompiledKernel(op_l.forward_ast_gpu)
+        dh.owned('u').copy_(glob[sl])
+        dh.peer.dirty = True
+        res = dh.run_steps(kl, steps, fuse=fuse)
+        ref = kg.run_steps(glob, steps, fuse=fuse)
+        torch.cuda.synchronize()
+        same = torch.equal(res[dh.dec.owned], ref[sl]) and dh.peer.errors() == 0
+        ok = ok and same
+        print('[rank %d] %s %s steps=%d fuse=%s peer halos (%s, %d launches): %s' % (
+            rank, name, bh, steps, fuse, kl.last_instance, dh.peer.seq, 'IDENTICAL' if same else
+            'DIFFERENT (max %.3e, errors %d)' % (float((res[dh.dec.owned] - ref[sl]).abs().max()), dh.peer.errors())), flush=True)
+        dh.peer.fence()
+    return ok
+
+
+def timing(name, rank, world, dev, steps=20):
+    shape = tuple(CONFIG_SHAPES[name]['shape'])
+    out = {'workload': name, 'n_gpus': world, 'per_gpu_shape': list(shape)}
+    for mode in ('nccl', 'peer'):
+        op = make_config(name, shape=shape, boundary_handling='zeros')
+        slab = SlabStencilOp(op, shape, rank, world, dev, peer_halo=(mode == 'peer'))
+        g = torch.Generator(device=dev)
+        g.manual_seed(3 + rank)
+        slab.randomize(g)
+
+        def barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+        for _ in range(5):
+            slab.forward()
+            slab.backward()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            slab.forward()
+            slab.backward()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out['%s_ms_per_step' % mode] = float(t.item())
+        if mode == 'peer':
+            out['peer_errors'] = slab.dh.peer.errors()
+            out['peer_launches'] = slab.dh.peer.seq
+        keep = {n: slab.dh.owned(n).clone() for n in ('out', 'diffu') if n in slab.dh.gpu_arrays}
+        out.setdefault('_results', {})[mode] = keep
+        del slab
+        torch.cuda.empty_cache()
+    res = out.pop('_results')
+    out['peer_equals_nccl'] = all(torch.equal(res['nccl'][n], res['peer'][n]) for n in res['nccl'])
+    out['speedup'] = out['nccl_ms_per_step'] / out['peer_ms_per_step']
+    return out
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    name = args[0] if args else 'c3'
+    bh = None if (len(args) > 1 and args[1] == 'none') else 'zeros'
+    steps = int(args[2]) if len(args) > 2 else 9
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    dev = torch.device('cuda', int(os.environ['LOCAL_RANK']))
+    dist.init_process_group('nccl', device_id=dev)
+    ok = correctness(name, bh, steps, rank, world, dev)
+    res = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if '--time' in sys.argv and int(res.item()) == 1:
+        t = timing(name, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(t), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if res.item() == 1 else 1)
+
+
+if __name__ == '__main__':
+    main()

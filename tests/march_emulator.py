@@ -164,8 +164,10 @@ def run_generic(emitted, arrays, scalars=(), launch_range=None, sm_count=4):
 
 
 def _args_size():
-    # sizeof(PsadArgs), from the header's layout: 12 ptrs + 12*4 strides + 5*3 int64 + 16 doubles + int64 + 4 ints
-    return 12 * 8 + 12 * 4 * 8 + 5 * 3 * 8 + 16 * 8 + 8 + 4 * 4
+    # sizeof(PsadArgs), from the header's layout: 12 ptrs + 12*4 strides + 5*3 int64 + 16 doubles + int64 + 4 ints, then the
+    # peer-halo block (3 pointers, 1 unsigned, 4 ints), padded to the struct's 8-byte alignment
+    n = 12 * 8 + 12 * 4 * 8 + 5 * 3 * 8 + 16 * 8 + 8 + 4 * 4 + 3 * 8 + 4 + 4 * 4
+    return -(-n // 8) * 8
 
 
 def aligned_empty(shape, dtype, fill=None):
