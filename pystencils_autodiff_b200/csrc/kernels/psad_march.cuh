@@ -140,6 +140,9 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
       if (++ph == cfg::NP) ph = 0;
     }
   }
+#if PSAD_PEER
+  if (A.peer_self != nullptr) psad_signal_peers(A.peer_self, A.peer_count, A.peer_expect + 1u, tid, cfg::THREADS);
+#endif
 }
 
 #endif

@@ -548,6 +548,45 @@ static int build_args(const psad_plan_t& P, const char* kname, int sm_count, int
   return 0;
 }
 
+// Peer halos: what psad_kernel_launch_peer checks and derives without touching a device.
+static int check_peer(const psad_plan_t& P, const char* kname, int n_fields, const psad_peer_t* peer) {
+  const bool peer_kernel = P.reserved[2] == 1;
+  if (peer_kernel != (peer != nullptr))
+    return fail(PSAD_ERR_INVALID, "%s: %s", kname, peer_kernel ? "a peer-halo kernel needs psad_kernel_launch_peer"
+                                                               : "not a peer-halo kernel (plan.reserved[2] != 1)");
+  if (!peer) return 0;
+  if (P.kind != PSAD_KIND_MARCH || P.ndim != 3) return fail(PSAD_ERR_INVALID, "%s: peer halos need a 3-D march kernel", kname);
+  if (peer->ghost_planes < 1) return fail(PSAD_ERR_INVALID, "%s: peer halos need at least one ghost plane", kname);
+  if ((peer->self_flag == nullptr) != (peer->self_count == nullptr))
+    return fail(PSAD_ERR_INVALID, "%s: self_flag and self_count go together", kname);
+  for (int s = 0; s < 2; ++s) {
+    const void* flag = s ? peer->flag_hi : peer->flag_lo;
+    if (!flag) continue;
+    if ((s ? peer->hi_planes : peer->lo_planes) < 2 * peer->ghost_planes + 1)
+      return fail(PSAD_ERR_INVALID, "%s: the %s neighbour's array has too few planes", kname, s ? "upper" : "lower");
+    for (int f = 0; f < n_fields; ++f)
+      if (P.field[f].tma && !(s ? peer->hi_ptr[f] : peer->lo_ptr[f]))
+        return fail(PSAD_ERR_INVALID, "%s: field %d has no %s-neighbour array", kname, f, s ? "upper" : "lower");
+  }
+  return 0;
+}
+
+static int fill_peer_args(const char* kname, const psad_peer_t* peer, PsadArgs& A) {
+  const int g = peer->ghost_planes;
+  if (A.shape[0] < 2 * g + 1) return fail(PSAD_ERR_INVALID, "%s: the array has too few planes for %d ghost planes", kname, g);
+  A.peer_flag_lo = static_cast<const unsigned*>(peer->flag_lo);
+  A.peer_flag_hi = static_cast<const unsigned*>(peer->flag_hi);
+  A.peer_error = static_cast<unsigned*>(peer->error_flag);
+  A.peer_expect = peer->expect;
+  A.peer_self = static_cast<unsigned*>(peer->self_flag);
+  A.peer_count = static_cast<unsigned*>(peer->self_count);
+  A.peer_lo_end = g;
+  A.peer_hi_begin = (int)A.shape[0] - g;
+  A.peer_lo_shift = (int)peer->lo_planes - 2 * g;     // ghost plane p of the lower block = the neighbour's plane p + n_lo
+  A.peer_hi_shift = (int)A.shape[0] - 2 * g;          // ghost plane p of the upper block = the neighbour's plane p - n
+  return 0;
+}
+
 extern "C" int psad_plan_launch(const psad_plan_t* plan, int sm_count, int ctas_per_sm, const psad_field_arg_t* fields,
                                 int n_fields, const double* scalars, int n_scalars, const psad_range_t* range,
                                 void* args_out, size_t args_bytes, unsigned grid_out[3]) {
@@ -556,6 +595,23 @@ extern "C" int psad_plan_launch(const psad_plan_t* plan, int sm_count, int ctas_
   int empty = 0;
   PsadArgs A;
   if (int rc = build_args(*plan, "plan", sm_count, ctas_per_sm, fields, n_fields, scalars, n_scalars, range, A, grid_out, &empty)) return rc;
+  if (empty) grid_out[0] = 0;
+  memcpy(args_out, &A, sizeof(A));
+  return 0;
+}
+
+extern "C" size_t psad_args_size(void) { return sizeof(PsadArgs); }
+
+extern "C" int psad_plan_launch_peer(const psad_plan_t* plan, int sm_count, int ctas_per_sm, const psad_field_arg_t* fields,
+                                     int n_fields, const double* scalars, int n_scalars, const psad_range_t* range,
+                                     const psad_peer_t* peer, void* args_out, size_t args_bytes, unsigned grid_out[3]) {
+  if (!plan || !fields || !args_out || !grid_out || !peer) return fail(PSAD_ERR_INVALID, "psad_plan_launch_peer: null argument");
+  if (args_bytes != sizeof(PsadArgs)) return fail(PSAD_ERR_INVALID, "psad_plan_launch_peer: parameter block is %zu bytes", sizeof(PsadArgs));
+  if (int rc = check_peer(*plan, "plan", n_fields, peer)) return rc;
+  int empty = 0;
+  PsadArgs A;
+  if (int rc = build_args(*plan, "plan", sm_count, ctas_per_sm, fields, n_fields, scalars, n_scalars, range, A, grid_out, &empty)) return rc;
+  if (int rc = fill_peer_args("plan", peer, A)) return rc;
   if (empty) grid_out[0] = 0;
   memcpy(args_out, &A, sizeof(A));
   return 0;
@@ -612,23 +668,7 @@ static int launch_impl(psad_kernel_t k, const psad_field_arg_t* fields, int n_fi
   if (n_fields != P.n_fields) return fail(PSAD_ERR_INVALID, "%s: expected %d fields, got %d", k->name.c_str(), P.n_fields, n_fields);
   if (n_scalars != P.n_scalars) return fail(PSAD_ERR_INVALID, "%s: expected %d scalars, got %d", k->name.c_str(), P.n_scalars, n_scalars);
   if (n_scalars > 0 && !scalars) return fail(PSAD_ERR_INVALID, "null scalars");
-  const bool peer_kernel = P.reserved[2] == 1;
-  if (peer_kernel != (peer != nullptr))
-    return fail(PSAD_ERR_INVALID, "%s: %s", k->name.c_str(), peer_kernel ? "a peer-halo kernel needs psad_kernel_launch_peer"
-                                                                         : "not a peer-halo kernel (plan.reserved[2] != 1)");
-  if (peer) {
-    if (P.kind != PSAD_KIND_MARCH || P.ndim != 3) return fail(PSAD_ERR_INVALID, "%s: peer halos need a 3-D march kernel", k->name.c_str());
-    if (peer->ghost_planes < 1) return fail(PSAD_ERR_INVALID, "%s: peer halos need at least one ghost plane", k->name.c_str());
-    for (int s = 0; s < 2; ++s) {
-      const void* flag = s ? peer->flag_hi : peer->flag_lo;
-      if (!flag) continue;
-      if ((s ? peer->hi_planes : peer->lo_planes) < 2 * peer->ghost_planes + 1)
-        return fail(PSAD_ERR_INVALID, "%s: the %s neighbour's array has too few planes", k->name.c_str(), s ? "upper" : "lower");
-      for (int f = 0; f < n_fields; ++f)
-        if (P.field[f].tma && !(s ? peer->hi_ptr[f] : peer->lo_ptr[f]))
-          return fail(PSAD_ERR_INVALID, "%s: field %d has no %s-neighbour array", k->name.c_str(), f, s ? "upper" : "lower");
-    }
-  }
+  if (int rc = check_peer(P, k->name.c_str(), n_fields, peer)) return rc;
   static const bool debug = getenv("PSAD_DEBUG") != nullptr;
   static const bool no_cache = getenv("PSAD_NO_LAUNCH_CACHE") != nullptr;
 
@@ -674,16 +714,8 @@ static int launch_impl(psad_kernel_t k, const psad_field_arg_t* fields, int n_fi
   } else {
     g_cache_misses.fetch_add(1, std::memory_order_relaxed);
     if (int rc = build_args(P, k->name.c_str(), k->sm_count, k->occupancy, fields, n_fields, scalars, n_scalars, range, A, grid, &empty)) return rc;
-    if (peer) {
-      const int g = peer->ghost_planes;
-      A.peer_flag_lo = static_cast<const unsigned*>(peer->flag_lo);
-      A.peer_flag_hi = static_cast<const unsigned*>(peer->flag_hi);
-      A.peer_error = static_cast<unsigned*>(peer->error_flag);
-      A.peer_lo_end = g;
-      A.peer_hi_begin = (int)A.shape[0] - g;
-      A.peer_lo_shift = (int)peer->lo_planes - 2 * g;     // ghost plane p of the lower block = the neighbour's plane p + n_lo
-      A.peer_hi_shift = (int)A.shape[0] - 2 * g;          // ghost plane p of the upper block = the neighbour's plane p - n
-    }
+    if (peer)
+      if (int rc = fill_peer_args(k->name.c_str(), peer, A)) return rc;
     if (!empty && P.kind == PSAD_KIND_MARCH)
       if (int rc = encode_tensor_maps(P, A, n_fields, peer, TM)) return rc;
     if (!no_cache) {
@@ -702,7 +734,12 @@ static int launch_impl(psad_kernel_t k, const psad_field_arg_t* fields, int n_fi
       }
     }
   }
-  if (empty || grid[0] == 0) return 0;
+  if (empty || grid[0] == 0) {
+    // nothing to write, but the launch still counts: the neighbours wait for its number
+    if (peer && peer->self_flag && g_drv.cuMemsetD32Async)
+      CU_CHECK(g_drv.cuMemsetD32Async((CUdeviceptr)(uintptr_t)peer->self_flag, peer->expect + 1u, 1, (CUstream)stream));
+    return 0;
+  }
   for (int i = 0; i < n_scalars; ++i) A.scalar[i] = scalars[i];      // scalars are not part of the key
   if (peer) A.peer_expect = peer->expect;                           // nor is the launch counter
   void* params[2] = {&A, &TM};   // both are copied by cuLaunchKernel (the kernel declares as many maps as it uses)
@@ -796,6 +833,52 @@ extern "C" int psad_stream_write_u32(void* dst, uint32_t value, void* stream) {
   if (int rc = need_driver()) return rc;
   if (!g_drv.cuMemsetD32Async) return fail(PSAD_ERR_NO_DRIVER, "cuMemsetD32Async is not available");
   CU_CHECK(g_drv.cuMemsetD32Async((CUdeviceptr)(uintptr_t)dst, value, 1, (CUstream)stream));
+  return 0;
+}
+
+// A stream-ordered wait on the neighbours' launch counters for launches that do not wait themselves (kernels outside the
+// peer protocol, or with a shorter reach than the launch before them): one thread of a built-in kernel spins until both
+// counters have reached `expect` (psad_wait_peer, bounded), everything behind it on the stream starts after that.
+static const char* k_peer_wait_source =
+    "#include \"psad_args.h\"\n#include \"psad_common.cuh\"\n"
+    "extern \"C\" __global__ void psad_peer_wait_kernel(const unsigned* lo, const unsigned* hi, unsigned expect, unsigned* error) {\n"
+    "  if (lo) psad_wait_peer(lo, expect, error);\n"
+    "  if (hi) psad_wait_peer(hi, expect, error);\n"
+    "}\n";
+struct WaitKernel { CUcontext ctx; CUmodule module; CUfunction fn; };
+static std::mutex g_wait_mutex;
+static std::vector<WaitKernel> g_wait_kernels;   // one per context (one per GPU a process drives)
+
+extern "C" int psad_peer_wait(const void* flag_lo, const void* flag_hi, uint32_t expect, void* error_flag, void* stream) {
+  if (!flag_lo && !flag_hi) return 0;
+  if (int rc = need_driver()) return rc;
+  if (int rc = ensure_context()) return rc;
+  CUcontext ctx = nullptr;
+  CU_CHECK(g_drv.cuCtxGetCurrent(&ctx));
+  CUfunction fn = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_wait_mutex);
+    for (const WaitKernel& w : g_wait_kernels)
+      if (w.ctx == ctx) fn = w.fn;
+    if (!fn) {
+      std::string path;
+      if (int rc = compile_to_cache(k_peer_wait_source, "psad_peer_wait_v1", nullptr, 0, nullptr, nullptr, &path)) return rc;
+      std::vector<char> cubin;
+      if (!read_file(path, cubin)) return fail(PSAD_ERR_IO, "cannot read %s", path.c_str());
+      WaitKernel w{ctx, nullptr, nullptr};
+      CUresult r = g_drv.cuModuleLoadData(&w.module, cubin.data());
+      if (r != 0) return cu_fail(r, "cuModuleLoadData(psad_peer_wait)");
+      r = g_drv.cuModuleGetFunction(&w.fn, w.module, "psad_peer_wait_kernel");
+      if (r != 0) { g_drv.cuModuleUnload(w.module); return cu_fail(r, "cuModuleGetFunction(psad_peer_wait_kernel)"); }
+      g_wait_kernels.push_back(w);
+      fn = w.fn;
+    }
+  }
+  unsigned e = expect;
+  void* params[4] = {&flag_lo, &flag_hi, &e, &error_flag};
+  CUresult r = g_drv.cuLaunchKernel(fn, 1, 1, 1, 1, 1, 1, 0, (CUstream)stream, params, nullptr);
+  if (r != 0) return cu_fail(r, "cuLaunchKernel(psad_peer_wait_kernel)");
+  g_launches.fetch_add(1);
   return 0;
 }
 

@@ -234,8 +234,13 @@ class _PeerHalo:
     (stream order); launch k on a neighbour waits inside the kernel — only in the CTAs that touch ghost planes, and only
     before their first such load — until it reads k - 1 there.  That one condition covers both hazards (the neighbour has
     produced what is read, and has finished reading what is about to be overwritten) as long as all ranks issue the same
-    sequence of launches, which an SPMD program does.  Anything that changes an array outside that sequence (``fill``,
-    ``to_gpu``, writes through ``owned()``) must be followed by ``fence()`` — ``fill`` / ``to_gpu`` do it themselves.
+    sequence of launches, which an SPMD program does — and as long as the launch reaches at least as far along dim 0 as the
+    launch before it did from the other side (the CTAs that overwrite planes a neighbour may still be reading are then CTAs
+    that load ghost planes, hence wait).  A launch with a shorter reach, and every launch outside the protocol (kernels
+    without a march instance, pointwise kernels), is preceded by ``psad_peer_wait``: a one-thread kernel that does the same
+    wait in stream order.  Anything that changes an array outside the launch sequence (``fill``, ``to_gpu``, writes through
+    ``owned()``) must be followed by ``fence()`` — ``fill`` / ``to_gpu`` do it themselves.  All launches of a data handling
+    are expected on one stream (the counter is written in the order of the stream current at the launch).
     """
 
     def __init__(self, data_handling):
@@ -245,13 +250,17 @@ class _PeerHalo:
         dec = data_handling.dec
         self.lo_rank, self.hi_rank = dec.lo_rank, dec.hi_rank
         self.seq = 0
+        self.last_reach = (0, 0)         # planes the previous launch read below / above its own planes (from the neighbours)
         self.dirty = True                # arrays were written outside the launch sequence: fence before the next launch
         self.buffers = {}                # data_ptr of a registered array -> (lower neighbour's ptr, planes, upper ptr, planes)
         self.structs = {}
         self._keep = []
+        self._opened = []
         self._ranges = {}
-        # [0]: this rank's "launches completed" counter, [1]: error flag (a kernel gave up waiting for a neighbour)
-        self.flags = torch.zeros(2, dtype=torch.int32, device=data_handling.device)
+        # [0]: this rank's "launches completed" counter, [1]: error flag (a kernel gave up waiting for a neighbour),
+        # [2]: CTAs of the running launch that have finished (the last one publishes [0] and resets this)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=data_handling.device)
+        self.signal_in_kernel = not _os.environ.get('PSAD_PEER_STREAM_SIGNAL')
         (self.flag_lo, _), (self.flag_hi, _) = self._exchange(self.flags, 1)
 
     def _exchange(self, tensor, planes):
@@ -269,12 +278,28 @@ class _PeerHalo:
             else:
                 h, off, pl = everyone[r]
                 out.append((runtime.ipc_open(h, off), pl))
+                self._opened.append(out[-1][0])
         self._keep.append(tensor)        # exported memory must stay alive while a neighbour maps it
         return out
 
     def register(self, tensor):
         (lo, lo_planes), (hi, hi_planes) = self._exchange(tensor, tensor.shape[0])
         self.buffers[tensor.data_ptr()] = (lo, lo_planes, hi, hi_planes)
+
+    def close(self):
+        """Collective: unmap the neighbours' arrays (they may be freed only after every rank that mapped them has closed
+        them) and let go of the exported ones."""
+        if self._opened is None:
+            return
+        import torch.distributed as dist
+        self.fence()
+        for p in self._opened:
+            runtime.ipc_close(p)
+        self._opened = None
+        self.buffers.clear()
+        self.structs.clear()
+        dist.barrier(group=self.dh.exchanger.group)
+        self._keep = []
 
     def applies(self, kernel, arrays, fused_steps):
         if kernel.ir.ndim != 3 or 'march' not in kernel._emitted or kernel._components:
@@ -295,8 +320,22 @@ class _PeerHalo:
         """1 if a kernel of this rank gave up waiting for a neighbour (host synchronisation)."""
         return int(self.flags[1].item())
 
+    def _wait_in_stream(self):
+        """The neighbours have finished their launch number ``seq`` (ours is about to be number ``seq + 1``)."""
+        cur = self.torch.cuda.current_stream(self.dh.device).cuda_stream
+        runtime.peer_wait(self.flag_lo, self.flag_hi, self.seq, self.flags.data_ptr() + 4, cur)
+
+    def before_foreign_launch(self):
+        """A launch outside the protocol is about to write arrays: the neighbours' previous launch may still be reading
+        their boundary planes."""
+        if self.dirty:
+            self.fence()
+        if self.last_reach != (0, 0):
+            self._wait_in_stream()
+
     def count_foreign_launch(self):
         self.seq += 1
+        self.last_reach = (0, 0)
         cur = self.torch.cuda.current_stream(self.dh.device).cuda_stream
         runtime.stream_write_u32(self.flags.data_ptr(), self.seq, cur)
 
@@ -318,8 +357,14 @@ class _PeerHalo:
             # ONE launch for all owned planes: nothing waits for an exchange
             whole = slab_ranges(dec.global_shape, dec.start, dec.n_local, dec.g, False, False, ir.boundary, ir.ghost_layers,
                                 ir.ndim, fused_steps, halo, periodic=dec.periodic)[0]
-            self._ranges[key] = (kernel, whole)
-        whole = self._ranges[key][1]
+            lo, hi = ir.max_halo[0]
+            self._ranges[key] = (kernel, whole, (lo * fused_steps, hi * fused_steps))
+        _, whole, reach = self._ranges[key]
+        # the lower neighbour's previous launch read `last_reach[1]` of our lowest planes: the CTAs that overwrite them wait
+        # for it if they load lower ghost planes, i.e. if this launch reaches as far down — likewise upwards
+        if reach[0] < self.last_reach[1] or reach[1] < self.last_reach[0]:
+            self._wait_in_stream()
+        self.last_reach = reach
         tensors = [arrays[f.name] for f in kernel.fields]
         skey = (id(kernel),) + tuple(t.data_ptr() for t in tensors)
         peer = self.structs.get(skey)
@@ -332,6 +377,8 @@ class _PeerHalo:
             peer.flag_lo, peer.flag_hi = self.flag_lo, self.flag_hi
             peer.error_flag = self.flags.data_ptr() + 4
             peer.ghost_planes = dec.g
+            if self.signal_in_kernel:
+                peer.self_flag, peer.self_count = self.flags.data_ptr(), self.flags.data_ptr() + 8
             if len(self.structs) > 256:
                 self.structs.clear()
             self.structs[skey] = peer
@@ -340,7 +387,8 @@ class _PeerHalo:
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
         kernel(**arrays, **kwargs, _range=whole, _peer=peer)
-        runtime.stream_write_u32(self.flags.data_ptr(), self.seq, self.torch.cuda.current_stream(dh.device).cuda_stream)
+        if not self.signal_in_kernel:
+            runtime.stream_write_u32(self.flags.data_ptr(), self.seq, self.torch.cuda.current_stream(dh.device).cuda_stream)
 
 
 class SlabDataHandling:
@@ -375,6 +423,12 @@ class SlabDataHandling:
         # peer halos: the stencil kernels read their ghost planes from the neighbouring GPUs' arrays (CUDA IPC mappings,
         # NVLink) instead of having them exchanged first — see _PeerHalo
         self.peer = _PeerHalo(self) if (peer_halo and self.dec.world_size > 1 and self.dec.g > 0) else None
+
+    def close(self):
+        """Collective when peer halos are on: unmaps the neighbours' arrays before anyone frees them."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     max_recorded_calls = 1 << 16      # the reference records without bound; a long-running time loop must not leak
 
@@ -654,6 +708,8 @@ class SlabDataHandling:
         interior, lo, hi = self._range_cache[key][1]
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
+        if self.peer is not None:
+            self.peer.before_foreign_launch()     # the neighbours may still be reading what this launch overwrites
         ordered = [self.start_exchange(n) for n in halo_fields]      # True where the comm stream was ordered behind `cur`
         side = [r for r in (lo, hi) if r is not None]
         on_comm = bool(side) and self._comm_stream is not None and all(t.is_cuda for t in arrays.values())

@@ -61,7 +61,7 @@ class Peer(ctypes.Structure):
     _fields_ = [('lo_ptr', ctypes.c_void_p * PSAD_MAX_FIELDS), ('hi_ptr', ctypes.c_void_p * PSAD_MAX_FIELDS),
                 ('lo_planes', ctypes.c_int64), ('hi_planes', ctypes.c_int64), ('flag_lo', ctypes.c_void_p),
                 ('flag_hi', ctypes.c_void_p), ('error_flag', ctypes.c_void_p), ('expect', ctypes.c_uint32),
-                ('ghost_planes', ctypes.c_int32)]
+                ('ghost_planes', ctypes.c_int32), ('self_flag', ctypes.c_void_p), ('self_count', ctypes.c_void_p)]
 
 
 class Range(ctypes.Structure):
@@ -123,6 +123,7 @@ def lib():
         L.psad_ipc_open.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
         L.psad_ipc_close.argtypes = [ctypes.c_void_p]
         L.psad_stream_write_u32.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+        L.psad_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         L.psad_launch_cache_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)] * 2
         L.psad_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
         L.psad_nccl_unique_id.argtypes = [ctypes.c_void_p]
@@ -293,6 +294,14 @@ def stream_write_u32(ptr, value, stream):
     rc = lib().psad_stream_write_u32(ctypes.c_void_p(ptr), ctypes.c_uint32(value & 0xffffffff), ctypes.c_void_p(stream))
     if rc:
         check(rc, 'psad_stream_write_u32')
+
+
+def peer_wait(flag_lo, flag_hi, expect, error_flag, stream):
+    """Everything behind this call on ``stream`` starts once the neighbours' launch counters have reached ``expect``."""
+    rc = lib().psad_peer_wait(ctypes.c_void_p(flag_lo), ctypes.c_void_p(flag_hi), ctypes.c_uint32(expect & 0xffffffff),
+                              ctypes.c_void_p(error_flag), ctypes.c_void_p(stream))
+    if rc:
+        check(rc, 'psad_peer_wait')
 
 
 def launch_count():

@@ -50,16 +50,21 @@ def correctness(name, bh, steps, rank, world, dev):
         print('[rank %d] %s %s steps=%d fuse=%s peer halos (%s, %d launches): %s' % (
             rank, name, bh, steps, fuse, kl.last_instance, dh.peer.seq, 'IDENTICAL' if same else
             'DIFFERENT (max %.3e, errors %d)' % (float((res[dh.dec.owned] - ref[sl]).abs().max()), dh.peer.errors())), flush=True)
-        dh.peer.fence()
+        dh.close()
     return ok
 
 
 def timing(name, rank, world, dev, steps=20):
     shape = tuple(CONFIG_SHAPES[name]['shape'])
+    if os.environ.get('PSAD_CHECK_SHAPE'):           # e.g. 128,1024,1024: the per-GPU slab of the N = 8 strong-scaling run
+        shape = tuple(int(v) for v in os.environ['PSAD_CHECK_SHAPE'].split(','))
     out = {'workload': name, 'n_gpus': world, 'per_gpu_shape': list(shape)}
-    for mode in ('nccl', 'peer'):
+    for mode in ('alone', 'nccl', 'peer'):
         op = make_config(name, shape=shape, boundary_handling='zeros')
-        slab = SlabStencilOp(op, shape, rank, world, dev, peer_halo=(mode == 'peer'))
+        if mode == 'alone':      # every GPU on its own slab without neighbours: what the kernels take with no halo at all
+            slab = SlabStencilOp(op, shape, 0, 1, dev)
+        else:
+            slab = SlabStencilOp(op, shape, rank, world, dev, peer_halo=(mode == 'peer'))
         g = torch.Generator(device=dev)
         g.manual_seed(3 + rank)
         slab.randomize(g)
@@ -84,13 +89,16 @@ def timing(name, rank, world, dev, steps=20):
         if mode == 'peer':
             out['peer_errors'] = slab.dh.peer.errors()
             out['peer_launches'] = slab.dh.peer.seq
-        keep = {n: slab.dh.owned(n).clone() for n in ('out', 'diffu') if n in slab.dh.gpu_arrays}
-        out.setdefault('_results', {})[mode] = keep
+        if mode != 'alone':
+            keep = {n: slab.dh.owned(n).clone() for n in ('out', 'diffu') if n in slab.dh.gpu_arrays}
+            out.setdefault('_results', {})[mode] = keep
+        slab.dh.close()
         del slab
         torch.cuda.empty_cache()
     res = out.pop('_results')
     out['peer_equals_nccl'] = all(torch.equal(res['nccl'][n], res['peer'][n]) for n in res['nccl'])
     out['speedup'] = out['nccl_ms_per_step'] / out['peer_ms_per_step']
+    out['peer_signal'] = 'stream memset' if os.environ.get('PSAD_PEER_STREAM_SIGNAL') else 'in kernel'
     return out
 
 

@@ -118,6 +118,24 @@ PSAD_DEV void psad_tma_load_2d(psad_u32 dst, const PsadTensorMap* tmap, psad_u32
 PSAD_DEV void psad_tma_load_3d(psad_u32 dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1, int c2) { psad_emu_tma(dst, tmap, bar, c0, c1, c2); }
 PSAD_DEV void psad_tma_prefetch_desc(const PsadTensorMap*) {}
 
+// the end-of-kernel signal: CTAs run one after the other here, so the count reaches gridDim.x exactly at the last one
+PSAD_DEV void psad_signal_peers(unsigned* self_flag, unsigned* count, unsigned value, int tid, int) {
+  psad_emu_cta_consumers->arrive_and_wait();
+  if (tid == 0) {
+    std::lock_guard<std::mutex> g(psad_emu_mutex);
+    if (++*count == gridDim.x) { *count = 0u; *self_flag = value; }
+  }
+}
+
+// peer halos: the neighbours' counters are plain host words here; a counter that has not reached `expect` is what the
+// device version would spin on — recorded as an error instead (the test sets the counters before the launch)
+long long psad_emu_peer_waits = 0;
+PSAD_DEV void psad_wait_peer(const unsigned* flag, unsigned expect, unsigned* error) {
+  std::lock_guard<std::mutex> g(psad_emu_mutex);
+  ++psad_emu_peer_waits;
+  if ((int)(*flag - expect) < 0 && error) *error = 1u;
+}
+
 template <typename T> static inline T psad_emu_shift(T v, int delta) {
   PsadEmuWarp* w = psad_emu_warp;
   std::memcpy(&w->slots[psad_emu_lane], &v, sizeof(T));

@@ -53,13 +53,17 @@ def _compile(emitted, full=False):
     return ctypes.CDLL(base + '.so')
 
 
-def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=None, full=False):
+def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=None, full=False, peer=None):
     """``arrays``: numpy arrays in the plan's field order (outputs first; written in place).
 
     ``full=False``: the per-step bodies under a host copy of the consumer loop (``cpu_shim/``, warps one after the other
     or — exchange kernels — concurrently).  ``full=True``: the REAL ``psad_march.cuh`` (producer warp, TMA ring, full /
     empty mbarriers) with emulated mbarriers and TMA, every thread of the CTA an OS thread (``cpu_shim_full/``); returns
-    ``(ctas, mbarrier waits, TMA loads)``."""
+    ``(ctas, mbarrier waits, TMA loads)``.
+
+    ``peer`` (peer-halo kernels, ``full=True`` only): ``dict(lo=[arrays | None], hi=[arrays | None], ghost_planes=g,
+    flags=uint32 array [lower counter, upper counter, error(, own counter, CTA count)], expect=k)`` — the neighbouring slabs' arrays in plan order
+    (None: no neighbour on that side); the parameter block comes from the product's ``psad_plan_launch_peer``."""
     L = runtime.lib()
     plan = runtime.make_plan(emitted.plan)
     n = len(arrays)
@@ -81,15 +85,43 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
             rng.iter_lo[d], rng.iter_hi[d] = launch_range['iter_lo'][d], launch_range['iter_hi'][d]
             rng.write_lo[d], rng.write_hi[d] = launch_range['write_lo'][d], launch_range['write_hi'][d]
     size = _args_size()
-    runtime.check(L.psad_plan_launch(ctypes.byref(plan), sm_count, ctas_per_sm, fa, n, sc, len(scalars),
-                                     ctypes.byref(rng) if rng is not None else None, args, size, grid), 'psad_plan_launch')
+    tma = [(i, f) for i, f in enumerate(emitted.plan['fields']) if f['tma']]
+    sets = [arrays]
+    if peer is None:
+        runtime.check(L.psad_plan_launch(ctypes.byref(plan), sm_count, ctas_per_sm, fa, n, sc, len(scalars),
+                                         ctypes.byref(rng) if rng is not None else None, args, size, grid), 'psad_plan_launch')
+    else:
+        assert full, 'peer kernels are replayed through the real psad_march.cuh only'
+        P = runtime.Peer()
+        flags = peer['flags']
+        for side, nb in (('lo', peer.get('lo')), ('hi', peer.get('hi'))):
+            if nb is None:
+                continue
+            for i, a in enumerate(nb):
+                assert a.flags['C_CONTIGUOUS'] and a.shape[1:] == arrays[i].shape[1:]
+                getattr(P, side + '_ptr')[i] = a.ctypes.data
+            setattr(P, side + '_planes', nb[0].shape[0])
+            setattr(P, 'flag_' + side, flags.ctypes.data + (0 if side == 'lo' else 4))
+        P.error_flag = flags.ctypes.data + 8
+        if len(flags) >= 5:          # [.., this slab's own counter, its CTA count]: the kernel signals completion itself
+            P.self_flag, P.self_count = flags.ctypes.data + 12, flags.ctypes.data + 16
+        P.expect = peer['expect']
+        P.ghost_planes = peer['ghost_planes']
+        L.psad_plan_launch_peer.argtypes = [ctypes.POINTER(runtime.Plan), ctypes.c_int, ctypes.c_int,
+                                            ctypes.POINTER(runtime.FieldArg), ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.c_int, ctypes.POINTER(runtime.Range), ctypes.POINTER(runtime.Peer),
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint)]
+        runtime.check(L.psad_plan_launch_peer(ctypes.byref(plan), sm_count, ctas_per_sm, fa, n, sc, len(scalars),
+                                              ctypes.byref(rng) if rng is not None else None, ctypes.byref(P), args, size, grid),
+                      'psad_plan_launch_peer')
+        # a missing neighbour gets the local arrays (never read: the kernel takes that branch only with a counter)
+        sets = [arrays, peer.get('lo') or arrays, peer.get('hi') or arrays]
     if grid[0] == 0:
         return 0
-    tma = [(i, f) for i, f in enumerate(emitted.plan['fields']) if f['tma']]
-    tf = ((_EmuFieldFull if full else _EmuField) * len(tma))()
+    tf = ((_EmuFieldFull if full else _EmuField) * (len(tma) * len(sets)))()
     nd = arrays[0].ndim
-    for k, (i, f) in enumerate(tma):
-        a = arrays[i]
+    for k, (i, f) in enumerate((i, f) for arrs in sets for (i, f) in tma):
+        a = sets[k // len(tma)][i]
         st = [0] * (3 - nd) + [s // a.itemsize for s in a.strides]
         tf[k].ptr = a.ctypes.data
         tf[k].stride[:] = st
@@ -102,7 +134,7 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
         so.psad_emulate_full.argtypes = [ctypes.c_void_p, ctypes.POINTER(_EmuFieldFull), ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_longlong)]
         stats = (ctypes.c_longlong * 2)()
-        rc = so.psad_emulate_full(args, tf, len(tma), int(grid[0]), stats)
+        rc = so.psad_emulate_full(args, tf, len(tma) * len(sets), int(grid[0]), stats)
         assert rc == 0, 'psad_emulate_full failed'
         return int(grid[0]), int(stats[0]), int(stats[1])
     so = _compile(emitted)
@@ -164,10 +196,10 @@ def run_generic(emitted, arrays, scalars=(), launch_range=None, sm_count=4):
 
 
 def _args_size():
-    # sizeof(PsadArgs), from the header's layout: 12 ptrs + 12*4 strides + 5*3 int64 + 16 doubles + int64 + 4 ints, then the
-    # peer-halo block (3 pointers, 1 unsigned, 4 ints), padded to the struct's 8-byte alignment
-    n = 12 * 8 + 12 * 4 * 8 + 5 * 3 * 8 + 16 * 8 + 8 + 4 * 4 + 3 * 8 + 4 + 4 * 4
-    return -(-n // 8) * 8
+    """sizeof(PsadArgs) of the library under test (the shims include the same psad_args.h)."""
+    L = runtime.lib()
+    L.psad_args_size.restype = ctypes.c_size_t
+    return int(L.psad_args_size())
 
 
 def aligned_empty(shape, dtype, fill=None):

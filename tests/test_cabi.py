@@ -108,10 +108,13 @@ def test_plan_launch_work_decomposition():
             fa[i].ptr = base                       # never dereferenced: planning only
             fa[i].shape[:] = shape
             fa[i].stride[:] = [shape[1] * shape[2], shape[2], 1, 0]
-        args = ctypes.create_string_buffer(800)
+        L.psad_args_size.restype = ctypes.c_size_t
+        nbytes = int(L.psad_args_size())
+        assert nbytes >= 752 and nbytes % 8 == 0
+        args = ctypes.create_string_buffer(nbytes)
         grid = (ctypes.c_uint * 3)()
         for sms, ctas in ((148, 1), (4, 2)):
-            rc = L.psad_plan_launch(ctypes.byref(plan), sms, ctas, fa, 2, None, 0, None, args, 800, grid)
+            rc = L.psad_plan_launch(ctypes.byref(plan), sms, ctas, fa, 2, None, 0, None, args, nbytes, grid)
             assert rc == 0, L.psad_last_error()
             n_items, = struct.unpack_from('q', args.raw, 728)
             tiles_x, tiles_y, n_chunks, chunk = struct.unpack_from('4i', args.raw, 736)
@@ -123,7 +126,7 @@ def test_plan_launch_work_decomposition():
             steps = -(-n_items // (sms * ctas)) * (chunk + 2 * halo)
             assert steps <= 1.15 * (tiles_x * tiles_y * shape[0] / (sms * ctas)) + chunk + 2 * halo
         # wrong field count and wrong block size are rejected with a message
-        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 1, None, 0, None, args, 800, grid) != 0
+        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 1, None, 0, None, args, nbytes, grid) != 0
         assert b'expected 2 fields' in L.psad_last_error()
         assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, None, args, 100, grid) != 0
         # launch ranges (slabs): the chunks cover the WRITTEN planes only — also for fused-step kernels — and a write
@@ -132,10 +135,10 @@ def test_plan_launch_work_decomposition():
         for d in range(3):
             rng.iter_hi[d] = rng.write_hi[d] = shape[d]
         rng.write_lo[0], rng.write_hi[0] = 2 * halo, 2 * halo + 40
-        rc = L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, 800, grid)
+        rc = L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, nbytes, grid)
         assert rc == 0, L.psad_last_error()
         tiles_x, tiles_y, n_chunks, chunk = struct.unpack_from('4i', args.raw, 736)
         assert chunk * n_chunks >= 40 > chunk * (n_chunks - 1)
         rng.write_hi[0] = shape[0] + 1
-        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, 800, grid) != 0
+        assert L.psad_plan_launch(ctypes.byref(plan), 148, 1, fa, 2, None, 0, ctypes.byref(rng), args, nbytes, grid) != 0
         assert b'outside the array extent' in L.psad_last_error()
