@@ -26,11 +26,11 @@ struct PsadArgs {
   unsigned* peer_error;                    // set to 1 by a CTA that gave up waiting (timeout), never cleared by kernels
   unsigned peer_expect;
   int peer_lo_end, peer_hi_begin, peer_lo_shift, peer_hi_shift;
-  // "this launch has completed", raised by the kernel itself: every CTA counts itself in *peer_count once its stores are
-  // fenced; the last one resets the count and stores peer_expect + 1 into *peer_self (release, system scope) — the counter
-  // the neighbours' next launch waits on.  NULL: the caller writes the counter behind the kernel (psad_stream_write_u32).
-  unsigned* peer_self;
-  unsigned* peer_count;
+  // Order of the z-chunks (3-D march): chunk c of the item numbering works on planes of chunk (c + chunk_rot) % n_chunks.
+  // Peer-halo launches start in the middle of the slab (chunk_rot = n_chunks / 2): the chunks that touch ghost planes — the
+  // ones that wait for the neighbour's previous launch and load over NVLink — are then neither the first work of every
+  // CTA (a wait at the start of every kernel) nor its tail.
+  int chunk_rot;
 };
 
 // 128-byte opaque CUtensorMap image (cuTensorMapEncodeTiled output), 64-byte aligned as the driver requires.

@@ -57,23 +57,6 @@ PSAD_DEV void psad_wait_peer(const unsigned* flag, unsigned expect, unsigned* er
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
-// ---- the other half of the handshake, at the end of a peer-halo kernel (consumer threads only; the producer warp has
-// nothing in flight once the consumers have seen every plane).  Each thread fences its own stores at system scope, the
-// CTA's consumers meet at their named barrier, one thread counts the CTA in; the CTA that completes the count publishes
-// the launch number.  Fences are cumulative: a neighbour that acquires the counter sees every store of every CTA.
-PSAD_DEV void psad_signal_peers(unsigned* self_flag, unsigned* count, unsigned value, int tid, int n_consumer_threads) {
-  __threadfence_system();
-  asm volatile("bar.sync 1, %0;" ::"r"(n_consumer_threads) : "memory");
-  if (tid == 0) {
-    const unsigned arrived = atomicAdd(count, 1u);
-    if (arrived == gridDim.x - 1) {
-      *count = 0u;                        // the next launch (stream order) starts from zero again
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(self_flag), "r"(value) : "memory");
-    }
-  }
-}
-
 // ---- TMA tile loads (global -> shared, completion on an mbarrier; out-of-bounds elements are zero-filled) ---
 PSAD_DEV void psad_tma_load_2d(psad_u32 smem_dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1) {
   asm volatile(

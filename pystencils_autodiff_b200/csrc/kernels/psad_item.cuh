@@ -23,7 +23,8 @@ PSAD_DEV PsadItem psad_decode_item(const PsadArgs& A, long long item) {
   it.x0 = tx * cfg::TXS + cfg::XORG;
   if (cfg::NDIM == 3) {
     const int ty = (int)(rest % A.tiles_y);
-    const int c = (int)(rest / A.tiles_y);
+    int c = (int)(rest / A.tiles_y) + A.chunk_rot;
+    if (c >= A.n_chunks) c -= A.n_chunks;
     it.y0 = ty * cfg::TYS + cfg::YORG;
     it.z0 = (int)A.wr_lo[0] + c * A.chunk;
     int z1 = it.z0 + A.chunk;

@@ -25,11 +25,81 @@
 #define PSAD_PEER 0     // 1: ghost planes along z come from the neighbouring GPUs' arrays (peer memory over NVLink)
 #endif
 
+#ifndef PSAD_PEER_PRODUCER
+#define PSAD_PEER_PRODUCER 1        // 0: source chosen per plane inside one loop; 1: three plane loops per item (lower
+#endif                              //    neighbour's planes, own planes, upper neighbour's planes), wait once per item
+// Not inlined: measured on the 27-point fp64 kernel, the peer producer inlined into the kernel changes ptxas' register
+// allocation / schedule of the CONSUMER loop (1.13 -> 1.25 ms with no neighbour at all); as a separate function the
+// consumers' code is the plain kernel's again (1.137 ms).  For the same reason the kernel does not announce its own
+// completion (a fence + count + flag store at its end cost 0.03-0.05 ms there, inlined or not): the caller writes the
+// launch counter behind the kernel in stream order (psad_stream_write_u32).  profiles/r2_peer_halo.md.
+#ifndef PSAD_PEER_PRODUCER_NOINLINE
+#define PSAD_PEER_PRODUCER_NOINLINE 1
+#endif
+#ifndef PSAD_TMAPS_SETS
+#define PSAD_TMAPS_SETS (PSAD_PEER ? 3 : 1)
+#endif
+
 struct PsadTmaps {
-  PsadTensorMap m[cfg::NTMA * (PSAD_PEER ? 3 : 1)];   // [this GPU's arrays | lower neighbour's | upper neighbour's]
+  PsadTensorMap m[cfg::NTMA * PSAD_TMAPS_SETS];   // [this GPU's arrays | lower neighbour's | upper neighbour's]
 };
 
 #include "psad_item.cuh"
+
+#if PSAD_PEER && PSAD_PEER_PRODUCER
+// The producer lane of a peer-halo kernel (3-D).  Per item: the planes below peer_lo_end come from the lower neighbour's
+// array, the planes from peer_hi_begin on from the upper neighbour's, everything between from this GPU's — three loops
+// with one TMA instruction each (constant descriptor address), the middle one being the loop of the plain kernel.  Before
+// the first plane it takes from a neighbour the lane waits — once per kernel and side — for that neighbour's counter.
+struct PsadRing { int slot; psad_u32 parity; };
+PSAD_DEV void psad_stage_plane(const PsadTensorMap* maps, PsadRing& r, psad_u32 ring_s, psad_u32 full_s, psad_u32 empty_s,
+                               int x0, int y0, int pz) {
+  psad_mbar_wait(empty_s + 8 * r.slot, r.parity);
+  psad_mbar_arrive_expect_tx(full_s + 8 * r.slot, cfg::TX_BYTES);
+  const psad_u32 base = ring_s + r.slot * cfg::STAGE_BYTES;
+#pragma unroll
+  for (int f = 0; f < cfg::NTMA; ++f)
+    psad_tma_load_3d(base + cfg::F_OFF[f], &maps[f], full_s + 8 * r.slot, x0 + cfg::F_ORGX[f], y0 + cfg::F_ORGY[f], pz);
+  if (++r.slot == cfg::STAGES) {
+    r.slot = 0;
+    r.parity ^= 1;
+  }
+}
+
+#if PSAD_PEER_PRODUCER_NOINLINE
+__device__ __noinline__
+#else
+PSAD_DEV
+#endif
+void psad_produce_peer(const PsadArgs& A, const PsadTmaps& TM, psad_u32 ring_s, psad_u32 full_s, psad_u32 empty_s) {
+#pragma unroll
+  for (int f = 0; f < 3 * cfg::NTMA; ++f) psad_tma_prefetch_desc(&TM.m[f]);
+  PsadRing r{0, 1u};   // the first pass over the ring does not wait (barrier phase -1 counts as complete)
+  bool lo_ready = false, hi_ready = false;
+  const int lo_end = A.peer_flag_lo != nullptr ? A.peer_lo_end : -(1 << 30);       // no neighbour: no plane qualifies
+  const int hi_begin = A.peer_flag_hi != nullptr ? A.peer_hi_begin : (1 << 30);
+#pragma unroll 1
+  for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    const PsadItem it = psad_decode_item(A, item);
+    int p = it.p_first;
+    if (p < lo_end) {
+      if (!lo_ready) { psad_wait_peer(A.peer_flag_lo, A.peer_expect, A.peer_error); lo_ready = true; }
+#pragma unroll 1
+      for (; p < lo_end && p <= it.p_last; ++p)
+        psad_stage_plane(&TM.m[cfg::NTMA], r, ring_s, full_s, empty_s, it.x0, it.y0, p + A.peer_lo_shift);
+    }
+    const int own_last = it.p_last < hi_begin ? it.p_last : hi_begin - 1;
+#pragma unroll 1
+    for (; p <= own_last; ++p) psad_stage_plane(&TM.m[0], r, ring_s, full_s, empty_s, it.x0, it.y0, p);
+    if (p <= it.p_last) {
+      if (!hi_ready) { psad_wait_peer(A.peer_flag_hi, A.peer_expect, A.peer_error); hi_ready = true; }
+#pragma unroll 1
+      for (; p <= it.p_last; ++p)
+        psad_stage_plane(&TM.m[2 * cfg::NTMA], r, ring_s, full_s, empty_s, it.x0, it.y0, p - A.peer_hi_shift);
+    }
+  }
+}
+#endif
 
 extern "C" __global__ void __launch_bounds__(cfg::THREADS + 32, cfg::MIN_CTAS)
 PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ PsadTmaps TM) {
@@ -60,6 +130,10 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
 
   if (warp == NWARPS) {
     // ================= producer warp =================
+#if PSAD_PEER && PSAD_PEER_PRODUCER
+    if (lane == 0) psad_produce_peer(A, TM, ring_s, full_s, empty_s);
+    return;
+#endif
     if (lane == 0) {
 #pragma unroll
       for (int f = 0; f < cfg::NTMA * (PSAD_PEER ? 3 : 1); ++f) psad_tma_prefetch_desc(&TM.m[f]);
@@ -140,9 +214,6 @@ PSAD_KERNEL_NAME(const __grid_constant__ PsadArgs A, const __grid_constant__ Psa
       if (++ph == cfg::NP) ph = 0;
     }
   }
-#if PSAD_PEER
-  if (A.peer_self != nullptr) psad_signal_peers(A.peer_self, A.peer_count, A.peer_expect + 1u, tid, cfg::THREADS);
-#endif
 }
 
 #endif

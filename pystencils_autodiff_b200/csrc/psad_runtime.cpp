@@ -557,8 +557,6 @@ static int check_peer(const psad_plan_t& P, const char* kname, int n_fields, con
   if (!peer) return 0;
   if (P.kind != PSAD_KIND_MARCH || P.ndim != 3) return fail(PSAD_ERR_INVALID, "%s: peer halos need a 3-D march kernel", kname);
   if (peer->ghost_planes < 1) return fail(PSAD_ERR_INVALID, "%s: peer halos need at least one ghost plane", kname);
-  if ((peer->self_flag == nullptr) != (peer->self_count == nullptr))
-    return fail(PSAD_ERR_INVALID, "%s: self_flag and self_count go together", kname);
   for (int s = 0; s < 2; ++s) {
     const void* flag = s ? peer->flag_hi : peer->flag_lo;
     if (!flag) continue;
@@ -578,8 +576,8 @@ static int fill_peer_args(const char* kname, const psad_peer_t* peer, PsadArgs& 
   A.peer_flag_hi = static_cast<const unsigned*>(peer->flag_hi);
   A.peer_error = static_cast<unsigned*>(peer->error_flag);
   A.peer_expect = peer->expect;
-  A.peer_self = static_cast<unsigned*>(peer->self_flag);
-  A.peer_count = static_cast<unsigned*>(peer->self_count);
+  static const bool no_rot = getenv("PSAD_PEER_NO_ROTATION") != nullptr;
+  A.chunk_rot = no_rot ? 0 : A.n_chunks / 2;
   A.peer_lo_end = g;
   A.peer_hi_begin = (int)A.shape[0] - g;
   A.peer_lo_shift = (int)peer->lo_planes - 2 * g;     // ghost plane p of the lower block = the neighbour's plane p + n_lo
@@ -734,12 +732,7 @@ static int launch_impl(psad_kernel_t k, const psad_field_arg_t* fields, int n_fi
       }
     }
   }
-  if (empty || grid[0] == 0) {
-    // nothing to write, but the launch still counts: the neighbours wait for its number
-    if (peer && peer->self_flag && g_drv.cuMemsetD32Async)
-      CU_CHECK(g_drv.cuMemsetD32Async((CUdeviceptr)(uintptr_t)peer->self_flag, peer->expect + 1u, 1, (CUstream)stream));
-    return 0;
-  }
+  if (empty || grid[0] == 0) return 0;
   for (int i = 0; i < n_scalars; ++i) A.scalar[i] = scalars[i];      // scalars are not part of the key
   if (peer) A.peer_expect = peer->expect;                           // nor is the launch counter
   void* params[2] = {&A, &TM};   // both are copied by cuLaunchKernel (the kernel declares as many maps as it uses)

@@ -34,6 +34,7 @@ __all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataH
 
 
 import os as _os
+_PEER_NEVER_WAIT = bool(_os.environ.get('PSAD_PEER_NEVER_WAIT'))    # timing experiments only: results are then unordered
 _ALWAYS_ORDER_SIDE_LAUNCHES = bool(_os.environ.get('PSAD_ALWAYS_ORDER_SIDE'))     # diagnostic switch (scripts/r2_ab_multi.sh)
 
 
@@ -257,10 +258,8 @@ class _PeerHalo:
         self._keep = []
         self._opened = []
         self._ranges = {}
-        # [0]: this rank's "launches completed" counter, [1]: error flag (a kernel gave up waiting for a neighbour),
-        # [2]: CTAs of the running launch that have finished (the last one publishes [0] and resets this)
-        self.flags = torch.zeros(4, dtype=torch.int32, device=data_handling.device)
-        self.signal_in_kernel = not _os.environ.get('PSAD_PEER_STREAM_SIGNAL')
+        # [0]: this rank's "launches completed" counter, [1]: error flag (a kernel gave up waiting for a neighbour)
+        self.flags = torch.zeros(2, dtype=torch.int32, device=data_handling.device)
         (self.flag_lo, _), (self.flag_hi, _) = self._exchange(self.flags, 1)
 
     def _exchange(self, tensor, planes):
@@ -377,18 +376,15 @@ class _PeerHalo:
             peer.flag_lo, peer.flag_hi = self.flag_lo, self.flag_hi
             peer.error_flag = self.flags.data_ptr() + 4
             peer.ghost_planes = dec.g
-            if self.signal_in_kernel:
-                peer.self_flag, peer.self_count = self.flags.data_ptr(), self.flags.data_ptr() + 8
             if len(self.structs) > 256:
                 self.structs.clear()
             self.structs[skey] = peer
         self.seq += 1
-        peer.expect = self.seq - 1
+        peer.expect = 0 if _PEER_NEVER_WAIT else self.seq - 1
         if fused_steps > 1:
             kwargs = dict(kwargs, _variant='march_x2')
         kernel(**arrays, **kwargs, _range=whole, _peer=peer)
-        if not self.signal_in_kernel:
-            runtime.stream_write_u32(self.flags.data_ptr(), self.seq, self.torch.cuda.current_stream(dh.device).cuda_stream)
+        runtime.stream_write_u32(self.flags.data_ptr(), self.seq, self.torch.cuda.current_stream(dh.device).cuda_stream)
 
 
 class SlabDataHandling:

@@ -61,7 +61,7 @@ class Peer(ctypes.Structure):
     _fields_ = [('lo_ptr', ctypes.c_void_p * PSAD_MAX_FIELDS), ('hi_ptr', ctypes.c_void_p * PSAD_MAX_FIELDS),
                 ('lo_planes', ctypes.c_int64), ('hi_planes', ctypes.c_int64), ('flag_lo', ctypes.c_void_p),
                 ('flag_hi', ctypes.c_void_p), ('error_flag', ctypes.c_void_p), ('expect', ctypes.c_uint32),
-                ('ghost_planes', ctypes.c_int32), ('self_flag', ctypes.c_void_p), ('self_count', ctypes.c_void_p)]
+                ('ghost_planes', ctypes.c_int32)]
 
 
 class Range(ctypes.Structure):

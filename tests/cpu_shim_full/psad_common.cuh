@@ -25,6 +25,7 @@ typedef unsigned long long psad_u64;
 
 #define PSAD_DEV static inline
 #define __device__
+#define __noinline__
 #define __global__
 #define __grid_constant__
 #define __shared__
@@ -117,15 +118,6 @@ static inline void psad_emu_tma(psad_u32 dst, const PsadTensorMap* tmap, psad_u3
 PSAD_DEV void psad_tma_load_2d(psad_u32 dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1) { psad_emu_tma(dst, tmap, bar, c0, c1, 0); }
 PSAD_DEV void psad_tma_load_3d(psad_u32 dst, const PsadTensorMap* tmap, psad_u32 bar, int c0, int c1, int c2) { psad_emu_tma(dst, tmap, bar, c0, c1, c2); }
 PSAD_DEV void psad_tma_prefetch_desc(const PsadTensorMap*) {}
-
-// the end-of-kernel signal: CTAs run one after the other here, so the count reaches gridDim.x exactly at the last one
-PSAD_DEV void psad_signal_peers(unsigned* self_flag, unsigned* count, unsigned value, int tid, int) {
-  psad_emu_cta_consumers->arrive_and_wait();
-  if (tid == 0) {
-    std::lock_guard<std::mutex> g(psad_emu_mutex);
-    if (++*count == gridDim.x) { *count = 0u; *self_flag = value; }
-  }
-}
 
 // peer halos: the neighbours' counters are plain host words here; a counter that has not reached `expect` is what the
 // device version would spin on — recorded as an error instead (the test sets the counters before the launch)

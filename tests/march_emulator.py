@@ -62,7 +62,7 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
     ``(ctas, mbarrier waits, TMA loads)``.
 
     ``peer`` (peer-halo kernels, ``full=True`` only): ``dict(lo=[arrays | None], hi=[arrays | None], ghost_planes=g,
-    flags=uint32 array [lower counter, upper counter, error(, own counter, CTA count)], expect=k)`` — the neighbouring slabs' arrays in plan order
+    flags=uint32 array [lower counter, upper counter, error], expect=k)`` — the neighbouring slabs' arrays in plan order
     (None: no neighbour on that side); the parameter block comes from the product's ``psad_plan_launch_peer``."""
     L = runtime.lib()
     plan = runtime.make_plan(emitted.plan)
@@ -103,8 +103,6 @@ def run(emitted, arrays, scalars=(), sm_count=3, ctas_per_sm=1, launch_range=Non
             setattr(P, side + '_planes', nb[0].shape[0])
             setattr(P, 'flag_' + side, flags.ctypes.data + (0 if side == 'lo' else 4))
         P.error_flag = flags.ctypes.data + 8
-        if len(flags) >= 5:          # [.., this slab's own counter, its CTA count]: the kernel signals completion itself
-            P.self_flag, P.self_count = flags.ctypes.data + 12, flags.ctypes.data + 16
         P.expect = peer['expect']
         P.ghost_planes = peer['ghost_planes']
         L.psad_plan_launch_peer.argtypes = [ctypes.POINTER(runtime.Plan), ctypes.c_int, ctypes.c_int,
