@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument('--strong', action='store_true',
                     help='strong scaling: the workload shape is the GLOBAL field, split along dim 0 over the ranks '
                          '(default: weak scaling, every rank owns the full workload shape)')
+    ap.add_argument('--halo', default='auto', choices=['auto', 'nccl', 'peer'],
+                    help='N > 1: ghost planes by NCCL exchange, read by the kernels from the neighbours\' memory (peer), or '
+                         'whichever was measured to win for this slab size (auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (diagnostic runs)')
     ap.add_argument('--only-headline', action='store_true', help='skip the extra N = 1 legs (workloads, function path, parity)')
@@ -293,7 +296,7 @@ class Env:
         return [float(v) for v in t.tolist()]
 
 
-def measure_resident(env, wl, shape, steps, warmup, cooldown_s=0.0):
+def measure_resident(env, wl, shape, steps, warmup, cooldown_s=0.0, halo='auto'):
     """The device-timed metric for one workload: K steps of forward + adjoint launches through the C ABI on resident
     arrays, CUDA events, barrier on both sides, max over ranks.  Returns ``(result dict, slab, op)``."""
     import numpy as np
@@ -303,7 +306,8 @@ def measure_resident(env, wl, shape, steps, warmup, cooldown_s=0.0):
     torch = env.torch
     t_setup0 = time.perf_counter()
     op = make_config(wl, shape=shape, boundary_handling='zeros')
-    slab = SlabStencilOp(op, local_shape=shape, rank=env.rank, world_size=env.world, device=env.dev)
+    slab = SlabStencilOp(op, local_shape=shape, rank=env.rank, world_size=env.world, device=env.dev,
+                         peer_halo={'auto': 'auto', 'nccl': False, 'peer': True}[halo])
     setup_ms = {'symbolic_and_emit_ms': (time.perf_counter() - t_setup0) * 1e3}
     cells = int(np.prod(shape))
     b_fwd = op.forward_ast_gpu.bytes_per_cell()
@@ -687,7 +691,7 @@ def main_ours(args):
             raise SystemExit('--strong: dim 0 (%d) must be divisible by the number of GPUs (%d)' % (shape[0], env.world))
         shape = (shape[0] // env.world,) + shape[1:]
     n_launch0 = runtime.launch_count()
-    head, slab, op = measure_resident(env, wl, shape, args.steps, args.warmup)
+    head, slab, op = measure_resident(env, wl, shape, args.steps, args.warmup, halo=args.halo)
     cells = int(np.prod(shape))
 
     legs = {}
@@ -727,6 +731,8 @@ def main_ours(args):
     if env.world == 1 and e2e_error is None and not args.only_headline:
         legs['e2e_plugin'] = guarded(plugin_e2e, env, op, slab, 2)
 
+    peer_errors = slab.dh.peer.errors() if slab.dh.peer is not None else None
+    slab.dh.close()            # collective: peer-halo mappings of the neighbours' arrays are released before anyone frees them
     if env.rank != 0:
         if env.world > 1:
             dist.destroy_process_group()
@@ -755,6 +761,8 @@ def main_ours(args):
         'setup': head['setup'],
         'host_issue_ms_per_step': head['host_issue_ms_per_step'],
     }
+    if env.world > 1:
+        line['halo'] = {'requested': args.halo, 'used': 'peer' if peer_errors is not None else 'nccl', 'peer_wait_timeouts': peer_errors}
     line.update(legs)
 
     # ---- the other named configurations (BASELINE.json configs 2, 4, 5): own timed region, roofline and clocks each ----

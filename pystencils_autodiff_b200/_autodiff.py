@@ -447,12 +447,12 @@ class AutoDiffOp:
     def create_torch_op(self, *args, **kwargs):
         return self.create_tensorflow_op(*args, backend='torch_native', **kwargs)
 
-    def create_unrolled_torch_op(self, steps, op_name=None, tuning=None):
+    def create_unrolled_torch_op(self, steps, op_name=None, tuning=None, fuse=None):
         """``Function`` applying this one-field stencil ``steps`` times (pairs of steps fused into one launch); see
         ``backends/_torch_native.create_unrolled_function``.  Not part of the reference API: its users chain
         ``op.apply`` calls, which still works here."""
         from .backends._torch_native import create_unrolled_function
-        return create_unrolled_function(self, steps, op_name=op_name, tuning=tuning)
+        return create_unrolled_function(self, steps, op_name=op_name, tuning=tuning, fuse=fuse)
 
     def create_slab_torch_op(self, data_handling, **kwargs):
         """``Function`` of this op on one rank's slab of slab-decomposed fields (halo exchange in forward and on the

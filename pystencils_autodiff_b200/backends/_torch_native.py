@@ -486,14 +486,16 @@ def create_autograd_function(autodiff_obj, use_cuda=True, op_name=None, tuning=N
     return cls
 
 
-def create_unrolled_function(autodiff_obj, steps, op_name=None, tuning=None):
+def create_unrolled_function(autodiff_obj, steps, op_name=None, tuning=None, fuse=None):
     """``torch.autograd.Function`` for ``steps`` unrolled applications of a one-field stencil, ``u_T = S^T(u_0)``.
 
     The reference unrolls time steps by chaining ``op.apply`` calls (tests/test_tfmad.py style) — T forward and T
     adjoint launches, each a full read + write of the field, with T - 1 intermediate tensors kept alive by autograd.
     Here pairs of steps run as one launch (``CompiledKernel.run_steps``, emit_chain.py) and nothing is saved: the
     adjoint of a stencil whose adjoint kernel reads only the upstream gradient is ``(S^T)`` applied ``steps`` times to
-    that gradient.  Stencils whose adjoint needs forward values are rejected (chain ``op.apply`` for those)."""
+    that gradient.  Stencils whose adjoint needs forward values are rejected (chain ``op.apply`` for those).
+    ``fuse``: as in ``CompiledKernel.run_steps`` (None: pairs wherever they can be built; False: single steps — the
+    results of a fused pair and of two single launches may differ in the last bit, the sums are ordered differently)."""
     import torch
     fwd_ir = autodiff_obj.forward_ast_gpu
     bwd_ir = autodiff_obj.backward_ast_gpu
@@ -518,10 +520,10 @@ def create_unrolled_function(autodiff_obj, steps, op_name=None, tuning=None):
 
     def forward(ctx, u):
         ctx.scalars = dict(class_kwargs)
-        return (fwd_kernel.run_steps(_prep(u), steps, **{k: v for k, v in ctx.scalars.items() if k in fwd_kernel.scalars}),)
+        return (fwd_kernel.run_steps(_prep(u), steps, fuse=fuse, **{k: v for k, v in ctx.scalars.items() if k in fwd_kernel.scalars}),)
 
     def backward(ctx, grad):
-        return bwd_kernel.run_steps(_prep(grad), steps, **{k: v for k, v in ctx.scalars.items() if k in bwd_kernel.scalars})
+        return bwd_kernel.run_steps(_prep(grad), steps, fuse=fuse, **{k: v for k, v in ctx.scalars.items() if k in bwd_kernel.scalars})
 
     cls = type(op_name or '%s_x%d' % (autodiff_obj.op_name, steps), (torch.autograd.Function,),
                {'forward': staticmethod(forward), 'backward': staticmethod(backward)})

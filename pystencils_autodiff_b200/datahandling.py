@@ -387,6 +387,30 @@ class _PeerHalo:
         runtime.stream_write_u32(self.flags.data_ptr(), self.seq, self.torch.cuda.current_stream(dh.device).cuda_stream)
 
 
+PEER_HALO_MAX_CELLS = 600 * 1000 * 1000
+
+
+def peer_halos_pay_off(local_shape, world_size, backend='nccl', device=None):
+    """``peer_halo='auto'``: peer halos where they were measured to win (profiles/r2_peer_halo.md, two B200s over NVLink).
+    One launch per kernel with the ghost planes read from the neighbours costs ~18 us per forward+adjoint step next to a GPU
+    that has no neighbours at all, the NCCL exchange + interior / boundary launches 60-95 us — until the slabs get thick
+    enough for the boundary launches to hide completely behind the interior one (7-point fp32, 1024 planes of 1024^2: NCCL
+    +29 us, peer +54 us per step).  So: all ranks on one node, NCCL backend, 3-D slabs of at most 6e8 cells."""
+    if world_size < 2 or backend != 'nccl' or len(local_shape) != 3:
+        return False
+    if device is not None and getattr(device, 'type', 'cuda') != 'cuda':
+        return False
+    local_world = _os.environ.get('LOCAL_WORLD_SIZE')
+    if local_world is not None and int(local_world) != world_size:
+        return False                     # ranks on several nodes: no peer memory between them
+    if 'expandable_segments:True' in _os.environ.get('PYTORCH_CUDA_ALLOC_CONF', ''):
+        return False                     # such allocations cannot be exported through CUDA IPC
+    cells = 1
+    for v in local_shape:
+        cells *= int(v)
+    return cells <= PEER_HALO_MAX_CELLS
+
+
 class SlabDataHandling:
     """Array registry with the reference's data-handling vocabulary (``add_array``, ``fields``, ``run_kernel``,
     ``synchronization_function``, ``swap``, ``fill``, ``gather_array``; graph_datahandling.py:202-327,
@@ -418,7 +442,11 @@ class SlabDataHandling:
         self._ev_halo = None
         # peer halos: the stencil kernels read their ghost planes from the neighbouring GPUs' arrays (CUDA IPC mappings,
         # NVLink) instead of having them exchanged first — see _PeerHalo
-        self.peer = _PeerHalo(self) if (peer_halo and self.dec.world_size > 1 and self.dec.g > 0) else None
+        if peer_halo == 'auto':
+            peer_halo = peer_halos_pay_off(self.dec.local_shape, self.dec.world_size, backend, self.device)
+        if peer_halo and periodic:
+            raise ValueError('peer halos are not available on periodic domains (use the NCCL exchange)') if peer_halo is True else None
+        self.peer = _PeerHalo(self) if (peer_halo and not periodic and self.dec.world_size > 1 and self.dec.g > 0) else None
 
     def close(self):
         """Collective when peer halos are on: unmaps the neighbours' arrays before anyone frees them."""
@@ -1255,6 +1283,9 @@ class SlabStencilOp:
         self.dh = SlabDataHandling(global_shape, rank, world_size, g, device, backend, peer_halo=peer_halo)
         self.exchange_kind = ('ncclSend/ncclRecv via psad_halo_exchange on a comm stream, overlapped with interior planes'
                               if backend == 'nccl' else 'torch.distributed P2P')
+        if self.dh.peer is not None:
+            self.exchange_kind = ('peer halos: ghost planes staged by the stencil kernel\'s own TMA loads from the neighbouring '
+                                  'GPUs\' arrays (CUDA IPC, NVLink), one launch per kernel, per-rank launch counters')
         self.local_shape = tuple(local_shape)
         names = OrderedDict()
         for f in list(op.forward_fields) + list(op.backward_fields):

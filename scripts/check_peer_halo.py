@@ -54,6 +54,58 @@ def correctness(name, bh, steps, rank, world, dev):
     return ok
 
 
+def mixed_sequence(name, bh, steps, rank, world, dev):
+    """Launches inside and outside the peer protocol on the same arrays: the stencil with peer halos (u -> out), a pointwise
+    kernel without any reach (out -> u: overwrites planes the neighbours' stencil launch may still be reading — ordered by
+    psad_peer_wait), the same stencil through the NCCL path (its march instances removed: a 'foreign' launch), pointwise
+    again.  Against the same sequence unsharded."""
+    import pystencils_autodiff_b200 as ps
+    local = SHAPES[name]
+    gshape = (local[0] * world,) + local[1:]
+    op_g = make_config(name, shape=gshape, boundary_handling=bh)
+    ir_g = op_g.forward_ast_gpu
+    halo = max(ir_g.halo(ir_g.input_fields[0].name)[0])
+    dtype = ir_g.input_fields[0].dtype.numpy_dtype
+    g = torch.Generator(device='cpu')
+    g.manual_seed(11)
+    glob = torch.randn(gshape, generator=g, dtype=torch.float64).to(getattr(torch, str(dtype))).to(dev)
+    sl = slice(rank * local[0], (rank + 1) * local[0])
+
+    def pointwise(shape):
+        u, out = ps.fields('u, out: %s[%s]' % (dtype, ','.join(str(v) for v in shape)))
+        return ps.AutoDiffOp(ps.AssignmentCollection([ps.Assignment(u.center, 0.5 * out.center + 0.25)]), op_name='halve',
+                             boundary_handling='zeros').forward_ast_gpu
+
+    dh = SlabDataHandling(gshape, rank, world, halo, dev, peer_halo=True)
+    dh.add_arrays('u, out', dtype=dtype)
+    lshape = dh.dec.local_shape
+    k_st = CompiledKernel(make_config(name, shape=lshape, boundary_handling=bh).forward_ast_gpu)
+    k_foreign = CompiledKernel(make_config(name, shape=lshape, boundary_handling=bh).forward_ast_gpu)
+    for v in [v for v in k_foreign._emitted if v.startswith('march')]:
+        del k_foreign._emitted[v]                  # only the generic kernel is left: never a peer launch
+    k_pw = CompiledKernel(pointwise(lshape))
+    kg_st, kg_pw = CompiledKernel(ir_g), CompiledKernel(pointwise(gshape))
+    kg_foreign = CompiledKernel(make_config(name, shape=gshape, boundary_handling=bh).forward_ast_gpu)
+    for v in [v for v in kg_foreign._emitted if v.startswith('march')]:
+        del kg_foreign._emitted[v]
+    dh.owned('u').copy_(glob[sl])
+    dh.peer.dirty = True
+    u_ref, out_ref = glob.clone(), torch.zeros_like(glob)
+    for i in range(steps):
+        dh.run_kernel(k_st if i % 2 == 0 else k_foreign, halo_fields=['u'])
+        dh.run_kernel(k_pw)
+        (kg_st if i % 2 == 0 else kg_foreign)(u=u_ref, out=out_ref)
+        kg_pw(u=u_ref, out=out_ref)
+    torch.cuda.synchronize()
+    same = torch.equal(dh.owned('u'), u_ref[sl]) and dh.peer.errors() == 0
+    print('[rank %d] %s %s mixed sequence, %d steps (%s / %s / %s, %d launches counted): %s' % (
+        rank, name, bh, steps, k_st.last_instance, k_foreign.last_instance, k_pw.last_instance, dh.peer.seq,
+        'IDENTICAL' if same else 'DIFFERENT (max %.3e, errors %d)' % (float((dh.owned('u') - u_ref[sl]).abs().max()), dh.peer.errors())),
+        flush=True)
+    dh.close()
+    return same
+
+
 def timing(name, rank, world, dev, steps=20, reps=3):
     """ms per forward+adjoint step: every GPU alone on its slab (no neighbours, no halos), NCCL exchange, peer halos — the
     three operators are built once and timed in rotating order, each timed region started from an idle GPU (this pool's
@@ -121,6 +173,7 @@ def main():
     dev = torch.device('cuda', int(os.environ['LOCAL_RANK']))
     dist.init_process_group('nccl', device_id=dev)
     ok = correctness(name, bh, steps, rank, world, dev)
+    ok = mixed_sequence(name, bh, steps, rank, world, dev) and ok
     res = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if '--time' in sys.argv and int(res.item()) == 1:

@@ -78,7 +78,7 @@ def main():
     fuse = glob.element_size() == 4
     dh2 = SlabDataHandling(gshape, rank, world, (2 if fuse else 1) * halo, dev)
     Many = create_slab_unrolled_function(make_config(name, shape=local, boundary_handling=bh), dh2, steps, fuse=fuse)
-    WholeMany = op_g.create_unrolled_torch_op(steps)
+    WholeMany = op_g.create_unrolled_torch_op(steps, fuse=fuse)     # like with like: a fused pair rounds differently
     u = glob[sl].clone().requires_grad_(True)
     (o,) = Many.apply(u)
     (o * r[sl]).sum().backward()

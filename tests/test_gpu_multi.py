@@ -30,3 +30,25 @@ def test_sharded_equals_unsharded(name, bh):
     # the ranks print concurrently: two reports can share a line, so count verdicts, not lines
     assert out.stdout.count('[rank') >= world and out.stdout.count('IDENTICAL') == out.stdout.count('[rank')
     assert 'DIFFERENT' not in out.stdout
+
+
+@pytest.mark.no_launch
+@pytest.mark.parametrize('name,bh,steps', [('c3', 'zeros', 9), ('c3', 'none', 7), ('c4', 'zeros', 6)])
+def test_peer_halos_equal_unsharded(name, bh, steps):
+    """Peer halos (``SlabDataHandling(peer_halo=True)``: the stencil kernels stage their ghost planes by TMA from the
+    neighbouring GPUs' arrays over NVLink, one launch per kernel, per-rank launch counters as the only ordering): time
+    loops of single steps and fused pairs, and a sequence mixing peer launches with launches outside the protocol
+    (``psad_peer_wait``, NCCL exchange), bit for bit against the unsharded kernels — many more launches than ranks, so a
+    missed wait shows up as a difference."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    world = 2 if n < 4 else 4
+    port = 29400 + (hash((name, bh, 'peer')) % 200)
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+                          '--master-addr', '127.0.0.1', '--master-port', str(port),
+                          os.path.join(ROOT, 'scripts', 'check_peer_halo.py'), name, bh, str(steps)],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count('[rank') >= 3 * world and out.stdout.count('IDENTICAL') == out.stdout.count('[rank')
+    assert 'DIFFERENT' not in out.stdout
