@@ -20,8 +20,9 @@ from pystencils_autodiff_b200.datahandling import SlabDataHandling
 
 
 def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else 'c3'
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    name = args[0] if args else 'c3'
+    steps = int(args[1]) if len(args) > 1 else 8
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
@@ -35,13 +36,16 @@ def main():
             dist.barrier()
 
     local = tuple(CONFIG_SHAPES[name]['shape'])
+    if '--strong' in sys.argv:           # the global field is the workload's shape, every rank owns 1 / world of its planes
+        local = (local[0] // world,) + local[1:]
+    peer = '--peer' in sys.argv          # ghost planes read by the kernels from the neighbouring GPUs (no exchange launches)
     gshape = (local[0] * world,) + local[1:]
     probe = make_config(name, shape=gshape).forward_ast_gpu
     halo = max(probe.halo(probe.input_fields[0].name)[0])
     dtype = probe.input_fields[0].dtype.numpy_dtype
     results = {}
     for fuse in (False, True):
-        dh = SlabDataHandling(gshape, rank, world, 2 * halo, dev)
+        dh = SlabDataHandling(gshape, rank, world, 2 * halo, dev, peer_halo=peer and world > 1)
         dh.add_arrays('u, out', dtype=dtype)
         kernel = CompiledKernel(make_config(name, shape=dh.dec.local_shape).forward_ast_gpu)
         gen = torch.Generator(device=dev)
@@ -51,6 +55,8 @@ def main():
         dh.run_steps(kernel, steps, fuse=fuse)               # warm-up (NVRTC, module load, NCCL connections)
         dh.run_steps(kernel, steps, fuse=fuse)
         dh.owned('u').copy_(start_state)
+        if dh.peer is not None:
+            dh.peer.dirty = True
         del start_state
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -64,6 +70,8 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         results[fuse] = (float(ms), dh.owned('u').clone() if steps * reps <= 64 else None)
+        peer_errors = dh.peer.errors() if dh.peer is not None else None
+        dh.close()
         del dh
         torch.cuda.empty_cache()
     diff = None
@@ -76,7 +84,8 @@ def main():
             ms = results[fuse][0]
             print(json.dumps({'workload': name, 'n_gpus': world, 'per_gpu_shape': list(local), 'steps': steps, 'fused_pairs': fuse,
                               'ms_per_step': ms, 'gcell_steps_per_s': cells / ms / 1e6,
-                              'speedup_vs_single': results[False][0] / ms, 'rel_diff_fused_vs_single': diff}), flush=True)
+                              'speedup_vs_single': results[False][0] / ms, 'rel_diff_fused_vs_single': diff,
+                              'halo': 'peer' if peer and world > 1 else 'nccl', 'peer_wait_timeouts': peer_errors}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
