@@ -80,6 +80,9 @@ def build_library(force=False, verbose=False):
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ['g++', '-O2', '-fPIC', '-shared', '-std=c++17', '-Wall', '-o', LIB_PATH + '.tmp', src, '-ldl', '-lpthread']
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    if os.path.exists(os.path.join(cuda_inc, 'nvtx3', 'nvToolsExt.h')):     # header-only NVTX ranges (optional)
+        cmd += ['-isystem', cuda_inc]
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)
