@@ -664,6 +664,36 @@ def extra_legs(env, wl, op, slab, args, with_fused=True):
                           'used_by_default': True,
                           'note': 'out = S(S(u)) with one read and one write of the field; the default of run_steps() / '
                                   'create_unrolled_torch_op() wherever a pair can be built'}
+            # the same through the REFERENCE's time-loop API (GraphDataHandling.TimeLoop: add_call(kernel) + swap(in, out),
+            # graph_datahandling.py:152-197): the loop recognises the idiom and issues fused pairs by default
+            try:
+                keep_src, keep_dst = src.clone(), dst.clone()
+                T = 8
+
+                def _loop(fuse):
+                    tl = slab.dh.create_timeloop(use_cuda_graph=True, fuse_steps=fuse)
+                    tl.add_call(fk, {})
+                    tl.swap(fin, fout)
+                    tl.run(T)                         # warm-up, graph capture
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    a.record()
+                    tl.run(T)
+                    tl.run(T)
+                    b.record()
+                    torch.cuda.synchronize()
+                    return a.elapsed_time(b) / (2 * T), tl.fused_last_run
+                t_single, f_single = _loop(False)
+                t_default, f_default = _loop(None)
+                src.copy_(keep_src)
+                dst.copy_(keep_dst)
+                del keep_src, keep_dst
+                steps_info['time_loop_api'] = {
+                    'ms_per_time_step_default': t_default, 'fused_pairs_by_default': bool(f_default),
+                    'ms_per_time_step_single_steps': t_single, 'speedup': t_single / t_default, 'time_steps': 2 * T,
+                    'api': 'dh.create_timeloop(); tl.add_call(kernel, {}); tl.swap(in, out); tl.run(T)'}
+            except Exception as exc:
+                steps_info['time_loop_api'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     except Exception as exc:   # a diagnostic beside the headline must never take the line down
         steps_info = {'error': '%s: %s' % (type(exc).__name__, exc)}
     out['fused_steps'] = steps_info

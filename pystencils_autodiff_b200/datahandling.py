@@ -668,8 +668,8 @@ class SlabDataHandling:
             return
         self.torch.cuda.current_stream(self.device).wait_event(self._ev_halo)
 
-    def create_timeloop(self, use_cuda_graph=True, concurrent=True):
-        return TimeLoop(self, use_cuda_graph, concurrent)
+    def create_timeloop(self, use_cuda_graph=True, concurrent=True, fuse_steps=None):
+        return TimeLoop(self, use_cuda_graph, concurrent, fuse_steps)
 
     # -- kernels ---------------------------------------------------------------------------------------------------
     def run_kernel(self, kernel, halo_fields=(), fused_steps=1, **kwargs):
@@ -714,6 +714,13 @@ class SlabDataHandling:
                 kwargs = dict(kwargs, _variant='march_x2')
             return kernel(**arrays, **kwargs)          # whole arrays, every rank, no exchange
         ir = kernel.ir
+        if fused_steps > 1 and ir.ndim != 3 and self.dec.world_size == 1 and self.dec.g == 0:
+            # the arrays ARE the field (one rank, no ghost planes): the 2-D pair runs on them whole, like
+            # CompiledKernel.run_steps (lifted to a one-plane 3-D field by the emitter)
+            reason = kernel.fused_steps_reason()
+            if reason:
+                raise ValueError('%s: steps cannot be fused: %s' % (kernel.function_name, reason))
+            return kernel(**arrays, **dict(kwargs, _variant='march_x2'))
         if self.peer is not None and self.peer.applies(kernel, arrays, fused_steps):
             return self.peer.run(kernel, arrays, fused_steps, kwargs)
         key = (id(kernel), fused_steps)
@@ -790,10 +797,12 @@ def _pairs_pay_off(kernel, dec):
     """Default of ``fuse=None``: fused pairs of steps where they were measured to win (3-D, 4-byte elements) and the slab
     stores the ``2 x reach`` ghost planes a pair needs."""
     ir = kernel.ir
-    if ir.ndim != 3 or kernel.fused_steps_reason() is not None:
+    if kernel.fused_steps_reason() is not None:
         return False
     if any(f.dtype.itemsize != 4 for f in ir.all_fields):
         return False
+    if ir.ndim != 3:      # 2-D pairs (5-point fp32 8192^2: 1.39x) run on whole arrays only: one rank, no ghost planes
+        return ir.ndim == 2 and dec.world_size == 1 and dec.g == 0
     reach = max(ir.halo(ir.input_fields[0].name)[0])
     return dec.world_size == 1 or dec.g >= 2 * reach
 
@@ -1082,11 +1091,16 @@ class TimeLoop:
     (``computationgraph.ComputationGraph.levels``) and — on one rank — issues the calls of one level on different streams,
     forked from and joined back into the current stream with events.  Inside the captured CUDA graph those become parallel
     branches.  ``levels()`` shows the schedule; ``concurrent=False`` turns it off.
+
+    **Fused pairs of steps** (f-1): a loop whose step is ``add_call(kernel)`` + ``swap(input, output)`` of a one-field stencil
+    runs two time steps per launch (``fused_pair``; ``fuse_steps=False`` turns it off, ``True`` insists), on one GPU and on
+    slabs (one exchange of twice the reach per pair) — the reference's own loop idiom gets what ``run_steps`` does.
     """
 
-    def __init__(self, data_handling, use_cuda_graph=True, concurrent=True):
+    def __init__(self, data_handling, use_cuda_graph=True, concurrent=True, fuse_steps=None):
         self.dh = data_handling
         self.concurrent = concurrent
+        self.fuse_steps = fuse_steps      # None: fused pairs where run_steps() would take them; False: never; True: must
         self._entries = []                # structured step parts: ('kernel', kernel, kwargs, halo) | ('swap', a, b) | None
         self._side_streams = []
         self._pre, self._post, self._steps = [], [], []
@@ -1097,6 +1111,7 @@ class TimeLoop:
         self.use_cuda_graph = use_cuda_graph
 
     max_cached_graphs = 4
+    fused_last_run = False            # whether the last run() issued fused pairs of steps
 
     @property
     def parent(self):                     # the reference's name for the data handling (graph_datahandling.py:155)
@@ -1124,7 +1139,7 @@ class TimeLoop:
                 halo = a.pop('halo_fields', ()) if isinstance(a, dict) else ()
                 self._single_step_asts.append(('KernelCall', functor.function_name))
                 self.add_single_step_function(lambda k=functor, kw=a, h=halo: self.dh.run_kernel(k, halo_fields=h, **kw),
-                                              _entry=('kernel', functor))
+                                              _entry=('kernel', functor, a, tuple(halo)))
             else:
                 self._single_step_asts.append(('Call', getattr(functor, '__name__', type(functor).__name__)))
                 self.add_single_step_function(lambda f=functor, kw=a: f(**kw))
@@ -1157,6 +1172,54 @@ class TimeLoop:
             graph = ComputationGraph(queue, io)
             self._levels = [[n.index for n in level] for level in graph.levels()]
         return self._levels
+
+    def fused_pair(self):
+        """``(kernel, scalars, halo_fields)`` when two steps of this loop can run as ONE launch, else None.
+
+        The reference's time-loop idiom — ``add_call(kernel)`` then ``swap(in, out)`` (graph_datahandling.py:152-197, the
+        pair ``merge_swaps_with_kernel_calls`` folds into one node, :329-344) — is recognised when the kernel is a
+        one-field stencil whose pair the emitter can build (``CompiledKernel.fused_steps_reason``) and, for the default
+        ``fuse_steps=None``, where ``SlabDataHandling.run_steps`` fuses by default (``_pairs_pay_off``).  ``run`` then
+        issues ``out = S(S(u))`` + one swap per two time steps — one read and one write of the field, one halo exchange of
+        twice the reach — exactly what ``run_steps`` does, through the reference's API.  Results can differ from single
+        steps in the last bit (sums are ordered differently)."""
+        if self.fuse_steps is False:
+            return None
+        e = self._entries
+        ok = (len(e) == 2 and e[0] is not None and e[1] is not None and e[0][0] == 'kernel' and e[1][0] == 'swap')
+        why = 'the step is not `add_call(kernel)` followed by `swap(input, output)`'
+        if ok:
+            kernel, kw, halo = e[0][1], e[0][2], e[0][3]
+            ir = kernel.ir
+            ok = len(ir.input_fields) == 1 and len(ir.output_fields) == 1
+            why = 'the kernel is not a one-input / one-output stencil'
+        if ok:
+            fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
+            ok = {e[1][1], e[1][2]} == {fin, fout} and all(n == fin for n in halo) and \
+                all(isinstance(v, (int, float)) and not isinstance(v, bool) for v in kw.values())
+            why = 'the swap does not exchange the kernel\'s input and output arrays (or the call passes non-scalar arguments)'
+        if ok:
+            reason = kernel.fused_steps_reason()
+            ok, why = reason is None, reason
+        if ok and self.fuse_steps is None:
+            ok = _pairs_pay_off(kernel, self.dh.dec)
+        elif ok:
+            reach = max(ir.halo(fin)[0])
+            ok = self.dh.dec.world_size == 1 or self.dh.dec.g >= 2 * reach
+            why = 'a fused pair needs %d ghost layers along dim 0, the data handling stores %d' % (2 * reach, self.dh.dec.g)
+        if not ok:
+            if self.fuse_steps is True:
+                raise ValueError('TimeLoop(fuse_steps=True): %s' % why)
+            return None
+        dec = self.dh.dec
+        needs_halo = dec.world_size > 1 and dec.g > 0 and max(ir.halo(fin)[0]) > 0
+        return kernel, dict(kw), ((fin,) if needs_halo else ())
+
+    def _one_pair(self, fused):
+        kernel, kw, halo = fused
+        ir = kernel.ir
+        self.dh.run_kernel(kernel, halo_fields=halo, fused_steps=2, **kw)
+        self.dh.swap(ir.input_fields[0].name, ir.output_fields[0].name)
 
     def _one_step(self):
         n = len(self.dh.call_queue)
@@ -1194,10 +1257,12 @@ class TimeLoop:
         """Identity of every registered buffer under its current name: what a captured graph has baked in."""
         return tuple((n, t.data_ptr(), tuple(t.shape)) for n, t in self.dh.gpu_arrays.items())
 
-    def _capture_two_steps(self):
-        """Two steps as one CUDA graph (a step that swaps buffers is only periodic with period 2).  Capturing executes
+    def _capture_two_steps(self, unit=None):
+        """Two steps (two fused PAIRS of steps when ``unit`` is given) as one CUDA graph (a step that swaps buffers is only
+        periodic with period 2).  Capturing executes
         the steps' host side — the swaps — but no kernel, so the registry is put back afterwards; a step sequence that is
         not back at the same buffer roles after two steps (a three-buffer rotation) cannot be replayed: None."""
+        unit = unit or self._one_step
         torch, dh = self.dh.torch, self.dh
         before = OrderedDict(dh.gpu_arrays)
         roles, n_swaps, n_calls = self._roles(), dh._swap_count, len(dh.call_queue)
@@ -1206,8 +1271,8 @@ class TimeLoop:
         with torch.cuda.stream(stream):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
-                self._one_step()
-                self._one_step()
+                unit()
+                unit()
         torch.cuda.current_stream(dh.device).wait_stream(stream)
         periodic = self._roles() == roles
         dh.gpu_arrays.clear()
@@ -1229,25 +1294,35 @@ class TimeLoop:
             graph_ok = (self.use_cuda_graph and dh.dec.world_size == 1 and torch.cuda.is_available()
                         and all(t.is_cuda for t in dh.gpu_arrays.values()))
             done = 0
-            if graph_ok and time_steps >= 4:
+            fused = self.fused_pair() if time_steps >= 2 else None
+            if fused is not None:
+                # two time steps per launch (f-1); `per` = time steps one unit advances
+                unit, per = (lambda: self._one_pair(fused)), 2
+            else:
+                unit, per = self._one_step, 1
+            self.fused_last_run = fused is not None
+            if graph_ok and time_steps >= 4 * per:
                 # warm up (NVRTC / module load must not happen during capture)
                 n0 = dh._swap_count
-                self._one_step()
-                self._one_step()
+                unit()
+                unit()
                 swaps_per_step = (dh._swap_count - n0) // 2
-                done = 2
+                done = 2 * per
                 # a graph bakes the buffer pointers in: it is only valid for the roles it was captured with (an odd
                 # number of steps in an earlier run, an external swap or a replaced array all change them)
-                roles = self._roles()
+                roles = (self._roles(), per)
                 if roles not in self._graphs:
                     if len(self._graphs) >= self.max_cached_graphs:
                         self._graphs.clear()
-                    self._graphs[roles] = self._capture_two_steps()
+                    self._graphs[roles] = self._capture_two_steps(unit)
                 graph = self._graphs[roles]
-                while graph is not None and done + 2 <= time_steps:
+                while graph is not None and done + 2 * per <= time_steps:
                     graph.replay()
-                    done += 2
-            for _ in range(time_steps - done):
+                    done += 2 * per
+            while done + per <= time_steps:
+                unit()
+                done += per
+            for _ in range(time_steps - done):        # the odd last step of a fused run
                 self._one_step()
             self.time_steps_run += time_steps
             for f in self._post:

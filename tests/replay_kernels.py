@@ -32,6 +32,8 @@ class ReplayKernel(CompiledKernel):
         type(self).launches.append(ek.name)
         rng = None if _range is None else {k: v for k, v in _range.items() if not k.startswith('_')}
         arrays = [t.detach().numpy() for t in tensors]
+        if variant == 'march_x2' and nd == 2:      # the lifted pair takes one-plane 3-D fields, like CompiledKernel.__call__
+            arrays = [a[None] for a in arrays]
         if variant == 'generic':
             emu.run_generic(ek, arrays, scal, launch_range=rng)
         else:

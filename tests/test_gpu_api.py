@@ -258,10 +258,12 @@ def test_timeloop_with_swap_and_cuda_graph_replay():
     assert np.abs(results[0].cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
-def test_timeloop_graph_follows_the_buffer_roles():
+@pytest.mark.parametrize('fuse_steps, counts', [(False, (5, 4, 6, 7)), (None, (9, 8, 10, 11))])
+def test_timeloop_graph_follows_the_buffer_roles(fuse_steps, counts):
     """a captured graph bakes buffer pointers in.  ``run(5)`` leaves ``u`` / ``out`` swapped after its odd
     eager tail step, an external ``swap`` or a replaced array changes the roles too — each must re-capture (or reuse the
-    graph captured for exactly those roles), never replay a stale one."""
+    graph captured for exactly those roles), never replay a stale one.  Second case: the same with the loop issuing fused
+    pairs of steps (the graph then holds two pairs = four time steps)."""
     import torch
     from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
     from pystencils_autodiff_b200.datahandling import SlabDataHandling
@@ -274,27 +276,79 @@ def test_timeloop_graph_follows_the_buffer_roles():
         dh = SlabDataHandling(shape, 0, 1, 0, device='cuda:0')
         dh.add_arrays('u, out', dtype=np.float32)
         dh.owned('u').copy_(_t(U0))
-        tl = dh.create_timeloop(use_cuda_graph=use_graph)
+        tl = dh.create_timeloop(use_cuda_graph=use_graph, fuse_steps=fuse_steps)
         tl.add_call(kern, {})
         tl.swap('u', 'out')
-        tl.run(5)
-        tl.run(4)                                  # roles swapped relative to the first capture
+        tl.run(counts[0])
+        assert tl.fused_last_run == (fuse_steps is None)
+        tl.run(counts[1])                          # roles swapped relative to the first capture
         dh.swap('u', 'out')
         dh.swap('u', 'out')
-        tl.run(6)
+        tl.run(counts[2])
         fresh = dh.owned('u').clone()              # a replaced array: same values, new pointer
         dh.gpu_arrays['u'] = fresh
-        tl.run(7)
+        tl.run(counts[3])
         torch.cuda.synchronize()
-        assert tl.time_steps_run == 22
-        if use_graph:
+        assert tl.time_steps_run == sum(counts)
+        if use_graph and torch.cuda.is_available():          # (the CPU dry run of this body has no CUDA graphs)
             assert len(tl._graphs) >= 2 and all(g is not None for g in tl._graphs.values())
         finals.append(dh.owned('u').clone())
     assert torch.equal(finals[0], finals[1])
     ref = U0
-    for _ in range(22):
+    for _ in range(sum(counts)):
         ref = evaluate(op.forward_assignments, dict(u=ref), 'zeros')['out']
     assert np.abs(finals[0].cpu().numpy() - ref).max() <= 4e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('name, shape, g', [('c3', (20, 30, 128), 2), ('c3', (20, 30, 128), 0), ('c2', (64, 128), 0)])
+def test_timeloop_runs_fused_pairs_of_steps(name, shape, g):
+    """f-1 through the reference's API: ``add_call(kernel)`` + ``swap(in, out)`` runs as ``out = S(S(u))`` launches (two time
+    steps each, CUDA-graph replayed) where ``run_steps`` fuses by default — bit-identical to ``run_steps``, half the launches,
+    the oracle chain within tolerance; ``fuse_steps=False`` issues single steps."""
+    import torch
+    from pystencils_autodiff_b200 import runtime
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    T = 13
+    op = make_config(name, shape=shape)
+    U0 = np.random.default_rng(6).normal(size=shape).astype(np.float32)
+    finals, launches = {}, {}
+    for mode in (None, False, 'run_steps'):
+        dh = SlabDataHandling(shape, 0, 1, g, device='cuda:0')
+        dh.add_arrays('u, out', dtype=np.float32)
+        kern = CompiledKernel(make_config(name, shape=dh.dec.local_shape).forward_ast_gpu)
+        dh.owned('u').copy_(_t(U0))
+        n0 = runtime.launch_count()
+        if mode == 'run_steps':
+            dh.run_steps(kern, T)
+        else:
+            tl = dh.create_timeloop(use_cuda_graph=False, fuse_steps=mode)
+            tl.add_call(kern, {})
+            tl.swap('u', 'out')
+            tl.run(T)
+            assert tl.fused_last_run == (mode is None)
+        torch.cuda.synchronize()
+        launches[mode] = runtime.launch_count() - n0
+        finals[mode] = dh.owned('u').clone()
+        if mode is None:                       # the same loop replayed from a CUDA graph of two pairs
+            dh.owned('u').copy_(_t(U0))
+            tg = dh.create_timeloop(use_cuda_graph=True)
+            tg.add_call(kern, {})
+            tg.swap('u', 'out')
+            tg.run(T)
+            torch.cuda.synchronize()
+            assert tg.fused_last_run
+            if torch.cuda.is_available():          # (the CPU dry run of this body has no CUDA graphs)
+                assert len(tg._graphs) == 1 and all(v is not None for v in tg._graphs.values())
+            assert torch.equal(dh.owned('u'), finals[None])
+    if torch.cuda.is_available():              # (replayed launches of the CPU dry run are not counted by the runtime)
+        assert launches[None] == launches['run_steps'] == T // 2 + 1 and launches[False] == T
+    assert torch.equal(finals[None], finals['run_steps'])
+    ref = U0.astype(np.float64)
+    for _ in range(T):
+        ref = evaluate(op.forward_assignments, dict(u=ref), 'zeros')['out']
+    for mode in (None, False):
+        assert np.abs(finals[mode].cpu().numpy() - ref).max() <= 4e-6 * np.abs(ref).max()
 
 
 def test_tensor_field_front_door():

@@ -185,6 +185,16 @@ def _steps_worker(rank, world, port, bh, steps, q):
             parts = 1 + int(rank > 0) + int(rank < world - 1)     # interior + the planes next to each neighbour
             assert sum('x2' in n for n in ReplayKernel.launches) == parts * (steps // 2 if fuse else 0)
             assert len(ReplayKernel.launches) == parts * n_launch
+            # the same loop through the reference's TimeLoop API (add_call + swap): fused pairs by default on a data
+            # handling that stores 2 x halo ghost planes, single steps with fuse_steps=False — bit-identical to run_steps
+            dh.owned('u').copy_(torch.from_numpy(glob_u[sl]))
+            del dh.call_queue[:]
+            tl = dh.create_timeloop(fuse_steps=None if fuse else False)
+            tl.add_call(kernel, {'halo_fields': ['u']})
+            tl.swap('u', 'out')
+            tl.run(steps)
+            assert tl.fused_last_run == fuse and [c[0] for c in dh.call_queue] == ['TimeloopRun']
+            assert np.array_equal(dh.gather_array('u'), res[fuse])
         q.put((rank, res[False], res[True]))
     finally:
         dist.destroy_process_group()
@@ -695,3 +705,76 @@ def test_periodic_single_rank_is_its_own_neighbour():
     assert GraphDataHandling((8, 8), 1, periodicity=(True, False), device='cpu').dec.periodic
     with pytest.raises(NotImplementedError, match='dim 0 only'):
         GraphDataHandling((8, 8), 1, periodicity=True, device='cpu')
+
+
+@pytest.mark.parametrize('name,shape,g,bh', [('c3', (10, 12, 136), 2, 'zeros'), ('c3', (9, 12, 132), 0, None),
+                                             ('c3', (7, 8, 132), 1, 'zeros'),
+                                             ('c2', (24, 136), 0, 'zeros')])
+def test_timeloop_fuses_pairs_of_steps(name, shape, g, bh):
+    """The reference's time-loop idiom — ``add_call(kernel)`` + ``swap(in, out)`` (graph_datahandling.py:152-197) — runs as
+    fused pairs of steps (``out = S(S(u))``, one launch per two time steps) where ``run_steps`` would fuse: same result as
+    ``run_steps`` bit for bit, the oracle chain within tolerance, ONE ``TimeloopRun`` record in the reference's vocabulary;
+    ``fuse_steps=False`` keeps single steps.  Kernels replayed on the CPU from the emitted source."""
+    from oracle import evaluate
+    from pystencils_autodiff_b200.configs import make_config
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    from replay_kernels import ReplayKernel
+    T = 5
+    op = make_config(name, shape=shape, boundary_handling=bh)
+    U0 = np.random.default_rng(11).normal(size=shape).astype(np.float32)
+    finals = {}
+    for mode in (None, False, 'run_steps'):
+        dh = SlabDataHandling(shape, 0, 1, g, device='cpu', backend='torch')
+        dh.add_arrays('u, out', dtype=np.float32)
+        kern = ReplayKernel(make_config(name, shape=dh.dec.local_shape, boundary_handling=bh).forward_ast_gpu)
+        dh.owned('u').copy_(torch.from_numpy(U0))
+        ReplayKernel.launches.clear()
+        if mode == 'run_steps':
+            dh.run_steps(kern, T)
+        else:
+            tl = dh.create_timeloop(fuse_steps=mode)
+            tl.add_call(kern, {})
+            tl.swap('u', 'out')
+            assert (tl.fused_pair() is not None) == (mode is None)
+            tl.run(T)
+            assert tl.time_steps_run == T and tl.fused_last_run == (mode is None)
+            kind, steps, recorded = dh.call_queue[-1]
+            assert kind == 'TimeloopRun' and steps == T and [c[0] for c in recorded] == ['KernelCall', 'Swap']
+            assert len(dh.call_queue) == 1
+        fused_launches = [n for n in ReplayKernel.launches if n.endswith('_x2') or '_x2' in n]
+        assert len(ReplayKernel.launches) == (T if mode is False else T // 2 + T % 2)
+        assert len(fused_launches) == (0 if mode is False else T // 2)
+        finals[mode] = dh.owned('u').clone()
+    assert torch.equal(finals[None], finals['run_steps'])
+    ref = U0.astype(np.float64)
+    for _ in range(T):
+        ref = evaluate(op.forward_assignments, dict(u=ref), bh)['out']
+    for mode in (None, False):
+        assert np.abs(finals[mode].numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_timeloop_fused_pairs_are_refused_where_they_cannot_be_built():
+    """``fuse_steps=True`` raises with the reason; the default silently keeps single steps."""
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.configs import make_config
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    dh = SlabDataHandling((4, 16, 132), 0, 1, 0, device='cpu', backend='torch')
+    dh.add_arrays('u, f, g', dtype=np.float32)
+    tv = CompiledKernel(make_config('c5', shape=(4, 16, 132)).forward_ast_gpu)       # two input fields
+    for fuse, raises in ((None, False), (True, True)):
+        tl = dh.create_timeloop(fuse_steps=fuse)
+        tl.add_call(tv, {})
+        tl.swap('u', 'g')
+        if raises:
+            with pytest.raises(ValueError, match='one-input'):
+                tl.fused_pair()
+        else:
+            assert tl.fused_pair() is None
+    heat = CompiledKernel(make_config('c3', shape=(4, 16, 132)).forward_ast_gpu)
+    dh2 = SlabDataHandling((4, 16, 132), 0, 1, 0, device='cpu', backend='torch')
+    dh2.add_arrays('u, out', dtype=np.float32)
+    tl = dh2.create_timeloop(fuse_steps=True)
+    tl.add_call(heat, {})
+    tl.add_single_step_function(lambda: dh2.swap('u', 'out'))          # an opaque function: the loop cannot know it swaps
+    with pytest.raises(ValueError, match='add_call'):
+        tl.fused_pair()
