@@ -682,15 +682,16 @@ def extra_legs(env, wl, op, slab, args, with_fused=True):
                     tl.run(T)
                     b.record()
                     torch.cuda.synchronize()
-                    return a.elapsed_time(b) / (2 * T), tl.fused_last_run
-                t_single, f_single = _loop(False)
-                t_default, f_default = _loop(None)
+                    return a.elapsed_time(b) / (2 * T), tl.fused_last_run, tl.capture_error
+                t_single, f_single, err_single = _loop(False)
+                t_default, f_default, err_default = _loop(None)
                 src.copy_(keep_src)
                 dst.copy_(keep_dst)
                 del keep_src, keep_dst
                 steps_info['time_loop_api'] = {
                     'ms_per_time_step_default': t_default, 'fused_pairs_by_default': bool(f_default),
                     'ms_per_time_step_single_steps': t_single, 'speedup': t_single / t_default, 'time_steps': 2 * T,
+                    'cuda_graph_capture_error': err_single or err_default,
                     'api': 'dh.create_timeloop(); tl.add_call(kernel, {}); tl.swap(in, out); tl.run(T)'}
             except Exception as exc:
                 steps_info['time_loop_api'] = {'error': '%s: %s' % (type(exc).__name__, exc)}

@@ -102,9 +102,16 @@ class CompiledKernel:
 
     def fused_steps_reason(self):
         """None when ``out = S(S(u))`` can run as one launch (emit_chain.py), else why not."""
+        try:
+            return self._fused_reason          # asked per launch / per run() by the data handling: computed once
+        except AttributeError:
+            pass
         if self._components:
-            return 'index dimensions'
-        return self._march_reason or chain_ineligible_reason(self._chain_ir())
+            reason = 'index dimensions'
+        else:
+            reason = self._march_reason or chain_ineligible_reason(self._chain_ir())
+        self._fused_reason = reason
+        return reason
 
     def run_steps(self, src, steps, out=None, fuse=None, **scalars):
         """``S^steps(src)``: the stencil applied ``steps`` times, ping-ponging between ``out`` and one scratch tensor;

@@ -776,7 +776,8 @@ class SlabDataHandling:
         message per neighbour replaces two.  Needs ``default_ghost_layers >= 2 * halo``.  Default (``fuse=None``): pairs
         wherever they are a measured win and possible — 3-D fields of 4-byte elements (7-point fp32, 1024^3 per GPU:
         1.63x at one GPU, 1.71x at two, profiles/r2_slab_steps_c3_n*.json) on a data handling that stores enough ghost
-        layers; everything else runs single steps (27-point fp64: 1.0x)."""
+        layers, 8-byte elements on one rank (27-point fp64 768^3: 1.08x, profiles/r2_slab_steps_c4_n1.json), 2-D 'zeros'
+        stencils on one rank without ghost planes; everything else runs single steps (``_pairs_pay_off``)."""
         ir = kernel.ir
         if len(ir.input_fields) != 1 or len(ir.output_fields) != 1:
             raise ValueError('%s: run_steps needs a kernel with one input and one output field' % kernel.function_name)
@@ -794,13 +795,14 @@ class SlabDataHandling:
 
 
 def _pairs_pay_off(kernel, dec):
-    """Default of ``fuse=None``: fused pairs of steps where they were measured to win (3-D, 4-byte elements) and the slab
-    stores the ``2 x reach`` ghost planes a pair needs."""
+    """Default of ``fuse=None``: fused pairs of steps where they were measured to win — 3-D fields of 4-byte elements on any
+    number of ranks when the slab stores the ``2 x reach`` ghost planes a pair needs (7-point fp32: 1.63x / 1.71x at one / two
+    GPUs), 8-byte elements on one rank (27-point fp64: 1.08x), 2-D 'zeros' stencils on one rank without ghost planes (1.4x)."""
     ir = kernel.ir
     if kernel.fused_steps_reason() is not None:
         return False
-    if any(f.dtype.itemsize != 4 for f in ir.all_fields):
-        return False
+    if any(f.dtype.itemsize != 4 for f in ir.all_fields) and dec.world_size > 1:
+        return False      # fp64 pairs: 1.08x on one rank (profiles/r2_slab_steps_c4_n1.json), not measured across ranks
     if ir.ndim != 3:      # 2-D pairs (5-point fp32 8192^2: 1.39x) run on whole arrays only: one rank, no ghost planes
         return ir.ndim == 2 and dec.world_size == 1 and dec.g == 0
     reach = max(ir.halo(ir.input_fields[0].name)[0])
@@ -1112,6 +1114,7 @@ class TimeLoop:
 
     max_cached_graphs = 4
     fused_last_run = False            # whether the last run() issued fused pairs of steps
+    capture_error = None              # why the last CUDA-graph capture failed (the loop then runs eagerly), else None
 
     @property
     def parent(self):                     # the reference's name for the data handling (graph_datahandling.py:155)
@@ -1129,6 +1132,7 @@ class TimeLoop:
         self._graphs.clear()
         self._step_record = None
         self._levels = None
+        self._fused = None
 
     def add_call(self, functor, argument_list=None):
         args = argument_list if argument_list is not None else {}
@@ -1185,6 +1189,14 @@ class TimeLoop:
         steps in the last bit (sums are ordered differently)."""
         if self.fuse_steps is False:
             return None
+        if self._fused is None or self._fused[0] is not self.fuse_steps:
+            # decided once per step definition and setting (add_single_step_function resets it)
+            self._fused = (self.fuse_steps, self._find_fused_pair())
+        return self._fused[1]
+
+    _fused = None                             # (fuse_steps it was decided for, None | (kernel, scalars, halo_fields))
+
+    def _find_fused_pair(self):
         e = self._entries
         ok = (len(e) == 2 and e[0] is not None and e[1] is not None and e[0][0] == 'kernel' and e[1][0] == 'swap')
         why = 'the step is not `add_call(kernel)` followed by `swap(input, output)`'
@@ -1266,19 +1278,35 @@ class TimeLoop:
         torch, dh = self.dh.torch, self.dh
         before = OrderedDict(dh.gpu_arrays)
         roles, n_swaps, n_calls = self._roles(), dh._swap_count, len(dh.call_queue)
+        import gc
         stream = torch.cuda.Stream(dh.device)
         stream.wait_stream(torch.cuda.current_stream(dh.device))
-        with torch.cuda.stream(stream):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                unit()
-                unit()
-        torch.cuda.current_stream(dh.device).wait_stream(stream)
-        periodic = self._roles() == roles
-        dh.gpu_arrays.clear()
-        dh.gpu_arrays.update(before)
-        dh._swap_count = n_swaps
-        del dh.call_queue[n_calls:]
+        g, periodic = None, False
+        # no cyclic garbage collection while the stream is capturing: a collected object that owns CUDA resources (an older
+        # graph, an event) would be destroyed in the middle of the capture and invalidate it (torch.cuda.graph collects
+        # once BEFORE it begins capturing for the same reason)
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.stream(stream):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    unit()
+                    unit()
+            periodic = self._roles() == roles
+            self.capture_error = None
+        except Exception as exc:         # a failed capture is not fatal: the loop issues its steps eagerly
+            chain = [exc] + ([exc.__context__] if exc.__context__ is not None else [])
+            self.capture_error = ' <- '.join('%s: %s' % (type(e).__name__, str(e).splitlines()[0] if str(e) else '') for e in chain)
+            g = None
+        finally:
+            if gc_was_on:
+                gc.enable()
+            torch.cuda.current_stream(dh.device).wait_stream(stream)
+            dh.gpu_arrays.clear()
+            dh.gpu_arrays.update(before)
+            dh._swap_count = n_swaps
+            del dh.call_queue[n_calls:]
         return g if periodic else None
 
     def run(self, time_steps=1):
