@@ -774,10 +774,10 @@ class SlabDataHandling:
         ``fuse=True``: pairs of steps run as one launch with one exchange of ``2 * halo`` ghost planes
         (``run_kernel(..., fused_steps=2)``): per pair the field is read and written once instead of twice and one
         message per neighbour replaces two.  Needs ``default_ghost_layers >= 2 * halo``.  Default (``fuse=None``): pairs
-        wherever they are a measured win and possible — 3-D fields of 4-byte elements (7-point fp32, 1024^3 per GPU:
+        wherever they are a measured win and possible — 3-D fields (7-point fp32, 1024^3 per GPU:
         1.63x at one GPU, 1.71x at two, profiles/r2_slab_steps_c3_n*.json) on a data handling that stores enough ghost
-        layers, 8-byte elements on one rank (27-point fp64 768^3: 1.08x, profiles/r2_slab_steps_c4_n1.json), 2-D 'zeros'
-        stencils on one rank without ghost planes; everything else runs single steps (``_pairs_pay_off``)."""
+        layers, 8-byte elements too (27-point fp64 768^3: 1.08x at one GPU, 1.07x at two, profiles/r2_slab_steps_c4_n*.json),
+        2-D 'zeros' stencils on one rank without ghost planes; everything else runs single steps (``_pairs_pay_off``)."""
         ir = kernel.ir
         if len(ir.input_fields) != 1 or len(ir.output_fields) != 1:
             raise ValueError('%s: run_steps needs a kernel with one input and one output field' % kernel.function_name)
@@ -795,14 +795,13 @@ class SlabDataHandling:
 
 
 def _pairs_pay_off(kernel, dec):
-    """Default of ``fuse=None``: fused pairs of steps where they were measured to win — 3-D fields of 4-byte elements on any
-    number of ranks when the slab stores the ``2 x reach`` ghost planes a pair needs (7-point fp32: 1.63x / 1.71x at one / two
-    GPUs), 8-byte elements on one rank (27-point fp64: 1.08x), 2-D 'zeros' stencils on one rank without ghost planes (1.4x)."""
+    """Default of ``fuse=None``: fused pairs of steps wherever they can run — every measured case wins: 3-D fields on any
+    number of ranks when the slab stores the ``2 x reach`` ghost planes a pair needs (7-point fp32 1024^3 per GPU: 1.63x /
+    1.71x at one / two GPUs; 27-point fp64 768^3: 1.08x / 1.07x, profiles/r2_slab_steps_c4_n*.json), 2-D 'zeros' stencils on
+    one rank without ghost planes (5-point fp32 8192^2: 1.4x)."""
     ir = kernel.ir
     if kernel.fused_steps_reason() is not None:
         return False
-    if any(f.dtype.itemsize != 4 for f in ir.all_fields) and dec.world_size > 1:
-        return False      # fp64 pairs: 1.08x on one rank (profiles/r2_slab_steps_c4_n1.json), not measured across ranks
     if ir.ndim != 3:      # 2-D pairs (5-point fp32 8192^2: 1.39x) run on whole arrays only: one rank, no ghost planes
         return ir.ndim == 2 and dec.world_size == 1 and dec.g == 0
     reach = max(ir.halo(ir.input_fields[0].name)[0])
