@@ -107,7 +107,7 @@ def slab_ranges(global_shape, start, n, g, has_lo, has_hi, boundary, margin, ndi
     if fused:
         if halo is None or halo < 0:
             raise ValueError('fused steps: the reach of the stencil along dim 0 (halo) is required')
-        if (has_lo or has_hi) and g < steps * halo:
+        if (has_lo or has_hi or periodic) and g < steps * halo:      # (one periodic rank is its own neighbour)
             raise ValueError('%d fused steps of a stencil reaching %d plane(s) need %d ghost planes, the slab stores %d'
                              % (steps, halo, steps * halo, g))
         if n < 2 * steps * halo and has_lo and has_hi:
@@ -784,7 +784,8 @@ class SlabDataHandling:
         if steps < 0:
             raise ValueError('steps must be >= 0')
         fin, fout = ir.input_fields[0].name, ir.output_fields[0].name
-        halo = [fin] if self.dec.world_size > 1 and self.dec.g > 0 and max(ir.halo(fin)[0]) > 0 else []
+        # ghost planes come from a neighbouring rank — or, on a periodic domain, possibly from this rank's own far side
+        halo = [fin] if (self.dec.world_size > 1 or self.dec.periodic) and self.dec.g > 0 and max(ir.halo(fin)[0]) > 0 else []
         if fuse is None:
             fuse = _pairs_pay_off(kernel, self.dec)
         launches = [2] * (steps // 2) + [1] * (steps % 2) if fuse else [1] * steps
@@ -805,7 +806,7 @@ def _pairs_pay_off(kernel, dec):
     if ir.ndim != 3:      # 2-D pairs (5-point fp32 8192^2: 1.39x) run on whole arrays only: one rank, no ghost planes
         return ir.ndim == 2 and dec.world_size == 1 and dec.g == 0
     reach = max(ir.halo(ir.input_fields[0].name)[0])
-    return dec.world_size == 1 or dec.g >= 2 * reach
+    return (dec.world_size == 1 and not dec.periodic) or dec.g >= 2 * reach
 
 
 class _SlabTensors:
@@ -1216,14 +1217,14 @@ class TimeLoop:
             ok = _pairs_pay_off(kernel, self.dh.dec)
         elif ok:
             reach = max(ir.halo(fin)[0])
-            ok = self.dh.dec.world_size == 1 or self.dh.dec.g >= 2 * reach
+            ok = (self.dh.dec.world_size == 1 and not self.dh.dec.periodic) or self.dh.dec.g >= 2 * reach
             why = 'a fused pair needs %d ghost layers along dim 0, the data handling stores %d' % (2 * reach, self.dh.dec.g)
         if not ok:
             if self.fuse_steps is True:
                 raise ValueError('TimeLoop(fuse_steps=True): %s' % why)
             return None
         dec = self.dh.dec
-        needs_halo = dec.world_size > 1 and dec.g > 0 and max(ir.halo(fin)[0]) > 0
+        needs_halo = (dec.world_size > 1 or dec.periodic) and dec.g > 0 and max(ir.halo(fin)[0]) > 0
         return kernel, dict(kw), ((fin,) if needs_halo else ())
 
     def _one_pair(self, fused):

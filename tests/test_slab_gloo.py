@@ -778,3 +778,64 @@ def test_timeloop_fused_pairs_are_refused_where_they_cannot_be_built():
     tl.add_single_step_function(lambda: dh2.swap('u', 'out'))          # an opaque function: the loop cannot know it swaps
     with pytest.raises(ValueError, match='add_call'):
         tl.fused_pair()
+
+
+def _periodic_steps_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    if world > 1:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import evaluate
+        from pystencils_autodiff_b200.configs import make_config
+        from pystencils_autodiff_b200.datahandling import SlabDataHandling
+        ReplayKernel, _ = _replay_kernel_class()
+        T = 5
+        gshape = (8 * world, 8, 132)
+        glob = np.random.default_rng(21).standard_normal(gshape).astype(np.float32)
+        ref = glob.astype(np.float64)
+        op_w = make_config('c3', shape=(gshape[0] + 2,) + gshape[1:], dtype='float64', boundary_handling='zeros')
+        for _ in range(T):       # periodic along dim 0, 'zeros' along the other axes
+            ref = evaluate(op_w.forward_assignments, {'u': np.concatenate([ref[-1:], ref, ref[:1]], 0)}, 'zeros')['out'][1:-1]
+        res = {}
+        for g, mode in ((1, 'steps'), (2, 'steps'), (2, 'loop')):
+            dh = SlabDataHandling(gshape, rank, world, g, device='cpu', backend='torch', periodic=True)
+            dh.add_arrays('u, out', dtype=np.float32)
+            kernel = ReplayKernel(make_config('c3', shape=dh.dec.local_shape, boundary_handling='zeros').forward_ast_gpu)
+            sl = slice(dh.dec.start, dh.dec.start + dh.dec.n_local)
+            dh.owned('u').copy_(torch.from_numpy(glob[sl]))
+            del ReplayKernel.launches[:]
+            if mode == 'steps':
+                dh.run_steps(kernel, T)              # default: pairs only where 2 x reach ghost planes are stored
+                if g == 1:
+                    with pytest.raises(ValueError, match='ghost planes'):
+                        dh.run_kernel(kernel, halo_fields=['u'], fused_steps=2)
+            else:
+                tl = dh.create_timeloop()
+                tl.add_call(kernel, {'halo_fields': ['u']})
+                tl.swap('u', 'out')
+                tl.run(T)
+                assert tl.fused_last_run
+            fused = sum('x2' in n for n in ReplayKernel.launches)
+            assert (fused > 0) == (g == 2), (g, mode, ReplayKernel.launches)
+            res['%d %s' % (g, mode)] = float(np.abs(dh.owned('u').numpy() - ref[sl]).max() / np.abs(ref).max())
+        q.put((rank, res))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [1, 2, 3])
+def test_periodic_time_loops_single_steps_and_fused_pairs(world):
+    """Time loops on a domain that is periodic along the decomposed axis (one rank: its own neighbour; two ranks: both
+    neighbours are the same peer): ``run_steps`` synchronises the ghost planes on ONE rank too, takes fused pairs only
+    where ``2 x reach`` ghost planes are stored (too few: single steps by default, an explicit request raises), and the
+    ``TimeLoop`` idiom does the same; all against the oracle on the wrapped global field."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_periodic_steps_worker, args=(r, world, 29840 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for rank, res in _collect(procs, q, world):
+        assert len(res) == 3 and all(v < 1e-6 for v in res.values()), (rank, res)
