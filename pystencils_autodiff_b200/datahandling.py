@@ -915,7 +915,7 @@ def create_slab_autograd_function(op, data_handling, op_name=None, tuning=None, 
         fwd = getattr(f, 'corresponding_forward_field', None)
         if fwd is not None:
             (grad_of if fwd in fwd_outputs else adjoint_of)[fwd.name] = f.name
-    sharded = dec.world_size > 1
+    sharded = dec.world_size > 1 or dec.periodic       # ghost planes are filled from a neighbour (possibly this rank)
 
     def reach(ir, name):
         return max(ir.halo(name)[0])
@@ -1007,7 +1007,7 @@ def create_slab_unrolled_function(op, data_handling, steps, fuse=None, op_name=N
     fwd_k, bwd_k = KC(fwd_ir, tuning), KC(bwd_ir, tuning)
     scalars = dict(scalars or {})
     _check_scalars((fwd_k, bwd_k), scalars)
-    sharded = dec.world_size > 1
+    sharded = dec.world_size > 1 or dec.periodic       # ghost planes are filled from a neighbour (possibly this rank)
     if fuse is None:
         fuse = _pairs_pay_off(fwd_k, dec) and _pairs_pay_off(bwd_k, dec)
     launches = [2] * (steps // 2) + [1] * (steps % 2) if fuse else [1] * steps

@@ -820,6 +820,27 @@ def _periodic_steps_worker(rank, world, port, q):
             fused = sum('x2' in n for n in ReplayKernel.launches)
             assert (fused > 0) == (g == 2), (g, mode, ReplayKernel.launches)
             res['%d %s' % (g, mode)] = float(np.abs(dh.owned('u').numpy() - ref[sl]).max() / np.abs(ref).max())
+        # autograd on the periodic slabs: two chained steps through the slab Function, loss = sum(out2 * r)
+        from pystencils_autodiff_b200.datahandling import create_slab_autograd_function
+        dh = SlabDataHandling(gshape, rank, world, 1, device='cpu', backend='torch', periodic=True)
+        sl = slice(dh.dec.start, dh.dec.start + dh.dec.n_local)
+        op_l = make_config('c3', shape=(dh.dec.n_local,) + gshape[1:], boundary_handling='zeros')
+        Step = create_slab_autograd_function(op_l, dh, kernel_class=ReplayKernel)
+        R = np.random.default_rng(22).standard_normal(gshape).astype(np.float32)
+        u = torch.from_numpy(glob[sl].copy()).requires_grad_(True)
+        (o1,) = Step.apply(u)
+        (o2,) = Step.apply(o1)
+        (o2 * torch.from_numpy(R[sl])).sum().backward()
+
+        def wrapped(assigns, key, src, a):
+            return evaluate(assigns, {src: np.concatenate([a[-1:], a, a[:1]], 0)}, 'zeros')[key][1:-1]
+        r2 = glob.astype(np.float64)
+        d = R.astype(np.float64)
+        for _ in range(2):
+            r2 = wrapped(op_w.forward_assignments, 'out', 'u', r2)
+            d = wrapped(op_w.backward_assignments, 'diffu', 'diffout', d)
+        res['autograd out'] = float(np.abs(o2.detach().numpy() - r2[sl]).max() / np.abs(r2).max())
+        res['autograd grad'] = float(np.abs(u.grad.numpy() - d[sl]).max() / np.abs(d).max())
         q.put((rank, res))
     finally:
         if world > 1:
@@ -831,11 +852,12 @@ def test_periodic_time_loops_single_steps_and_fused_pairs(world):
     """Time loops on a domain that is periodic along the decomposed axis (one rank: its own neighbour; two ranks: both
     neighbours are the same peer): ``run_steps`` synchronises the ghost planes on ONE rank too, takes fused pairs only
     where ``2 x reach`` ghost planes are stored (too few: single steps by default, an explicit request raises), and the
-    ``TimeLoop`` idiom does the same; all against the oracle on the wrapped global field."""
+    ``TimeLoop`` idiom does the same; the slab autograd Function (forward and adjoint chains) wraps around too; all against
+    the oracle on the wrapped global field."""
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     procs = [ctx.Process(target=_periodic_steps_worker, args=(r, world, 29840 + world, q)) for r in range(world)]
     for p in procs:
         p.start()
     for rank, res in _collect(procs, q, world):
-        assert len(res) == 3 and all(v < 1e-6 for v in res.values()), (rank, res)
+        assert len(res) == 5 and all(v < 1e-6 for v in res.values()), (rank, res)
