@@ -72,8 +72,9 @@ def _replay_gpu_tests_on_the_cpu():
     torch.Tensor.is_cuda = property(lambda self: True)      # shadows the C-level attribute for the dry run only
     real_init = datahandling.SlabDataHandling.__init__
 
-    def init_on_cpu(self, domain_size, rank=0, world_size=1, default_ghost_layers=1, device=None, backend='nccl', group=None):
-        real_init(self, domain_size, rank, world_size, default_ghost_layers, 'cpu', 'torch', group)
+    def init_on_cpu(self, domain_size, rank=0, world_size=1, default_ghost_layers=1, device=None, backend='nccl', group=None,
+                    periodic=False, peer_halo=False):
+        real_init(self, domain_size, rank, world_size, default_ghost_layers, 'cpu', 'torch', group, periodic=periodic)
     datahandling.SlabDataHandling.__init__ = init_on_cpu
     with fake_cuda.fake_cuda():
         try:

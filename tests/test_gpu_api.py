@@ -680,3 +680,18 @@ def test_timeloop_schedules_independent_calls_from_the_dependency_graph():
     tl2.add_call(fk, {})
     tl2.add_single_step_function(lambda: None)
     assert tl2.levels() is None
+
+
+@pytest.mark.no_launch          # the launches happen in the process this test starts
+@pytest.mark.parametrize('name,steps', [('c3', 5), ('c4', 4)])
+def test_periodic_time_loop_on_one_gpu(name, steps):
+    """One rank on a periodic domain is its own neighbour (two device copies per synchronisation): single steps and fused
+    pairs against a torch.roll restatement of the periodic stencil (``scripts/check_periodic.py`` as one process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'check_periodic.py'), name, str(steps)],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count('IDENTICAL') == 2 and 'DIFFERENT' not in out.stdout

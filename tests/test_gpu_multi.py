@@ -52,3 +52,24 @@ def test_peer_halos_equal_unsharded(name, bh, steps):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count('[rank') >= 3 * world and out.stdout.count('IDENTICAL') == out.stdout.count('[rank')
     assert 'DIFFERENT' not in out.stdout
+
+
+@pytest.mark.no_launch
+@pytest.mark.parametrize('name,steps', [('c3', 5), ('c4', 4)])
+def test_periodic_time_loops_wrap_around_between_gpus(name, steps):
+    """Periodic along the decomposed axis (graph_datahandling.py:305-316): the first and the last rank exchange planes — with
+    two ranks both neighbours are the same peer and the grouped ncclSend/ncclRecv must pair up in issue order.  Single
+    steps and fused pairs, bit for bit against the whole field run as ONE periodic rank, that one against a torch.roll
+    restatement (``scripts/check_periodic.py``)."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    world = 2 if n < 4 else 4
+    port = 29250 + (hash((name, 'periodic')) % 100)
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+                          '--master-addr', '127.0.0.1', '--master-port', str(port),
+                          os.path.join(ROOT, 'scripts', 'check_periodic.py'), name, str(steps)],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count('[rank') == 2 * world and out.stdout.count('IDENTICAL') == 2 * world
+    assert 'DIFFERENT' not in out.stdout
