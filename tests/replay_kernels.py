@@ -11,6 +11,12 @@ class ReplayKernel(CompiledKernel):
     launches = []
 
     def __call__(self, *, _range=None, _variant=None, _stream=None, **kwargs):
+        import fake_cuda
+        if fake_cuda.FakeGraph.capturing is not None:       # a capturing stream records the launch and executes nothing
+            graph, fake_cuda.FakeGraph.capturing = fake_cuda.FakeGraph.capturing, None
+            graph.ops.append(lambda kw=dict(kwargs): self(_range=_range, _variant=_variant, **kw))
+            fake_cuda.FakeGraph.capturing = graph
+            return None
         nd = self.ir.ndim
         tensors = [kwargs[f.name] for f in self.fields]
         scal = [float(kwargs[s_]) for s_ in self.scalars]

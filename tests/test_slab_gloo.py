@@ -861,3 +861,67 @@ def test_periodic_time_loops_single_steps_and_fused_pairs(world):
         p.start()
     for rank, res in _collect(procs, q, world):
         assert len(res) == 5 and all(v < 1e-6 for v in res.values()), (rank, res)
+
+
+@pytest.mark.parametrize('fuse_steps, counts', [(False, (5, 4, 6, 7)), (None, (9, 8, 10, 11))])
+def test_timeloop_cuda_graph_logic_with_recording_graphs(fuse_steps, counts):
+    """The CUDA-graph path of ``TimeLoop.run`` on the CPU: a recording stand-in for ``torch.cuda.CUDAGraph``
+    (tests/fake_cuda.py) captures the replayed launches with the tensors they were issued on — pointers baked in, like a
+    real graph — so stale-graph mistakes (odd tail steps, external swaps, a replaced array change the buffer
+    roles) show up as wrong values.  Same scenario as the GPU test ``test_timeloop_graph_follows_the_buffer_roles``, single
+    steps and fused pairs, bit for bit against the eager loop."""
+    from fake_cuda import FakeGraph, fake_cuda
+    from pystencils_autodiff_b200.configs import make_config
+    from pystencils_autodiff_b200.datahandling import SlabDataHandling
+    from replay_kernels import ReplayKernel
+    shape = (24, 136)
+    U0 = np.random.default_rng(5).normal(size=shape).astype(np.float32)
+    finals = []
+    with fake_cuda(graphs=True):
+        for use_graph in (True, False):
+            dh = SlabDataHandling(shape, 0, 1, 0, device='cpu', backend='torch')
+            dh.add_arrays('u, out', dtype=np.float32)
+            kern = ReplayKernel(make_config('c2', shape=shape).forward_ast_gpu)
+            dh.owned('u').copy_(torch.from_numpy(U0))
+            tl = dh.create_timeloop(use_cuda_graph=use_graph, fuse_steps=fuse_steps)
+            tl.add_call(kern, {})
+            tl.swap('u', 'out')
+            FakeGraph.replays = 0
+            tl.run(counts[0])
+            assert tl.fused_last_run == (fuse_steps is None)
+            tl.run(counts[1])                          # roles swapped relative to the first capture
+            dh.swap('u', 'out')
+            dh.swap('u', 'out')
+            tl.run(counts[2])
+            dh.gpu_arrays['u'] = dh.owned('u').clone()  # a replaced array: same values, new pointer
+            tl.run(counts[3])
+            assert tl.time_steps_run == sum(counts)
+            if use_graph:
+                assert len(tl._graphs) >= 2 and all(g is not None for g in tl._graphs.values()) and tl.capture_error is None
+                assert FakeGraph.replays >= 4           # every run() replayed at least once
+            else:
+                assert not tl._graphs and FakeGraph.replays == 0
+            finals.append(dh.owned('u').clone())
+        # a capture that fails is not fatal: the loop runs eagerly and says why
+        dh = SlabDataHandling(shape, 0, 1, 0, device='cpu', backend='torch')
+        dh.add_arrays('u, out', dtype=np.float32)
+        dh.owned('u').copy_(torch.from_numpy(U0))
+
+        class Failing(ReplayKernel):
+            def __call__(self, **kw):
+                if FakeGraph.capturing is not None:
+                    raise RuntimeError('launch refused during capture')
+                return ReplayKernel.__call__(self, **kw)
+        tl = dh.create_timeloop(fuse_steps=fuse_steps)
+        tl.add_call(Failing(make_config('c2', shape=shape).forward_ast_gpu), {})
+        tl.swap('u', 'out')
+        tl.run(counts[0])
+        assert 'launch refused during capture' in tl.capture_error and FakeGraph.capturing is None
+        eager = dh.owned('u').clone()
+        dh2 = SlabDataHandling(shape, 0, 1, 0, device='cpu', backend='torch')
+        dh2.add_arrays('u, out', dtype=np.float32)
+        dh2.owned('u').copy_(torch.from_numpy(U0))
+        dh2.run_steps(ReplayKernel(make_config('c2', shape=shape).forward_ast_gpu), counts[0], fuse=fuse_steps)
+        assert torch.equal(eager, dh2.owned('u'))
+    assert torch.equal(finals[0], finals[1])
+    assert not torch.ones(1).is_cuda                    # the stand-ins are gone
