@@ -27,6 +27,17 @@ def main():
                 k = CompiledKernel(make(shape=shape, boundary_handling=bh).forward_ast_gpu)
                 k.emitted('march_x2')
                 kernels.append(k)
+    from pystencils_autodiff_b200.configs import diffusion2d_op
+    # tests/test_gpu_api.py time loops (fused pairs through the TimeLoop API), scripts/check_periodic.py (one rank and slabs
+    # of two / four ranks, two ghost planes per side)
+    for make, shapes in ((heat3d_op, ((24, 30, 128), (20, 30, 128), (28, 40, 256), (52, 40, 256), (100, 40, 256))),
+                         (stencil27_op, ((20, 24, 128), (36, 24, 128), (68, 24, 128))),
+                         (diffusion2d_op, ((64, 128),))):
+        for shape in shapes:
+            k = CompiledKernel(make(shape=shape).forward_ast_gpu)
+            if k.fused_steps_reason() is None:
+                k.emitted('march_x2')
+            kernels.append(k)
     import pystencils_autodiff_b200 as ps
     from pystencils_autodiff_b200.configs import make_config
     from stencil_fuzz import random_stencil
