@@ -31,7 +31,14 @@ from pystencils_autodiff_b200 import assignment as A, field as F, transformation
 
 def install_shim():
     ps = types.ModuleType('pystencils')
-    ps.Field, ps.FieldType, ps.fields = F.Field, F.FieldType, F.fields
+    class ShimField(F.Field):
+        """pystencils' constructor derives the index dimensions from ``len(shape) - len(layout)`` (the reference's
+        AdjointField relies on it for vector fields); this front end sets them in its factory functions instead."""
+
+        def __init__(self, name, field_type, dtype, layout, shape, strides=None):
+            super().__init__(name, field_type, dtype, layout, shape, strides)
+            self._index_dimensions = len(self.shape) - len(self._layout)
+    ps.Field, ps.FieldType, ps.fields = ShimField, F.FieldType, F.fields
     ps.Assignment, ps.AssignmentCollection = A.Assignment, A.AssignmentCollection
     ps.x_vector = F.x_vector
     sub = {}
@@ -127,6 +134,33 @@ def cases():
     return c
 
 
+def symbolic_only_cases():
+    """Cases compared as printed assignments only (no numeric vectors): index-dimension outputs and symbolic shapes.
+    name -> (assignment factory, kwargs for AutoDiffOp)"""
+    c = {}
+
+    def curl():  # /root/reference/tests/test_tfmad.py:341-401 (get_curl + test_tfmad_two_outputs): scalar -> vector field
+        u = ours.Field.create_fixed_size('curl_input', (20, 30), index_dimensions=0)
+        cf = ours.Field.create_fixed_size('curl', (20, 30, 2), index_dimensions=1)
+        disc = ours.fd.Discretization2ndOrder(dx=1)
+        return ours.AssignmentCollection([ours.Assignment(cf.center(0), disc(ours.fd.Diff(u, 0))),
+                                          ours.Assignment(cf.center(1), disc(ours.fd.Diff(u, 1)))], [])
+    c['curl_vector_output'] = (curl, {'diff_mode': 'transposed-forward'})
+
+    def one_stencil():  # /root/reference/tests/test_tfmad.py:12-28, symbolic shapes
+        f, out = ours.fields('f, out: double[2D]')
+        cont = ours.fd.Diff(f, 0) - ours.fd.Diff(f, 1)
+        return ours.AssignmentCollection([ours.Assignment(out.center(), ours.fd.Discretization2ndOrder(dx=1)(cont))], [])
+    c['tfmad_stencil_2d_symbolic_shape'] = (one_stencil, {'diff_mode': 'transposed-forward'})
+
+    def two_stencils():  # /root/reference/tests/test_tfmad.py:31-53
+        a, b, out = ours.fields('a, b, out: double[2D]')
+        cont = ours.fd.Diff(a, 0) - ours.fd.Diff(a, 1) - ours.fd.Diff(b, 0) + ours.fd.Diff(b, 1)
+        return ours.AssignmentCollection([ours.Assignment(out.center(), ours.fd.Discretization2ndOrder(dx=1)(cont))], [])
+    c['tfmad_two_stencils_2d_symbolic_shape'] = (two_stencils, {'diff_mode': 'transposed-forward'})
+    return c
+
+
 RANDOM_SEEDS = (0, 4, 5, 8, 13, 21, 24, 31)
 
 
@@ -197,6 +231,22 @@ def main():
                 num[tag + 'out/' + k] = v
             for k, v in grads.items():
                 num[tag + 'grad/' + k] = v
+    for name, (factory, kw) in symbolic_only_cases().items():
+        ref_op = ad.AutoDiffOp(factory(), **kw)
+        entry = {
+            'forward': str(ref_op.forward_assignments),
+            'backward': str(ref_op.backward_assignments),
+            'forward_input_fields': [f.name for f in ref_op.forward_input_fields],
+            'forward_output_fields': [f.name for f in ref_op.forward_output_fields],
+            'backward_input_fields': sorted(f.name for f in ref_op.backward_input_fields),
+            'backward_output_fields': sorted(f.name for f in ref_op.backward_output_fields),
+            'symbolic_only': True,
+        }
+        try:
+            entry['backward_zeros'] = str(tr.add_fixed_constant_boundary_handling(ref_op.backward_assignments))
+        except Exception as exc:          # symbolic shapes: recorded, the consumer expects the same failure
+            entry['backward_zeros_error'] = type(exc).__name__
+        sym[name] = entry
     with open(os.path.join(HERE, 'reference_symbolic.json'), 'w') as fh:
         json.dump(sym, fh, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, 'reference_numeric.npz'), **num)

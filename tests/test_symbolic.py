@@ -149,8 +149,11 @@ def test_field_description_parser_and_access_names():
 def _golden_cases():
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
-    from make_reference_golden import cases, resolve_kwargs
-    return cases(), resolve_kwargs
+    from make_reference_golden import cases, resolve_kwargs, symbolic_only_cases
+    every = dict(cases())
+    # printed-form-only cases (index-dimension output, symbolic shapes): no numeric vectors, never seen by the GPU tests
+    every.update({k: (factory, kw, None) for k, (factory, kw) in symbolic_only_cases().items()})
+    return every, resolve_kwargs
 
 
 with open(GOLDEN) as _fh:
@@ -174,7 +177,15 @@ def test_matches_reference_symbolic_output(name):
     assert [f.name for f in op.forward_output_fields] == g['forward_output_fields']
     assert sorted(f.name for f in op.backward_input_fields) == g['backward_input_fields']
     assert sorted(f.name for f in op.backward_output_fields) == g['backward_output_fields']
-    assert canon(str(ps.add_fixed_constant_boundary_handling(op.backward_assignments))) == canon(g['backward_zeros'])
+    zeros = str(ps.add_fixed_constant_boundary_handling(op.backward_assignments))
+    if g.get('symbolic_only'):
+        # symbolic shapes: the transform takes the shape symbols of an ARBITRARY accessed field (transformations.py:20, set
+        # iteration) — all fields of a kernel share one shape at run time, so the comparison ignores whose symbols they are
+        import re
+        strip = lambda text: re.sub(r'_size_[A-Za-z]+_(\d)', r'_size_\1', text)
+        assert strip(zeros) == strip(g['backward_zeros'])
+    else:
+        assert canon(zeros) == canon(g['backward_zeros'])
 
 
 def test_fused_forward_adjoint_collection():
