@@ -792,7 +792,7 @@ def _periodic_steps_worker(rank, world, port, q):
         from pystencils_autodiff_b200.datahandling import SlabDataHandling
         ReplayKernel, _ = _replay_kernel_class()
         T = 5
-        gshape = (8 * world, 8, 132)
+        gshape = (6 * world, 6, 68)
         glob = np.random.default_rng(21).standard_normal(gshape).astype(np.float32)
         ref = glob.astype(np.float64)
         op_w = make_config('c3', shape=(gshape[0] + 2,) + gshape[1:], dtype='float64', boundary_handling='zeros')
@@ -847,7 +847,7 @@ def _periodic_steps_worker(rank, world, port, q):
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [1, 2, 3])
+@pytest.mark.parametrize('world', [1, 2])       # (three ranks: test_periodic_synchronisation_wraps_around)
 def test_periodic_time_loops_single_steps_and_fused_pairs(world):
     """Time loops on a domain that is periodic along the decomposed axis (one rank: its own neighbour; two ranks: both
     neighbours are the same peer): ``run_steps`` synchronises the ghost planes on ONE rank too, takes fused pairs only
