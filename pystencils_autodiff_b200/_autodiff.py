@@ -430,6 +430,24 @@ class AutoDiffOp:
         from .backends._torch_native import compile_kernel
         return compile_kernel(self.backward_ast_gpu)
 
+    def _create_kernel(self, assignments, suffix, args, kwargs):
+        """Reference :592-598: ``ps.create_kernel(assignments, *args, **kwargs).compile()`` on the RAW assignments (no
+        boundary transform; ``ghost_layers`` / ``data_type`` as given, the interior inferred from the offsets otherwise).
+        pystencils' ``target`` defaults to 'cpu', which this backend does not have: pass ``target='gpu'``."""
+        from .backends._torch_native import compile_kernel
+        kwargs = dict(kwargs)
+        target = kwargs.pop('target', args[0] if args else 'cpu')
+        if str(getattr(target, 'name', target)).lower() != 'gpu':
+            self._no_cpu()
+        kw = {k: v for k, v in kwargs.items() if k in ('ghost_layers', 'data_type', 'fast_math')}
+        return compile_kernel(lower_assignments(assignments, None, self.op_name + suffix, **kw))
+
+    def create_forward_kernel(self, *args, **kwargs):
+        return self._create_kernel(self._forward_assignments, '_forward_custom_gpu', args, kwargs)
+
+    def create_backward_kernel(self, *args, **kwargs):
+        return self._create_kernel(self._backward_assignments, '_backward_custom_gpu', args, kwargs)
+
     def get_forward_kernel(self, is_gpu):
         return self.forward_kernel_gpu if is_gpu else self.forward_kernel_cpu
 

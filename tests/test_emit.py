@@ -147,3 +147,23 @@ def test_linear_plan_shares_partial_sums():
         ref = float(expr.subs({s: vals[str(s)] for s in U.values()}))
         assert abs(got - ref) < 1e-12
     assert plan_linear([(0, U[0, 0] * U[0, 1])], set(U.values())) is None      # not linear -> no plan
+
+
+def test_create_forward_and_backward_kernel_like_the_reference():
+    """``AutoDiffOp.create_forward_kernel`` / ``create_backward_kernel`` (reference _autodiff.py:592-598:
+    ``ps.create_kernel(assignments, *args, **kwargs).compile()`` on the raw assignments): GPU kernels with the given
+    ``ghost_layers`` — no boundary transform even when the op has one — and pystencils' default target 'cpu' raises."""
+    import pytest
+    from pystencils_autodiff_b200.backends._torch_native import CompiledKernel
+    from pystencils_autodiff_b200.configs import make_config
+    op = make_config('c2', shape=(16, 32), boundary_handling='zeros')
+    fk = op.create_forward_kernel(target='gpu')
+    assert isinstance(fk, CompiledKernel) and fk.ir.boundary == 'none' and fk.ir.ghost_layers == 1
+    assert [f.name for f in fk.ir.input_fields] == ['u'] and [f.name for f in fk.ir.output_fields] == ['out']
+    bk = op.create_backward_kernel('gpu', ghost_layers=2)
+    assert bk.ir.ghost_layers == 2 and [f.name for f in bk.ir.input_fields] == ['diffout']
+    assert op.forward_ast_gpu.boundary == 'zeros'            # the op's own kernels are untouched
+    with pytest.raises(NotImplementedError, match='no CPU'):
+        op.create_forward_kernel()
+    with pytest.raises(NotImplementedError, match='no CPU'):
+        op.create_backward_kernel(target='cpu')
