@@ -33,6 +33,7 @@ __all__ = ['SlabDecomposition', 'HaloExchanger', 'SlabDataHandling', 'GraphDataH
            'SlabStencilOp', 'HostStreamedOp', 'TimeLoop']
 
 
+import enum as _enum
 import os as _os
 _PEER_NEVER_WAIT = bool(_os.environ.get('PSAD_PEER_NEVER_WAIT'))    # timing experiments only: results are then unordered
 _ALWAYS_ORDER_SIDE_LAUNCHES = bool(_os.environ.get('PSAD_ALWAYS_ORDER_SIDE'))     # diagnostic switch (scripts/r2_ab_multi.sh)
@@ -411,6 +412,71 @@ def peer_halos_pay_off(local_shape, world_size, backend='nccl', device=None):
     return cells <= PEER_HALO_MAX_CELLS
 
 
+class DataTransferKind(str, _enum.Enum):
+    """Kinds of recorded data movement (graph_datahandling.py:21-38).  The queue entries of this data handling carry the
+    member NAMES as strings (``('DataTransfer', name, 'HOST_TO_DEVICE')``): ``DataTransferKind(entry[2])`` gives the member."""
+    UNKNOWN = 'UNKNOWN'
+    HOST_ALLOC = 'HOST_ALLOC'
+    DEVICE_ALLOC = 'DEVICE_ALLOC'
+    HOST_TO_DEVICE = 'HOST_TO_DEVICE'
+    DEVICE_TO_HOST = 'DEVICE_TO_HOST'
+    HOST_COMMUNICATION = 'HOST_COMMUNICATION'
+    DEVICE_COMMUNICATION = 'DEVICE_COMMUNICATION'
+    HOST_SWAP = 'HOST_SWAP'
+    DEVICE_SWAP = 'DEVICE_SWAP'
+    HOST_GATHER = 'HOST_GATHER'
+    DEVICE_GATHER = 'DEVICE_GATHER'
+
+    def is_alloc(self):
+        return self in (DataTransferKind.HOST_ALLOC, DataTransferKind.DEVICE_ALLOC)
+
+    def is_transfer(self):
+        # (the reference's version names a member that does not exist — ``self.SWAP`` — and raises; both swaps count here)
+        return self in (DataTransferKind.HOST_TO_DEVICE, DataTransferKind.DEVICE_TO_HOST, DataTransferKind.HOST_SWAP,
+                        DataTransferKind.DEVICE_SWAP)
+
+
+class TorchArrayHandler:
+    """``PyTorchDataHandling.PyTorchArrayHandler`` (framework_integration/datahandling.py:137-174): the array factory /
+    transfer helper pystencils' serial data handling delegates to, on torch tensors.  Host arrays come from the factory
+    methods, ``to_gpu`` / ``upload`` put them on the data handling's device."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.device = device
+        self.from_numpy = torch.from_numpy
+
+    def zeros(self, shape, dtype=np.float32, order='C'):
+        assert order == 'C'
+        return self.torch.zeros(*shape, dtype=numpy_dtype_to_torch(dtype))
+
+    def ones(self, shape, dtype=np.float32, order='C'):
+        assert order == 'C'
+        return self.torch.ones(*shape, dtype=numpy_dtype_to_torch(dtype))
+
+    def empty(self, shape, dtype=np.float32, layout=None):
+        if layout not in (None, 'numpy', 'c', 'C') and tuple(layout) != tuple(range(len(shape))):
+            raise NotImplementedError("only the 'numpy' (C order) layout is supported")
+        return self.torch.empty(*shape, dtype=numpy_dtype_to_torch(dtype))
+
+    def randn(self, shape, dtype=np.float32):
+        return self.torch.randn(tuple(shape), dtype=numpy_dtype_to_torch(dtype))
+
+    def _on_device(self, array):
+        t = array if hasattr(array, 'cuda') else self.torch.from_numpy(array)
+        return t.to(self.device) if self.device is not None else t.cuda()
+
+    def to_gpu(self, array):
+        return self._on_device(array)
+
+    def upload(self, gpuarray, numpy_array):
+        gpuarray[...] = self._on_device(numpy_array)
+
+    def download(self, gpuarray, numpy_array):
+        numpy_array[...] = gpuarray.cpu() if hasattr(numpy_array, 'cuda') else gpuarray.cpu().numpy()
+
+
 class SlabDataHandling:
     """Array registry with the reference's data-handling vocabulary (``add_array``, ``fields``, ``run_kernel``,
     ``synchronization_function``, ``swap``, ``fill``, ``gather_array``; graph_datahandling.py:202-327,
@@ -431,6 +497,8 @@ class SlabDataHandling:
         self.exchanger = HaloExchanger(self.dec, backend, group)
         self.gpu_arrays = OrderedDict()
         self.cpu_arrays = OrderedDict()
+        self.custom_data_cpu, self.custom_data_gpu, self._custom_data_transfer_functions = {}, {}, {}
+        self.array_handler = TorchArrayHandler(self.device)
         self.fields = OrderedDict()
         self.call_queue = []
         self.kernel_io = {}            # kernel name -> (read field names, written field names) of the kernels run here
@@ -500,6 +568,23 @@ class SlabDataHandling:
             return tuple(self.add_array(n, values_per_cell=idx or 1, dtype=dt, spatial_shape=shape) for n, idx in infos)
         return tuple(self.add_array(n.strip(), dtype=dtype, spatial_shape=spatial_shape) for n in description.split(','))
 
+    def add_custom_data(self, name, cpu_creation_function, gpu_creation_function=None, cpu_to_gpu_transfer_func=None,
+                        gpu_to_cpu_transfer_func=None):
+        """Data that is not a field array (graph_datahandling.py:272-277 records a marker and defers to pystencils' serial
+        data handling): the creation functions are called once, their results kept under ``custom_data_cpu[name]`` /
+        ``custom_data_gpu[name]``; with both transfer functions ``to_gpu(name)`` / ``to_cpu(name)`` call
+        ``cpu_to_gpu_transfer_func(gpu_data, cpu_data)`` / ``gpu_to_cpu_transfer_func(gpu_data, cpu_data)``."""
+        if (cpu_to_gpu_transfer_func is None) != (gpu_to_cpu_transfer_func is None):
+            raise ValueError('For GPU data, both transfer functions have to be specified')
+        if name in self.custom_data_cpu or name in self.gpu_arrays:
+            raise ValueError('Data with this name has already been added')
+        self._record(('CustomData', name))
+        self.custom_data_cpu[name] = cpu_creation_function()
+        if gpu_creation_function is not None:
+            self.custom_data_gpu[name] = gpu_creation_function()
+            if cpu_to_gpu_transfer_func is not None:
+                self._custom_data_transfer_functions[name] = (cpu_to_gpu_transfer_func, gpu_to_cpu_transfer_func)
+
     def add_array_like(self, name, name_of_template_field):
         t = self.gpu_arrays[name_of_template_field]
         return self.add_array(name, dtype=np.dtype(str(t.dtype).replace('torch.', '')))
@@ -568,11 +653,17 @@ class SlabDataHandling:
 
     # -- host mirrors (reference: GraphDataHandling.to_cpu / to_gpu record a DataTransfer, graph_datahandling.py:255-282)
     def to_cpu(self, name):
+        if name in self._custom_data_transfer_functions:
+            self._record(('CustomTransfer', name, 'DEVICE_TO_HOST'))       # graph_datahandling.py:279-282
+            return self._custom_data_transfer_functions[name][1](self.custom_data_gpu[name], self.custom_data_cpu[name])
         self._record(('DataTransfer', name, 'DEVICE_TO_HOST'))
         self.cpu_arrays[name] = self.gpu_arrays[name].detach().to('cpu', copy=True)
         return self.cpu_arrays[name]
 
     def to_gpu(self, name):
+        if name in self._custom_data_transfer_functions:
+            self._record(('CustomTransfer', name, 'HOST_TO_DEVICE'))
+            return self._custom_data_transfer_functions[name][0](self.custom_data_gpu[name], self.custom_data_cpu[name])
         self._record(('DataTransfer', name, 'HOST_TO_DEVICE'))
         if name not in self.cpu_arrays:
             raise KeyError('no host copy of %r: call to_cpu(%r) first or fill cpu_arrays[%r]' % (name, name, name))

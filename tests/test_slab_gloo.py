@@ -925,3 +925,47 @@ def test_timeloop_cuda_graph_logic_with_recording_graphs(fuse_steps, counts):
         assert torch.equal(eager, dh2.owned('u'))
     assert torch.equal(finals[0], finals[1])
     assert not torch.ones(1).is_cuda                    # the stand-ins are gone
+
+
+def test_array_handler_custom_data_and_transfer_kinds():
+    """The rest of the reference's data-handling vocabulary: ``array_handler`` (PyTorchArrayHandler,
+    framework_integration/datahandling.py:137-174), ``add_custom_data`` with custom transfer functions
+    (graph_datahandling.py:272-290) and ``DataTransferKind`` (:21-38)."""
+    from pystencils_autodiff_b200.datahandling import DataTransferKind, GraphDataHandling
+    dh = GraphDataHandling((6, 8), default_ghost_layers=0, device='cpu')
+    h = dh.array_handler
+    z, o, e, r = h.zeros((2, 3)), h.ones((2, 3), np.float64), h.empty((4,), np.float32), h.randn((3, 2))
+    assert z.dtype == torch.float32 and float(z.abs().sum()) == 0 and o.dtype == torch.float64 and float(o.sum()) == 6
+    assert e.shape == (4,) and r.shape == (3, 2) and r.dtype == torch.float32
+    dev = h.to_gpu(np.arange(6, dtype=np.float32).reshape(2, 3))
+    assert isinstance(dev, torch.Tensor) and dev.device == dh.device
+    h.upload(z, np.full((2, 3), 2.0, dtype=np.float32))
+    back = np.zeros((2, 3), dtype=np.float32)
+    h.download(z, back)
+    assert np.all(back == 2.0)
+    with pytest.raises(NotImplementedError):
+        h.empty((2, 3), layout='fzyx')
+    # custom data with transfer functions: the data handling calls them and records markers
+    log = []
+    dh.add_custom_data('particles', lambda: {'host': [1, 2, 3]}, lambda: {'device': []},
+                       lambda gpu, cpu: (gpu.__setitem__('device', list(cpu['host'])), log.append('up')),
+                       lambda gpu, cpu: (cpu.__setitem__('host', list(gpu['device'])), log.append('down')))
+    dh.to_gpu('particles')
+    dh.custom_data_gpu['particles']['device'].append(4)
+    dh.to_cpu('particles')
+    assert dh.custom_data_cpu['particles']['host'] == [1, 2, 3, 4] and log == ['up', 'down']
+    assert [c[0] for c in dh.call_queue] == ['CustomData', 'CustomTransfer', 'CustomTransfer']
+    with pytest.raises(ValueError, match='both transfer functions'):
+        dh.add_custom_data('half', dict, dict, cpu_to_gpu_transfer_func=lambda g, c: None)
+    with pytest.raises(ValueError, match='already been added'):
+        dh.add_custom_data('particles', dict)
+    # plain arrays keep their recorded transfers, named after the enum's members
+    dh.add_arrays('u')
+    dh.to_cpu('u')
+    dh.to_gpu('u')
+    kinds = [DataTransferKind(c[2]) for c in dh.call_queue if c[0] == 'DataTransfer']
+    assert kinds == [DataTransferKind.DEVICE_TO_HOST, DataTransferKind.HOST_TO_DEVICE]
+    assert all(k.is_transfer() and not k.is_alloc() for k in kinds) and DataTransferKind.DEVICE_ALLOC.is_alloc()
+    assert DataTransferKind.DEVICE_SWAP.is_transfer() and not DataTransferKind.HOST_GATHER.is_transfer()
+    from pystencils_autodiff_b200.computationgraph import ComputationGraph
+    assert len(ComputationGraph(dh).computation_nodes) == 2          # the custom-data markers carry no array dependencies
